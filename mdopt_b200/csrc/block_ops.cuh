@@ -1,0 +1,414 @@
+// Block-cooperative FP64 building blocks for the MPS-MPO decode path (sm_100a).
+//
+// One CTA owns one matrix / one syndrome.  All routines are written as sequences of "parallel-for"
+// phases separated by CTA barriers, with every reduction going through shared memory in a fixed order.
+// That keeps the arithmetic order independent of the thread count, and lets the *same source* be
+// compiled by g++ with -DMDOPT_EMU (MD_PAR_FOR becomes a plain loop) so the index logic can be unit
+// tested on a CPU-only box.  The emulation build is test infrastructure (tests/emu); the product library
+// is built by nvcc only and has no host compute path.
+//
+// Matrix convention: row-major, leading dimension LD = 2*CHI+1 doubles (odd, so that column walks do not
+// hit a single shared-memory bank).  "X" is the 2*CHI x 2*CHI work matrix, "P2" a CHI x 2*CHI page.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef MDOPT_EMU
+#define MD_DEV inline
+#define MD_SYNC() ((void)0)
+#define MD_PAR_FOR(i, n) for (int i = 0; i < (n); ++i)
+#define MD_LEADER if (true)
+#else
+#define MD_DEV __device__ __forceinline__
+#define MD_SYNC() __syncthreads()
+#define MD_PAR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
+#define MD_LEADER if (threadIdx.x == 0)
+#endif
+
+namespace mdopt {
+
+constexpr int NCH = 8;            // row chunks used by every column-wise partial reduction
+constexpr double EPS = 2.220446049250313e-16;
+constexpr double TOL3Z = 1.4901161193847656e-08;  // sqrt(eps), LAPACK dlaqp2's norm-recompute trigger
+
+// Work counters a CTA accumulates (leader thread only); reported per launch for the roofline.
+struct Counters {
+  double flops_qr;      // Householder QRCP + forming Q
+  double flops_jacobi;  // one-sided Jacobi rotations + dot products
+  double flops_apply;   // site-apply / theta-build contractions and U^T X products
+  double bytes_hbm;     // global-memory bytes moved by the CTA (site tensors + carried-matrix scratch)
+  double n_steps;       // two-site steps (sweep + move)
+  double n_trunc;       // steps that needed the truncating SVD
+  double n_jacobi_sweeps;
+  double pad;
+};
+
+template <int CHI>
+struct Smem {
+  static constexpr int LD = 2 * CHI + 1;
+  static constexpr int N2 = 2 * CHI;
+  double X[N2 * LD];   // work matrix (up to 2CHI x 2CHI)
+  double P2[CHI * LD];  // coefficient page (up to CHI x 2CHI)
+  double part[NCH * N2 * 3];
+  double vn1[N2], vn2[N2], tau[N2], sig[N2], wv[N2];
+  double rot[N2 * 2];
+  double W[16];         // current MPO site tensor (vL, vR, pU, pD), vL,vR <= 2
+  double dscr[16];
+  int perm[N2], order[N2], flag[N2];
+  int iscr[16];
+};
+
+// -------------------------------------------------------------------------------------------------
+// Householder QR with column pivoting, in place (LAPACK dlaqp2 data flow).
+//   X (R x C) -> R factor in the upper trapezoid, reflector tails below the diagonal, tau[], perm[].
+//   Stops at step j when the largest remaining column norm is <= rel_tol * (largest initial column norm)
+//   or when j == kmax.  s.iscr[0] = number of reflectors K, s.iscr[1] = 1 if it stopped at kmax with a
+//   residual above the threshold (i.e. a genuine truncation is required).
+// -------------------------------------------------------------------------------------------------
+template <int CHI>
+MD_DEV void qrcp(Smem<CHI>& s, int R, int C, int kmax, double rel_tol, Counters& cnt) {
+  constexpr int LD = Smem<CHI>::LD;
+  constexpr int N2 = Smem<CHI>::N2;
+  double* X = s.X;
+  const int rows_per = (R + NCH - 1) / NCH;
+  MD_PAR_FOR(t, NCH * C) {
+    int ch = t / C, c = t - ch * C;
+    int i0 = ch * rows_per, i1 = min(R, i0 + rows_per);
+    double acc = 0.0;
+    for (int i = i0; i < i1; ++i) { double v = X[i * LD + c]; acc += v * v; }
+    s.part[ch * N2 + c] = acc;
+  }
+  MD_SYNC();
+  MD_PAR_FOR(c, C) {
+    double acc = 0.0;
+    for (int ch = 0; ch < NCH; ++ch) acc += s.part[ch * N2 + c];
+    acc = sqrt(acc);
+    s.vn1[c] = acc; s.vn2[c] = acc; s.perm[c] = c;
+  }
+  MD_SYNC();
+  MD_LEADER {
+    double mx = 0.0;
+    for (int c = 0; c < C; ++c) mx = fmax(mx, s.vn1[c]);
+    s.dscr[0] = mx * rel_tol;  // absolute stop threshold
+    s.iscr[0] = 0; s.iscr[1] = 0;
+    cnt.flops_qr += 2.0 * R * C;
+  }
+  MD_SYNC();
+  const double thresh = s.dscr[0];
+  const int jmax = min(R, C);
+  int K = 0;
+  for (int j = 0; j < jmax; ++j) {
+    // ---- pivot search over trailing columns (two-level argmax through shared memory) ----
+    MD_PAR_FOR(g, 32) {
+      int span = (C - j + 31) / 32;
+      int c0 = j + g * span, c1 = min(C, c0 + span);
+      double best = -1.0; int bi = -1;
+      for (int c = c0; c < c1; ++c) if (s.vn1[c] > best) { best = s.vn1[c]; bi = c; }
+      s.part[g] = best; s.flag[g] = bi;
+    }
+    MD_SYNC();
+    MD_LEADER {
+      double best = -1.0; int bi = j;
+      for (int g = 0; g < 32; ++g) if (s.part[g] > best) { best = s.part[g]; bi = s.flag[g]; }
+      int stop = 0;
+      if (!(best > thresh)) stop = 1;               // numerically rank deficient: done
+      else if (j >= kmax) { stop = 1; s.iscr[1] = 1; }  // more weight than kmax columns can hold
+      s.iscr[2] = stop; s.iscr[3] = bi;
+    }
+    MD_SYNC();
+    if (s.iscr[2]) break;
+    const int pv = s.iscr[3];
+    if (pv != j) {
+      MD_PAR_FOR(i, R) { double a = X[i * LD + j]; X[i * LD + j] = X[i * LD + pv]; X[i * LD + pv] = a; }
+      MD_LEADER {
+        int tp = s.perm[j]; s.perm[j] = s.perm[pv]; s.perm[pv] = tp;
+        s.vn1[pv] = s.vn1[j]; s.vn2[pv] = s.vn2[j];
+      }
+    }
+    MD_SYNC();
+    // ---- Householder vector from X[j:R, j] ----
+    MD_PAR_FOR(ch, NCH) {
+      int len = R - (j + 1);
+      int per = (len + NCH - 1) / NCH;
+      int i0 = j + 1 + ch * per, i1 = min(R, i0 + per);
+      double acc = 0.0;
+      for (int i = i0; i < i1; ++i) { double v = X[i * LD + j]; acc += v * v; }
+      s.part[ch] = acc;
+    }
+    MD_SYNC();
+    MD_LEADER {
+      double ss = 0.0;
+      for (int ch = 0; ch < NCH; ++ch) ss += s.part[ch];
+      double alpha = X[j * LD + j];
+      double xnorm = sqrt(ss);
+      double tau = 0.0, scal = 0.0, beta = alpha;
+      if (xnorm != 0.0) {
+        beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+        tau = (beta - alpha) / beta;
+        scal = 1.0 / (alpha - beta);
+      }
+      s.tau[j] = tau; s.dscr[1] = scal;
+      X[j * LD + j] = beta;
+      cnt.flops_qr += 4.0 * (R - j) * (C - j - 1) + 3.0 * (R - j);
+    }
+    MD_SYNC();
+    const double tau = s.tau[j];
+    const double scal = s.dscr[1];
+    MD_PAR_FOR(i, R - j - 1) { X[(j + 1 + i) * LD + j] *= scal; }
+    MD_SYNC();
+    const int nt = C - j - 1;  // trailing columns
+    if (nt > 0 && tau != 0.0) {
+      const int len = R - j;
+      const int per = (len + NCH - 1) / NCH;
+      MD_PAR_FOR(t, NCH * nt) {
+        int ch = t / nt, c = j + 1 + (t - ch * nt);
+        int i0 = j + ch * per, i1 = min(R, i0 + per);
+        double acc = 0.0;
+        for (int i = i0; i < i1; ++i) {
+          double v = (i == j) ? 1.0 : X[i * LD + j];
+          acc += v * X[i * LD + c];
+        }
+        s.part[ch * N2 + c] = acc;
+      }
+      MD_SYNC();
+      MD_PAR_FOR(t, nt) {
+        int c = j + 1 + t;
+        double acc = 0.0;
+        for (int ch = 0; ch < NCH; ++ch) acc += s.part[ch * N2 + c];
+        s.wv[c] = tau * acc;
+      }
+      MD_SYNC();
+      MD_PAR_FOR(t, len * nt) {
+        int ii = t / nt, c = j + 1 + (t - ii * nt);
+        int i = j + ii;
+        double v = (i == j) ? 1.0 : X[i * LD + j];
+        X[i * LD + c] -= v * s.wv[c];
+      }
+      MD_SYNC();
+    }
+    // ---- column-norm downdate with LAPACK's cancellation safeguard ----
+    MD_PAR_FOR(t, nt) {
+      int c = j + 1 + t;
+      int redo = 0;
+      if (s.vn1[c] != 0.0) {
+        double temp = fabs(X[j * LD + c]) / s.vn1[c];
+        temp = fmax(0.0, (1.0 + temp) * (1.0 - temp));
+        double r = s.vn1[c] / s.vn2[c];
+        double temp2 = temp * r * r;
+        if (temp2 <= TOL3Z) redo = 1;
+        else s.vn1[c] *= sqrt(temp);
+      }
+      s.flag[c] = redo;
+    }
+    MD_SYNC();
+    MD_PAR_FOR(t, nt) {
+      int c = j + 1 + t;
+      if (s.flag[c]) {
+        double acc = 0.0;
+        for (int i = j + 1; i < R; ++i) { double v = X[i * LD + c]; acc += v * v; }
+        acc = sqrt(acc);
+        s.vn1[c] = acc; s.vn2[c] = acc;
+      }
+    }
+    MD_SYNC();
+    K = j + 1;
+  }
+  MD_LEADER { s.iscr[0] = K; }
+  MD_SYNC();
+}
+
+// Coefficients of the original columns in the new basis: P2[k, perm[c]] = R[k, c] (K x C, ld LD).
+template <int CHI>
+MD_DEV void extract_coeff(Smem<CHI>& s, int K, int C) {
+  constexpr int LD = Smem<CHI>::LD;
+  MD_PAR_FOR(t, K * C) {
+    int k = t / C, c = t - k * C;
+    s.P2[k * LD + s.perm[c]] = (c >= k) ? s.X[k * LD + c] : 0.0;
+  }
+  MD_SYNC();
+}
+
+// Form the first K columns of Q in place over the reflectors (LAPACK dorg2r data flow).
+template <int CHI>
+MD_DEV void form_q(Smem<CHI>& s, int R, int K, Counters& cnt) {
+  constexpr int LD = Smem<CHI>::LD;
+  constexpr int N2 = Smem<CHI>::N2;
+  double* X = s.X;
+  for (int j = K - 1; j >= 0; --j) {
+    const double tau = s.tau[j];
+    const int nt = K - 1 - j;
+    const int len = R - j;
+    if (nt > 0 && tau != 0.0) {
+      const int per = (len + NCH - 1) / NCH;
+      MD_PAR_FOR(t, NCH * nt) {
+        int ch = t / nt, c = j + 1 + (t - ch * nt);
+        int i0 = j + ch * per, i1 = min(R, i0 + per);
+        double acc = 0.0;
+        for (int i = i0; i < i1; ++i) {
+          double v = (i == j) ? 1.0 : X[i * LD + j];
+          acc += v * X[i * LD + c];
+        }
+        s.part[ch * N2 + c] = acc;
+      }
+      MD_SYNC();
+      MD_PAR_FOR(t, nt) {
+        int c = j + 1 + t;
+        double acc = 0.0;
+        for (int ch = 0; ch < NCH; ++ch) acc += s.part[ch * N2 + c];
+        s.wv[c] = tau * acc;
+      }
+      MD_SYNC();
+      MD_PAR_FOR(t, len * nt) {
+        int ii = t / nt, c = j + 1 + (t - ii * nt);
+        int i = j + ii;
+        double v = (i == j) ? 1.0 : X[i * LD + j];
+        X[i * LD + c] -= v * s.wv[c];
+      }
+      MD_SYNC();
+    }
+    MD_PAR_FOR(i, R) {
+      double v;
+      if (i < j) v = 0.0;
+      else if (i == j) v = 1.0 - tau;
+      else v = -tau * X[i * LD + j];
+      X[i * LD + j] = v;
+    }
+    MD_LEADER { cnt.flops_qr += 4.0 * len * nt + 2.0 * len; }
+    MD_SYNC();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// One-sided (Hestenes) Jacobi on the columns of X (R x C), in place: X <- X J = U diag(sigma).
+//   Round-robin pair schedule, partial dot products through shared memory, rotation applied by all
+//   threads.  On exit: s.sig[c] = ||X[:,c]||, s.order[] = columns sorted by sigma descending (ties by
+//   index).  Returns the number of sweeps in s.iscr[4]; s.iscr[5] = 1 when it did not converge.
+// -------------------------------------------------------------------------------------------------
+template <int CHI>
+MD_DEV void jacobi_columns(Smem<CHI>& s, int R, int C, Counters& cnt, int max_sweeps = 60) {
+  constexpr int LD = Smem<CHI>::LD;
+  constexpr int N2 = Smem<CHI>::N2;
+  double* X = s.X;
+  const int n = (C + 1) & ~1;     // even number of players (last one may be a phantom)
+  const int npair = n / 2;
+  const double tol = EPS * sqrt((double)R);
+  const int per = (R + NCH - 1) / NCH;
+  int sweeps = 0;
+  int converged = (C < 2);
+  while (!converged && sweeps < max_sweeps) {
+    MD_LEADER { s.iscr[6] = 0; }
+    MD_SYNC();
+    for (int rnd = 0; rnd < n - 1; ++rnd) {
+      // pair k of this round: circle method with player n-1 fixed
+      MD_PAR_FOR(t, npair * NCH) {
+        int k = t / NCH, ch = t - k * NCH;
+        int a, b;
+        if (k == 0) { a = n - 1; b = rnd; }
+        else { a = (rnd + k) % (n - 1); b = (rnd - k + (n - 1)) % (n - 1); }
+        double saa = 0.0, sbb = 0.0, sab = 0.0;
+        if (a < C && b < C) {
+          int i0 = ch * per, i1 = min(R, i0 + per);
+          for (int i = i0; i < i1; ++i) {
+            double xa = X[i * LD + a], xb = X[i * LD + b];
+            saa += xa * xa; sbb += xb * xb; sab += xa * xb;
+          }
+        }
+        double* p = s.part + (k * NCH + ch) * 3;
+        p[0] = saa; p[1] = sbb; p[2] = sab;
+      }
+      MD_SYNC();
+      MD_PAR_FOR(k, npair) {
+        double saa = 0.0, sbb = 0.0, sab = 0.0;
+        for (int ch = 0; ch < NCH; ++ch) {
+          const double* p = s.part + (k * NCH + ch) * 3;
+          saa += p[0]; sbb += p[1]; sab += p[2];
+        }
+        double c = 1.0, sn = 0.0;
+        int did = 0;
+        if (sab != 0.0 && fabs(sab) > tol * sqrt(saa) * sqrt(sbb)) {
+          double zeta = (sbb - saa) / (2.0 * sab);
+          double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          c = 1.0 / sqrt(1.0 + t * t);
+          sn = c * t;
+          did = 1;
+        }
+        s.rot[2 * k] = c; s.rot[2 * k + 1] = sn;
+        s.flag[k] = did;
+      }
+      MD_SYNC();
+      MD_PAR_FOR(t, npair * R) {
+        int k = t / R, i = t - k * R;
+        if (s.flag[k]) {
+          int a, b;
+          if (k == 0) { a = n - 1; b = rnd; }
+          else { a = (rnd + k) % (n - 1); b = (rnd - k + (n - 1)) % (n - 1); }
+          double c = s.rot[2 * k], sn = s.rot[2 * k + 1];
+          double xa = X[i * LD + a], xb = X[i * LD + b];
+          X[i * LD + a] = c * xa - sn * xb;
+          X[i * LD + b] = sn * xa + c * xb;
+        }
+      }
+      MD_LEADER {
+        int nrot = 0;
+        for (int k = 0; k < npair; ++k) nrot += s.flag[k];
+        s.iscr[6] += nrot;
+        cnt.flops_jacobi += 6.0 * R * npair + 6.0 * R * nrot;
+      }
+      MD_SYNC();
+    }
+    ++sweeps;
+    converged = (s.iscr[6] == 0);
+    MD_SYNC();
+  }
+  // singular values = column norms; order by value (descending), ties by column index
+  MD_PAR_FOR(t, NCH * C) {
+    int ch = t / C, c = t - ch * C;
+    int i0 = ch * per, i1 = min(R, i0 + per);
+    double acc = 0.0;
+    for (int i = i0; i < i1; ++i) { double v = X[i * LD + c]; acc += v * v; }
+    s.part[ch * N2 + c] = acc;
+  }
+  MD_SYNC();
+  MD_PAR_FOR(c, C) {
+    double acc = 0.0;
+    for (int ch = 0; ch < NCH; ++ch) acc += s.part[ch * N2 + c];
+    s.sig[c] = sqrt(acc);
+  }
+  MD_SYNC();
+  MD_PAR_FOR(c, C) {
+    double v = s.sig[c];
+    int pos = 0;
+    for (int o = 0; o < C; ++o) {
+      double w = s.sig[o];
+      pos += (w > v) || (w == v && o < c);
+    }
+    s.order[pos] = c;
+  }
+  MD_LEADER {
+    s.iscr[4] = sweeps; s.iscr[5] = converged ? 0 : 1;
+    cnt.n_jacobi_sweeps += sweeps;
+    cnt.flops_jacobi += 2.0 * R * C;
+  }
+  MD_SYNC();
+}
+
+// Reference truncation rule (mdopt/utils/utils.py:119): keep min(chi_max, #(sigma > cut)) values.
+// Requires s.sig / s.order from jacobi_columns.  Result in s.iscr[0]; s.dscr[2] = truncation error
+// sum_{i>=k} sigma_i^2, s.dscr[3] = ||sigma_kept||_2.
+template <int CHI>
+MD_DEV void truncation_rule(Smem<CHI>& s, int C, int chi_lim, double cut) {
+  MD_LEADER {
+    int k = 0;
+    for (int i = 0; i < C; ++i) k += (s.sig[s.order[i]] > cut);
+    if (k > chi_lim) k = chi_lim;
+    double err = 0.0, kept = 0.0;
+    for (int i = 0; i < C; ++i) {
+      double v = s.sig[s.order[i]];
+      if (i >= k) err += v * v; else kept += v * v;
+    }
+    s.iscr[0] = k; s.dscr[2] = err; s.dscr[3] = sqrt(kept);
+  }
+  MD_SYNC();
+}
+
+}  // namespace mdopt

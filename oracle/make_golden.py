@@ -1,0 +1,125 @@
+"""Generate tests/golden/*.json by running the UNMODIFIED reference (imported from /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    PYTHONPATH=oracle/refshim:/root/reference python oracle/make_golden.py
+
+Third-party modules the reference imports but this image lacks are replaced by the stand-ins in
+oracle/refshim (opt_einsum -> numpy.einsum with the reference's explicit path; matrex.msro -> the
+(first site, last site) row sort; qecstruct -> duck-typed CSS code objects).  Every fixture stores the
+inputs (error strings, kwargs), the reference outputs, and for one case the singular values of every
+sweep split, so tests can pin oracle/mps_oracle.py against the reference without re-importing it.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+import qecstruct as qec  # noqa: E402  (refshim)
+import mdopt.utils.utils as ref_utils  # noqa: E402
+from examples.decoding.decoding import decode_css  # noqa: E402
+from mdopt.optimiser import utils as ref_opt  # noqa: E402
+from mdopt.mps.canonical import CanonicalMPS  # noqa: E402
+
+import mps_oracle as O  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def surface(L):
+    return qec.hypergraph_product(qec.repetition_code(L), qec.repetition_code(L))
+
+
+def run_batch(name, L, errors, **kw):
+    code = surface(L)
+    t0 = time.time()
+    rows = []
+    for e in errors:
+        dist, ok = decode_css(code, e, silent=True, contraction_strategy="Optimised", **kw)
+        rows.append({"error": e, "dist": [float(x) for x in dist], "success": int(ok)})
+    doc = {"name": name, "lattice_size": L, "kwargs": kw, "results": rows,
+           "reference_seconds": round(time.time() - t0, 2)}
+    with open(os.path.join(OUT, name + ".json"), "w") as fh:
+        json.dump(doc, fh, indent=0)
+    print(name, len(rows), "decodes", doc["reference_seconds"], "s")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    # config 1: README minimal example (README.md:38-61)
+    run_batch("readme_3x3", 3, ["IIXIIIIIIIIII"], chi_max=64, bias_type="Bitflip", bias_prob=0.01,
+              tolerance=1e-12)
+    # character-gating quirk cases
+    run_batch("gating_3x3", 3, ["IIYIIIIIIIIII", "IIXIIIIIIIIII", "IIXIIZIIIIIII", "YIXIIIIIIIIII",
+                                "IIIIZIIIIIIII", "XXXXXXXXXXXXX", "ZIIIIIIIIIIIX"],
+              chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, tolerance=1e-12)
+    n3, n5 = 13, 41
+    run_batch("d3_chi64_bitflip", 3, O.seeded_errors(n3, 0.05, 96, 123, "Bitflip"),
+              chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, tolerance=1e-12)
+    run_batch("d3_chi64_bitflip_cut0", 3, O.seeded_errors(n3, 0.10, 48, 100, "Bitflip"),
+              chi_max=64, cut=0.0, bias_type="Bitflip", bias_prob=0.1, tolerance=0.0)
+    run_batch("d3_chi64_depol", 3, O.seeded_errors(n3, 0.08, 48, 11, "Depolarising"),
+              chi_max=64, cut=1e-17, bias_type="Depolarising", bias_prob=0.1, tolerance=1e-12)
+    run_batch("d3_chi8_bitflip", 3, O.seeded_errors(n3, 0.08, 48, 7, "Bitflip"),
+              chi_max=8, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, tolerance=1e-12)
+    run_batch("d5_chi64_bitflip", 5, O.seeded_errors(n5, 0.05, 24, 123, "Bitflip"),
+              chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, tolerance=1e-12)
+    run_batch("d5_chi16_bitflip", 5, O.seeded_errors(n5, 0.05, 12, 5, "Bitflip"),
+              chi_max=16, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, tolerance=1e-12)
+
+    # exact MPO tensor tables (reference values: mdopt/optimiser/utils.py:23-43)
+    tables = {k: getattr(ref_opt, k).tolist() for k in
+              ["IDENTITY", "COPY_LEFT", "XOR_BULK", "XOR_LEFT", "XOR_RIGHT", "SWAP"]}
+    with open(os.path.join(OUT, "mpo_tensors.json"), "w") as fh:
+        json.dump(tables, fh)
+
+    # reference svd / split on seeded matrices (singular values + truncation counts)
+    rng = np.random.default_rng(2024)
+    cases = []
+    for (m, n, chi, cut) in [(8, 8, 4, 1e-12), (16, 32, 8, 1e-3), (32, 16, 100, 0.5), (64, 64, 64, 1e-17),
+                             (128, 128, 64, 1e-17), (20, 128, 16, 1e-12)]:
+        a = rng.standard_normal((m, n))
+        u, s, vh, err = ref_utils.svd(a, cut=cut, chi_max=chi, renormalise=False, return_truncation_error=True)
+        cases.append({"m": m, "n": n, "chi_max": chi, "cut": cut,
+                      "s": [float(x) for x in s], "trunc_err": float(err)})
+    with open(os.path.join(OUT, "svd_cases.json"), "w") as fh:
+        json.dump({"rng_seed": 2024, "note": "matrices are rng.standard_normal((m,n)) drawn in this order from default_rng(2024)", "cases": cases}, fh)
+
+    # marginal hand case (tests/mps/test_canonical.py:851-865 style): small random MPS, reference marginal
+    tens = [rng.standard_normal((1, 2, 3)), rng.standard_normal((3, 2, 4)), rng.standard_normal((4, 2, 2)),
+            rng.standard_normal((2, 2, 1))]
+    mps = CanonicalMPS([t.copy() for t in tens])
+    out = mps.marginal([1, 3], renormalise=True)
+    with open(os.path.join(OUT, "marginal_case.json"), "w") as fh:
+        json.dump({"tensors": [t.tolist() for t in tens], "sites": [1, 3],
+                   "result": [t.tolist() for t in out.tensors]}, fh)
+
+    # sweep spectra of one d=3 decode from the reference itself (hook on split_two_site_tensor's svd)
+    spectra = []
+    orig = ref_utils.svd
+
+    def spy(mat, cut=1e-12, chi_max=int(1e4), renormalise=False, return_truncation_error=False):
+        res = orig(mat, cut=cut, chi_max=chi_max, renormalise=renormalise,
+                   return_truncation_error=return_truncation_error)
+        spectra.append({"shape": list(mat.shape), "chi_max": int(chi_max), "s": [float(x) for x in res[1]]})
+        return res
+
+    ref_utils.svd = spy
+    try:
+        err = "IXIIIIIXIIIII"
+        dist, ok = decode_css(surface(3), err, silent=True, contraction_strategy="Optimised", chi_max=64,
+                              cut=1e-17, bias_type="Bitflip", bias_prob=0.1, tolerance=1e-12)
+    finally:
+        ref_utils.svd = orig
+    with open(os.path.join(OUT, "d3_spectra.json"), "w") as fh:
+        json.dump({"error": err, "dist": [float(x) for x in dist], "success": int(ok), "svds": spectra}, fh)
+    print("done")
+
+
+if __name__ == "__main__":
+    main()

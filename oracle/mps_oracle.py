@@ -1,0 +1,607 @@
+"""CPU oracle for the mdopt decode hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a plain-numpy restatement of the reference algorithm (quicophy/mdopt v1.1.1) for the one
+path this repo accelerates: ``decode_css`` -> ``apply_constraints`` -> ``mps_mpo_contract`` ->
+``split_two_site_tensor``/``svd`` -> ``marginal`` -> tolerant arg-max.  It exists to *check* the CUDA
+path; nothing under ``mdopt_b200/`` imports it, and only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may call it.
+
+Parity pinning: ``oracle/make_golden.py`` runs the unmodified reference (imported from
+``/root/reference`` with the stand-ins in ``oracle/refshim``) and this restatement on the same inputs
+and stores the reference outputs in ``tests/golden/``; ``tests/test_oracle.py`` re-checks this file
+against those fixtures and against the reference's notebook known answers.
+
+State representation: an MPS is a python list of float64 arrays ``(vL, p, vR)`` plus an integer
+``orth_centre`` (or ``None``), exactly the two things the reference's ``CanonicalMPS`` carries
+(``mdopt/mps/canonical.py:87-101``).  Every function cites the reference lines it follows.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg
+
+# --------------------------------------------------------------------------------------------------
+# MPO site tensors, legs (vL, vR, pU, pD).  Reference: mdopt/optimiser/utils.py:23-43.
+# --------------------------------------------------------------------------------------------------
+
+
+def _tensor(shape, rule):
+    out = np.zeros(shape)
+    for idx in np.ndindex(*shape):
+        out[idx] = float(rule(*idx))
+    return out
+
+
+IDENTITY = _tensor((1, 1, 2, 2), lambda a, b, u, d: u == d)
+COPY_LEFT = _tensor((1, 2, 2, 2), lambda a, b, u, d: b == d)
+XOR_BULK = _tensor((2, 2, 2, 2), lambda a, b, u, d: (b == (a ^ u)) and (u == d))
+XOR_LEFT = _tensor((1, 2, 2, 2), lambda a, b, u, d: (b == u) and (u == d))
+XOR_RIGHT = _tensor((2, 1, 2, 2), lambda a, b, u, d: (a == u) and (u == d))
+SWAP = _tensor((2, 2, 2, 2), lambda a, b, u, d: (a == b) and (u == d))
+
+# --------------------------------------------------------------------------------------------------
+# svd / split.  Reference: mdopt/utils/utils.py:29-138 and :290-383.
+# --------------------------------------------------------------------------------------------------
+
+SVD_HOOK = None  # tests may inject ``f(mat) -> (u, s, vh)`` the way the reference's xp.linalg.svd hook allows
+
+
+def svd(mat, cut=1e-12, chi_max=int(1e4), renormalise=False):
+    """Truncated SVD: keep ``min(chi_max, #(s > cut))`` values; returns (u, s, vh, truncation_error).
+
+    Driver order follows utils.py:77-111 (numpy gesdd, scipy gesdd, scipy gesvd, jittered gesvd).
+    """
+    mat = np.asarray(mat)
+    if mat.ndim != 2:
+        raise ValueError(f"A valid matrix must have 2 dimensions while the one given has {mat.ndim}.")
+    if SVD_HOOK is not None:
+        u, s, vh = SVD_HOOK(mat)
+    else:
+        err = None
+        for attempt in range(4):
+            try:
+                if attempt == 0:
+                    u, s, vh = np.linalg.svd(mat, full_matrices=False)
+                elif attempt == 1:
+                    u, s, vh = scipy.linalg.svd(mat, full_matrices=False, lapack_driver="gesdd")
+                elif attempt == 2:
+                    u, s, vh = scipy.linalg.svd(mat, full_matrices=False, lapack_driver="gesvd")
+                else:
+                    u, s, vh = scipy.linalg.svd(
+                        mat + 1e-12 * np.eye(*mat.shape), full_matrices=False, lapack_driver="gesvd"
+                    )
+                break
+            except Exception as exc:  # noqa: BLE001 - the reference swallows every driver failure
+                err = exc
+        else:
+            raise RuntimeError(f"All SVD methods failed. Last error: {err}")
+    s = np.asarray(s, dtype=float)
+    keep = min(int(chi_max), int(np.count_nonzero(s > cut)))  # utils.py:119
+    trunc_err = float(np.sum(s[keep:] ** 2))  # utils.py:120-121
+    u, s, vh = u[:, :keep], s[:keep], vh[:keep, :]
+    if renormalise and s.size:
+        nrm = float(np.linalg.norm(s))
+        if nrm > 0:
+            s = s / nrm  # utils.py:126-129
+    return u, s, vh, trunc_err
+
+
+def split_two_site_tensor(theta, chi_max=int(1e4), cut=1e-12, renormalise=False):
+    """(i,j,k,l) -> U(i,j,m), s(m), V(m,k,l), err.  Reference: utils.py:339-365 (svd strategy)."""
+    theta = np.asarray(theta)
+    if theta.ndim != 4:
+        raise ValueError(f"A valid two-site tensor must have 4 legs while the one given has {theta.ndim}.")
+    i, j, k, l = theta.shape
+    u, s, vh, err = svd(theta.reshape(i * j, k * l), cut=cut, chi_max=chi_max, renormalise=renormalise)
+    return u.reshape(i, j, s.size), s, vh.reshape(s.size, k, l), err
+
+
+# --------------------------------------------------------------------------------------------------
+# MPS helpers.  Reference: mdopt/mps/canonical.py.
+# --------------------------------------------------------------------------------------------------
+
+
+class MPS:
+    """Minimal carrier mirroring CanonicalMPS' data members (canonical.py:87-101)."""
+
+    def __init__(self, tensors, orth_centre=None, tolerance=1e-12, chi_max=int(1e4)):
+        self.tensors = list(tensors)
+        self.orth_centre = orth_centre
+        self.tolerance = tolerance
+        self.chi_max = chi_max
+
+    def __len__(self):
+        return len(self.tensors)
+
+    @property
+    def bond_dimensions(self):
+        return [t.shape[-1] for t in self.tensors[:-1]]
+
+    def copy(self):  # canonical.py:142-148
+        return MPS([t.copy() for t in self.tensors], self.orth_centre, self.tolerance, self.chi_max)
+
+    def reverse(self):  # canonical.py:150-161 (orth_centre 0 is falsy there and becomes None)
+        rev = [np.transpose(t) for t in reversed(self.tensors)]
+        oc = (len(self) - 1 - self.orth_centre) if self.orth_centre else None
+        return MPS(rev, oc, self.tolerance, self.chi_max)
+
+    def dense(self, flatten=True, renormalise=False, norm=2):  # canonical.py:241-272
+        out = self.tensors[0]
+        for t in self.tensors[1:]:
+            out = np.tensordot(out, t, (-1, 0))
+        out = out.squeeze()
+        if flatten:
+            out = out.flatten()
+        if renormalise:
+            n = float(np.linalg.norm(out, ord=norm))
+            if n > 1e-17:
+                out = out / n
+        return out
+
+
+def product_state(symbols):
+    """'0','1','+' -> (1,2,1) tensors, orth_centre None.  Reference: mdopt/mps/utils.py:439-512.
+
+    The reference routes through ExplicitMPS.right_canonical(); with unit singular values on every bond
+    that is the identity on the tensors (probed: tensors come out unchanged).
+    """
+    table = {"0": (1.0, 0.0), "1": (0.0, 1.0), "+": (1 / np.sqrt(2), 1 / np.sqrt(2))}
+    tensors = []
+    for ch in symbols:
+        if ch not in table:
+            raise ValueError(f"The string argument accepts only 0, 1 or + as elements, given {ch}.")
+        tensors.append(np.array(table[ch], dtype=float).reshape(1, 2, 1))
+    return MPS(tensors, None)
+
+
+def _is_identity(mat, tol):
+    return bool(np.isclose(np.linalg.norm(mat - np.eye(mat.shape[0])), 0, atol=tol))
+
+
+def find_orth_centre_for_constraints(mps, tol=1e-12):
+    """Orth-centre bootstrap used on the first MPO only.  Reference: mdopt/mps/utils.py:38-124 combined
+    with the convention block of mdopt/optimiser/utils.py:299-322."""
+    n = len(mps)
+    left, right, centres = [], [], []
+    for i, t in enumerate(mps.tensors):
+        fl = _is_identity(np.einsum("ijk,ijl->kl", t, t), tol)
+        fr = _is_identity(np.einsum("ijk,ljk->il", t, t), tol)
+        left.append(fl)
+        right.append(fr)
+        if not fl and not fr:
+            centres.append(i)
+    neg = [not f for f in left]
+    if left in ([True] + [False] * (n - 1), [False] * n) and right == neg:
+        centres.append(0)
+    if left in ([True] * (n - 1) + [False], [True] * n) and right == neg:
+        centres.append(n - 1)
+    if all(left) and all(right):
+        centres.append(0)
+    oc = None
+    if centres and len(centres) == 1:
+        oc = centres[0]
+    if all(left) and all(right):
+        oc = 0
+    elif left == [True] + [False] * (n - 1):
+        if right == neg:
+            oc = n - 1
+    elif left == [True] * (n - 1) + [False]:
+        if right == neg:
+            oc = 0
+    elif all(right):
+        oc = 0
+    elif all(left):
+        oc = n - 1
+    if len(centres) > 1:
+        oc = centres[0]
+    return oc
+
+
+def move_orth_centre(mps, final_pos, renormalise=False):
+    """Two-site SVD per bond with chi_max=mps.chi_max and the *default* cut 1e-12.
+    Reference: canonical.py:345-420."""
+    n = len(mps)
+    if final_pos not in range(n):
+        raise ValueError(f"The final position of the orthogonality centre should be from 0 to {n-1}, given {final_pos}.")
+    if mps.orth_centre is None:
+        raise ValueError("The orthogonality centre value is set to None.")
+    start = mps.orth_centre
+    if start == final_pos:
+        return mps
+    if start < final_pos:
+        work, begin, final = mps.copy(), start, final_pos
+    else:
+        work = mps.reverse()
+        begin, final = work.orth_centre if work.orth_centre is not None else 0, n - 1 - final_pos
+    for i in range(begin, final):
+        theta = np.tensordot(work.tensors[i], work.tensors[i + 1], (2, 0))
+        u, s, v, _ = split_two_site_tensor(theta, chi_max=mps.chi_max, renormalise=renormalise)
+        work.tensors[i] = u
+        work.tensors[i + 1] = v * s[:, None, None]
+        work.orth_centre = i + 1
+    if start > final_pos:
+        work = work.reverse()
+    return work
+
+
+def mps_mpo_contract(mps, mpo, start_site=0, renormalise=False, chi_max=int(1e4), cut=1e-17, record=None):
+    """Left-to-right zip-up of an MPO into an MPS.  Reference: mdopt/contractor/contractor.py:177-378.
+
+    ``record`` (optional list) receives the singular values of every split, for spectrum-level parity.
+    """
+    mps = mps.copy()
+    if mps.orth_centre != start_site:
+        mps = move_orth_centre(mps, start_site, renormalise=False)
+    for i, w in enumerate(mpo):
+        if np.ndim(w) != 4:
+            raise ValueError(f"A valid MPO tensor must have 4 legs while tensor {i} has {np.ndim(w)}.")
+    if start_site + len(mpo) > len(mps):
+        raise ValueError(
+            "The length of the MPO should correspond to the number of sites where it is applied, "
+            f"given MPO of length {len(mpo)} and the starting site {start_site}, while the MPS has length {len(mps)}."
+        )
+    t = mps.tensors
+    c = start_site
+    # contractor.py:276-291: theta(i, p, r, q*m); same pairwise order as the reference so that rounding
+    # (which decides the basis inside degenerate singular-value multiplets) is reproduced too.
+    theta = np.einsum("ijk,klm,nojp,oqlr->iprqm", t[c], t[c + 1], mpo[0], mpo[1],
+                      optimize=["einsum_path", (0, 1), (1, 2), (0, 1)])
+    theta = theta.reshape(theta.shape[0], theta.shape[1], theta.shape[2], -1)
+    for i in range(len(mpo) - 2):  # contractor.py:294-342
+        u, s, b, _ = split_two_site_tensor(theta, chi_max=chi_max, cut=cut, renormalise=renormalise)
+        if record is not None:
+            record.append(s.copy())
+        t[c] = u
+        c += 1
+        carried = (b * s[:, None, None]).reshape(s.size, mpo[i + 1].shape[3], mpo[i + 1].shape[1], t[c + 1].shape[0])
+        theta = np.einsum("ijkl,lmn,komp->ijpon", carried, t[c + 1], mpo[i + 2],
+                          optimize=["einsum_path", (0, 1), (0, 1)])
+        theta = theta.reshape(theta.shape[0], theta.shape[1], theta.shape[2], -1)
+    u, s, b, _ = split_two_site_tensor(theta, chi_max=chi_max, cut=cut, renormalise=renormalise)  # :345-360
+    if record is not None:
+        record.append(s.copy())
+    t[c] = u
+    t[c + 1] = b * s[:, None, None]
+    mps.orth_centre = c + 1
+    if renormalise:  # contractor.py:363-369 normalises tensors[c] (the left isometry), quirk kept
+        nrm = np.linalg.norm(t[c])
+        if nrm != 0:
+            t[c] = t[c] / nrm
+    return mps
+
+
+def marginal(mps, sites, renormalise=False):
+    """Trace sites out with (1,..,1)/sqrt(d), absorbing right (left for the last site).  MUTATES ``mps``.
+    Reference: canonical.py:906-991."""
+    if not sites:
+        return mps
+    if set(sites) - set(range(len(mps))):
+        raise ValueError("The list of sites to marginalise must be a subset of the list of all sites.")
+    t = mps.tensors
+    for site in sorted(sites, reverse=True):
+        d = t[site].shape[1]
+        traced = np.tensordot(t[site], np.ones(d) / np.sqrt(d), axes=([1], [0]))
+        if site < len(t) - 1:
+            merged = np.tensordot(traced, t[site + 1], axes=([1], [0]))
+            del t[site + 1]
+            del t[site]
+            t.insert(site, merged)
+        elif site > 0:
+            t[site - 1] = np.tensordot(t[site - 1], traced, axes=([-1], [0]))
+            del t[site]
+        else:
+            t[site] = traced.reshape(traced.shape + (1,))
+        mps.orth_centre = len(t) - 1
+        if renormalise:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                t[mps.orth_centre] = t[mps.orth_centre] / np.linalg.norm(t[mps.orth_centre])
+    return mps
+
+
+# --------------------------------------------------------------------------------------------------
+# Constraint strings and their application.  Reference: mdopt/optimiser/utils.py:141-359.
+# --------------------------------------------------------------------------------------------------
+
+
+def constraint_mpo(tensors, sites):
+    """ConstraintString(...).mpo(): lay ``tensors[g]`` on every site of group g across the span.
+    Reference: optimiser/utils.py:164-213."""
+    if not tensors:
+        raise ValueError("Empty list of constraints passed.")
+    if not sites:
+        raise ValueError("Empty list of sites passed.")
+    if len(sites) != len(tensors):
+        raise ValueError(
+            f"We have {len(tensors)} constraint(s) in the constraints list, "
+            f"but {len(sites)} constraint(s) assumed by the sites list."
+        )
+    flat = [s for group in sites for s in group]
+    if len(set(flat)) != len(flat):
+        raise ValueError("Non-unique sites encountered in the list.")
+    lo, hi = min(flat), max(flat)
+    if sorted(flat) != list(range(lo, hi + 1)):
+        raise ValueError("The string should not have breaks in it.")
+    mpo = [None] * (hi - lo + 1)
+    for g, group in enumerate(sites):
+        for s in group:
+            mpo[s - lo] = np.asarray(tensors[g])
+    return lo, mpo
+
+
+def default_order(strings, num_sites):
+    """Stand-in for matrex.msro (absent; parity on the order itself is unpinned): rows sorted by
+    (first site, last site).  Same rule as oracle/refshim/matrex and mdopt_b200.ordering.msro."""
+    keys = []
+    for r, groups in enumerate(strings):
+        flat = [s for g in groups for s in g]
+        keys.append((min(flat), max(flat), r))
+    return [k[2] for k in sorted(keys)]
+
+
+def apply_constraints(mps, strings, tensors, chi_max=int(1e4), cut=1e-17, renormalise=True,
+                      strategy="Naive", order=None, record=None):
+    """Reference: optimiser/utils.py:216-359 (dense / entropy branches omitted: not on the decode path)."""
+    if strategy == "Optimised":
+        perm = default_order(strings, len(mps)) if order is None else list(order)
+        strings = [strings[i] for i in perm]
+    for groups in strings:
+        start, mpo = constraint_mpo(tensors, groups)
+        if mps.orth_centre is None:
+            mps.orth_centre = find_orth_centre_for_constraints(mps)
+            mps = move_orth_centre(mps, start, renormalise=False)
+        mps = mps_mpo_contract(mps, mpo, start, renormalise=False, chi_max=chi_max, cut=cut, record=record)
+        if renormalise:
+            c = int(mps.orth_centre)
+            nrm = np.linalg.norm(mps.tensors[c])
+            if nrm > 0:
+                mps.tensors[c] = mps.tensors[c] / nrm
+    return mps
+
+
+# --------------------------------------------------------------------------------------------------
+# Decoder.  Reference: examples/decoding/decoding.py.
+# --------------------------------------------------------------------------------------------------
+
+_PAULI_BITS = {"I": "00", "X": "10", "Z": "01", "Y": "11", "E": "++"}  # decoding.py:283-320
+
+
+def pauli_to_mps(pauli):
+    out = []
+    for ch in pauli:
+        if ch not in _PAULI_BITS:
+            raise ValueError(f"Invalid Pauli encountered -- {ch}.")
+        out.append(_PAULI_BITS[ch])
+    return "".join(out)
+
+
+def bitflip_bias(p):  # decoding.py:49-89
+    if not 0 <= p <= 1:
+        raise ValueError(f"The channel parameter `prob_bias` should be a probability, given {p}.")
+    op = np.full((2, 2), np.sqrt(p))
+    np.fill_diagonal(op, np.sqrt(1 - p))
+    return op
+
+
+def depolarising_bias(p):  # decoding.py:92-137 (np.fill_diagonal on a 4-d array hits [i,i,i,i] only)
+    if not 0 <= p <= 1:
+        raise ValueError(f"The channel parameter `prob_bias` should be a probability, given {p}.")
+    op = np.full((2, 2, 2, 2), np.sqrt(p / 3))
+    np.fill_diagonal(op, np.sqrt(1 - p))
+    return op
+
+
+def apply_bitflip_bias(mps, sites, p):  # decoding.py:140-190 + contractor.py:16-63
+    op = bitflip_bias(p)
+    for s in sites:
+        mps.tensors[s] = np.einsum("ijk,jl->ilk", mps.tensors[s], op, optimize=["einsum_path", (0, 1)])
+    return mps
+
+
+def check_orth_centre(mps, tol=1e-12):
+    """CanonicalMPS.check_orth_centre (canonical.py:316-343) for the cases the decode path reaches."""
+    n = len(mps)
+    left, right, centres = [], [], []
+    for i, t in enumerate(mps.tensors):
+        fl = _is_identity(np.einsum("ijk,ijl->kl", t, t), tol)
+        fr = _is_identity(np.einsum("ijk,ljk->il", t, t), tol)
+        left.append(fl)
+        right.append(fr)
+        if not fl and not fr:
+            centres.append(i)
+    neg = [not f for f in left]
+    if left in ([True] + [False] * (n - 1), [False] * n) and right == neg:
+        return 0
+    if left in ([True] * (n - 1) + [False], [True] * n) and right == neg:
+        return n - 1
+    if all(left) and all(right):
+        return 0
+    raise ValueError(f"ambiguous orthogonality centre {centres}")
+
+
+def apply_depolarising_bias(mps, sites, p, renormalise=True):
+    """Two-site bias on every adjacent pair starting at each of ``sites[:-1]``.
+    Reference: decoding.py:193-276 (mixed_canonical = move_orth_centre(renormalise=True),
+    canonical.py:549-565; splits use the default chi_max=1e4 / cut=1e-12)."""
+    sites = list(sites)
+    if len(sites) % 2 != 0:
+        raise ValueError(f"The number of sites in the list should be even, given {len(sites)}.")
+    if not 0 <= p <= 1:
+        raise ValueError(f"The channel parameter should be a probability, given {p} at site 0.")
+    if mps.orth_centre is None:
+        mps.orth_centre = check_orth_centre(mps)
+    mps = move_orth_centre(mps, min(sites), renormalise=True)
+    op = depolarising_bias(p)
+    t = mps.tensors
+    for site in sites[:-1]:
+        theta = np.einsum("ijk,klm,jlno->inom", t[site], t[site + 1], op,
+                          optimize=["einsum_path", (0, 1), (0, 1)])
+        u, s, b, _ = split_two_site_tensor(theta, renormalise=renormalise)
+        t[site] = u
+        t[site + 1] = b * s[:, None, None]
+        mps.orth_centre = site + 1
+        if renormalise:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                t[site + 1] = t[site + 1] / np.linalg.norm(t[site + 1])
+    return mps
+
+
+def code_sites(code):
+    """Site lists for checks and logicals of a CSS code object (duck type of SURVEY.md 8b).
+    Reference: decoding.py:512-696.  X-type supports sit at 2q+k, Z-type at 2q+k+1."""
+    k = code.num_x_logicals() + code.num_z_logicals()
+
+    def supports(matrix, offset):
+        return [[2 * int(q) + k + offset for q in sorted(row)] for row in matrix.rows()]
+
+    def check_groups(sup):
+        inner = sup[1:-1]
+        swaps = [s for s in range(sup[0] + 1, sup[-1]) if s not in inner]
+        return [[sup[0]], inner, swaps, [sup[-1]]]
+
+    def logical_groups(index, sup):
+        bulk = sup[:-1]
+        swaps = [s for s in range(index + 1, sup[-1]) if s not in bulk]
+        return [[index], bulk, swaps, [sup[-1]]]
+
+    xs = supports(code.x_stabs_binary(), 0)
+    zs = supports(code.z_stabs_binary(), 1)
+    xl = supports(code.x_logicals_binary(), 0)
+    zl = supports(code.z_logicals_binary(), 1)
+    checks = ([check_groups(s) for s in xs], [check_groups(s) for s in zs])
+    logicals = (
+        [logical_groups(i, s) for i, s in enumerate(xl)],
+        [logical_groups(len(xl) + i, s) for i, s in enumerate(zl)],
+    )
+    return checks, logicals
+
+
+def readout(logical_dense):
+    """Tolerant arg-max.  Reference: decoding.py:1362-1379."""
+    v = np.abs(logical_dense)
+    top = np.max(v)
+    eps = max(1e-9 * top, 1e-12)
+    return v, int(v[0] >= top - eps)
+
+
+def decode_css(code, error, chi_max=int(1e4), cut=1e-17, bias_type="Depolarising", bias_prob=0.1,
+               renormalise=True, contraction_strategy="Naive", tolerance=1e-12, orders=None, record=None):
+    """Reference: decoding.py:1164-1404, dense read-out branch (<= 12 logical sites) only.
+
+    ``orders`` optionally maps 'xl','zl','xc','zc' to explicit MPO orders (used with "Optimised").
+    """
+    if error == "I" * len(error):
+        return [1.0, 0.0, 0.0, 0.0], 1  # decoding.py:1225-1228
+    has_x, has_z = "X" in error, "Z" in error  # literal-character gating, decoding.py:1230-1231
+    bits = pauli_to_mps(error)
+    k = code.num_x_logicals() + code.num_z_logicals()
+    n_sites = 2 * len(code) + k
+    if len(bits) != n_sites - k:
+        raise ValueError(f"The error length is {len(bits)}, expected {n_sites - k}.")
+    mps = product_state("+" * k + bits)
+    mps.tolerance = tolerance
+    checks, logicals = code_sites(code)
+    if bias_type == "Bitflip":
+        mps = apply_bitflip_bias(mps, range(k, n_sites), bias_prob)
+    else:  # any other string takes the depolarising branch, decoding.py:1267-1283
+        mps = apply_depolarising_bias(mps, range(k, n_sites), bias_prob, renormalise=renormalise)
+    orders = orders or {}
+    kw = dict(chi_max=chi_max, cut=cut, renormalise=renormalise, strategy=contraction_strategy, record=record)
+    logical_t = [COPY_LEFT, XOR_BULK, SWAP, XOR_RIGHT]
+    check_t = [XOR_LEFT, XOR_BULK, SWAP, XOR_RIGHT]
+    if has_x:
+        mps = apply_constraints(mps, logicals[0], logical_t, order=orders.get("xl"), **kw)
+    if has_z:
+        mps = apply_constraints(mps, logicals[1], logical_t, order=orders.get("zl"), **kw)
+    if has_x:
+        mps = apply_constraints(mps, checks[0], check_t, order=orders.get("xc"), **kw)
+    if has_z:
+        mps = apply_constraints(mps, checks[1], check_t, order=orders.get("zc"), **kw)
+    if "E" in error:
+        raise NotImplementedError("oracle does not restate the erasure branch")
+    mps = marginal(mps, list(range(k, n_sites)), renormalise=renormalise).reverse()
+    if len(mps) > 12:
+        raise NotImplementedError("Dephasing-DMRG read-out (> 12 logical sites) is out of scope")
+    return readout(mps.dense(flatten=True, renormalise=renormalise, norm=2))
+
+
+# --------------------------------------------------------------------------------------------------
+# Code objects (duck type) and seeded error batches.  Reference: quantum_surface.py:128-146.
+# --------------------------------------------------------------------------------------------------
+
+
+class _Matrix:
+    def __init__(self, ncols, rows):
+        self._n, self._rows = int(ncols), [sorted(int(c) for c in r) for r in rows]
+
+    def rows(self):
+        return [list(r) for r in self._rows]
+
+    def num_rows(self):
+        return len(self._rows)
+
+    def num_columns(self):
+        return self._n
+
+
+class CssCode:
+    """Duck-typed CSS code (methods listed in SURVEY.md 8b)."""
+
+    def __init__(self, n, x_stabs, z_stabs, x_logicals, z_logicals):
+        self._n = int(n)
+        self._m = [_Matrix(n, x_stabs), _Matrix(n, z_stabs), _Matrix(n, x_logicals), _Matrix(n, z_logicals)]
+
+    def __len__(self):
+        return self._n
+
+    def num_x_stabs(self):
+        return self._m[0].num_rows()
+
+    def num_z_stabs(self):
+        return self._m[1].num_rows()
+
+    def num_x_logicals(self):
+        return self._m[2].num_rows()
+
+    def num_z_logicals(self):
+        return self._m[3].num_rows()
+
+    def x_stabs_binary(self):
+        return self._m[0]
+
+    def z_stabs_binary(self):
+        return self._m[1]
+
+    def x_logicals_binary(self):
+        return self._m[2]
+
+    def z_logicals_binary(self):
+        return self._m[3]
+
+
+def surface_code(L):
+    """hypergraph_product(repetition_code(L), repetition_code(L)) in the convention reverse-engineered
+    from the printed 3x3 code (examples/decoding/quantum_surface.ipynb:79-94)."""
+    h = [[i, i + 1] for i in range(L - 1)]
+    n, m = L, L - 1
+    xs = [sorted([i * n + j for j in h[c]] + [n * n + r * m + c for r in range(m) if i in h[r]])
+          for i in range(n) for c in range(m)]
+    zs = [sorted([i * n + j for i in h[r]] + [n * n + r * m + c for c in range(m) if j in h[c]])
+          for r in range(m) for j in range(n)]
+    return CssCode(n * n + m * m, xs, zs, [[n - 1 + i * n for i in range(n)]], [list(range(n))])
+
+
+def seeded_errors(num_qubits, rate, count, seed, model="Bitflip"):
+    """One child generator per syndrome, as quantum_surface.py:130-137.  Depolarising draws X/Y/Z from the
+    same child generator (the reference uses the unseeded global RNG there, decoding.py:1018)."""
+    ss = np.random.SeedSequence(seed)
+    out = []
+    for child in ss.spawn(count):
+        rng = np.random.default_rng(child)
+        chars = []
+        for _ in range(num_qubits):
+            if rng.random() < rate:
+                chars.append("X" if model == "Bitflip" else "XYZ"[int(rng.integers(3))])
+            else:
+                chars.append("I")
+        out.append("".join(chars))
+    return out
