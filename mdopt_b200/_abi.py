@@ -1,0 +1,64 @@
+"""ctypes mirror of ``include/mdopt_b200.h`` (struct layout and prototypes); no CUDA needed to import."""
+from __future__ import annotations
+
+import ctypes as C
+
+
+class DecodeDesc(C.Structure):
+    _fields_ = [
+        ("n_sites", C.c_int32), ("n_logical", C.c_int32), ("chi_max", C.c_int32), ("mode", C.c_int32),
+        ("renormalise", C.c_int32), ("trace_stride", C.c_int32), ("trace_max", C.c_int32), ("n_ops", C.c_int32),
+        ("cut_sweep", C.c_double), ("cut_move", C.c_double), ("rank_tol", C.c_double), ("bias_p", C.c_double),
+    ]
+
+
+ST_OK, ST_NOT_CONVERGED, ST_CAPACITY, ST_ZERO_NORM = 0, 1, 2, 3
+E_BADARG, E_CAPACITY, E_NOGPU = -1, -2, -3
+DEFAULT_RANK_TOL = 1e-14
+CUT_MOVE = 1e-12  # default cut of split_two_site_tensor, used by move_orth_centre (mdopt/utils/utils.py:293)
+
+_p = C.c_void_p
+_i = C.c_int
+_d = C.c_double
+_sz = C.c_size_t
+_desc = C.POINTER(DecodeDesc)
+
+# name -> (restype, argtypes); every symbol include/mdopt_b200.h declares
+PROTOTYPES = {
+    "mdopt_b200_abi_version": (_i, []),
+    "mdopt_device_sm_count": (_i, []),
+    "mdopt_chi_capacity": (_i, [_i]),
+    "mdopt_decode_num_ctas": (_i, [_i]),
+    "mdopt_decode_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mdopt_decode_batch_device": (_i, [_desc, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mdopt_decode_batch_host": (_i, [_desc, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                     _sz, _p]),
+    "mdopt_site_stride": (_sz, [_i]),
+    "mdopt_mps_program_workspace_bytes": (_sz, [_i, _i]),
+    "mdopt_mps_program_device": (_i, [_desc, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mdopt_svd_batch_device": (_i, [_i, _i, _i, _i, _p, _i, _d, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "mdopt_site_apply_batch_device": (_i, [_i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "mdopt_readout_batch_device": (_i, [_i, _i, _p, _i, _p, _p, _p]),
+}
+
+
+def bind(lib: C.CDLL) -> C.CDLL:
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def make_desc(n_sites, n_logical, chi_max, mode, renormalise, n_ops, cut_sweep, bias_p, trace_stride=0,
+              trace_max=0, cut_move=CUT_MOVE, rank_tol=DEFAULT_RANK_TOL) -> DecodeDesc:
+    return DecodeDesc(int(n_sites), int(n_logical), int(chi_max), int(mode), int(bool(renormalise)),
+                      int(trace_stride), int(trace_max), int(n_ops), float(cut_sweep), float(cut_move),
+                      float(rank_tol), float(bias_p))
+
+
+def chi_capacity(chi: int) -> int:
+    for cap in (8, 16, 32, 64):
+        if chi <= cap:
+            return cap
+    return 0

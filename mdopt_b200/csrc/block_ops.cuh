@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #ifdef MDOPT_EMU
+#include <algorithm>
 #define MD_DEV inline
 #define MD_SYNC() ((void)0)
 #define MD_PAR_FOR(i, n) for (int i = 0; i < (n); ++i)
@@ -26,6 +27,11 @@
 #endif
 
 namespace mdopt {
+
+#ifdef MDOPT_EMU
+using std::max;
+using std::min;
+#endif
 
 constexpr int NCH = 8;            // row chunks used by every column-wise partial reduction
 constexpr double EPS = 2.220446049250313e-16;
@@ -49,12 +55,14 @@ struct Smem {
   static constexpr int N2 = 2 * CHI;
   double X[N2 * LD];   // work matrix (up to 2CHI x 2CHI)
   double P2[CHI * LD];  // coefficient page (up to CHI x 2CHI)
-  double part[NCH * N2 * 3];
+  static constexpr int NPART = (NCH * N2 * 3 / 2 > 256) ? NCH * N2 * 3 / 2 : 256;
+  double part[NPART];
   double vn1[N2], vn2[N2], tau[N2], sig[N2], wv[N2];
   double rot[N2 * 2];
   double W[16];         // current MPO site tensor (vL, vR, pU, pD), vL,vR <= 2
   double dscr[16];
-  int perm[N2], order[N2], flag[N2];
+  static constexpr int NFLAG = (N2 > 32) ? N2 : 32;
+  int perm[N2], order[N2], flag[NFLAG];
   int iscr[16];
 };
 
@@ -293,6 +301,28 @@ MD_DEV void jacobi_columns(Smem<CHI>& s, int R, int C, Counters& cnt, int max_sw
   const int npair = n / 2;
   const double tol = EPS * sqrt((double)R);
   const int per = (R + NCH - 1) / NCH;
+  // columns whose norm is below 4 eps * (largest column norm) are numerically zero: pairs involving
+  // one are never rotated (the angle is rounding noise and would never settle) and truncation_rule
+  // never keeps them, so U stays an isometry.
+  MD_PAR_FOR(t, NCH * C) {
+    int ch = t / C, c = t - ch * C;
+    int i0 = ch * per, i1 = min(R, i0 + per);
+    double acc = 0.0;
+    for (int i = i0; i < i1; ++i) { double v = X[i * LD + c]; acc += v * v; }
+    s.part[ch * N2 + c] = acc;
+  }
+  MD_SYNC();
+  MD_LEADER {
+    double mx = 0.0;
+    for (int c = 0; c < C; ++c) {
+      double acc = 0.0;
+      for (int ch = 0; ch < NCH; ++ch) acc += s.part[ch * N2 + c];
+      mx = fmax(mx, acc);
+    }
+    s.dscr[6] = mx * (4.0 * EPS) * (4.0 * EPS);  // squared-norm floor
+  }
+  MD_SYNC();
+  const double floor2 = s.dscr[6];
   int sweeps = 0;
   int converged = (C < 2);
   while (!converged && sweeps < max_sweeps) {
@@ -325,7 +355,7 @@ MD_DEV void jacobi_columns(Smem<CHI>& s, int R, int C, Counters& cnt, int max_sw
         }
         double c = 1.0, sn = 0.0;
         int did = 0;
-        if (sab != 0.0 && fabs(sab) > tol * sqrt(saa) * sqrt(sbb)) {
+        if (sab != 0.0 && fabs(sab) > tol * sqrt(saa) * sqrt(sbb) && saa > floor2 && sbb > floor2) {
           double zeta = (sbb - saa) / (2.0 * sab);
           double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           c = 1.0 / sqrt(1.0 + t * t);
@@ -399,7 +429,8 @@ template <int CHI>
 MD_DEV void truncation_rule(Smem<CHI>& s, int C, int chi_lim, double cut) {
   MD_LEADER {
     int k = 0;
-    for (int i = 0; i < C; ++i) k += (s.sig[s.order[i]] > cut);
+    const double sig_floor = sqrt(s.dscr[6]);
+    for (int i = 0; i < C; ++i) { double v = s.sig[s.order[i]]; k += (v > cut && v > sig_floor); }
     if (k > chi_lim) k = chi_lim;
     double err = 0.0, kept = 0.0;
     for (int i = 0; i < C; ++i) {

@@ -1,0 +1,534 @@
+// Per-CTA MPS engine: one CTA decodes one syndrome, start to finish.
+//
+// Replaces, for the batched decode path, the reference's
+//   mdopt/contractor/contractor.py:177-378   mps_mpo_contract (zip-up sweep)
+//   mdopt/mps/canonical.py:345-420           move_orth_centre
+//   mdopt/optimiser/utils.py:284-345         the per-string loop of apply_constraints
+//   mdopt/mps/canonical.py:906-991 + 241-272 marginal + dense
+//   examples/decoding/decoding.py:1362-1379  tolerant arg-max
+//
+// Formulation.  The reference builds theta = M . A_{c+1} . W_{c+1} and splits it.
+// Whenever the MPO site tensor W, read as a matrix (vL,pU) -> (vR,pD), has orthonormal rows (XOR_BULK,
+// SWAP, IDENTITY, XOR_LEFT/COPY_LEFT never occur in that position), theta = Mmat . T with T an isometry,
+// so the split of theta is the split of the carried matrix Mmat (2K x w*chi) followed by M' . T.  The
+// engine therefore factors Mmat (128 x 128 at chi=64 instead of 128 x 256) and applies the next site
+// afterwards.  For non-isometric W (XOR_RIGHT at the end of every string) theta is formed explicitly.
+// Orth-centre moves are the same step with an identity MPO, run in a mirrored frame when moving left.
+//
+// Two factorisation modes:
+//   MODE_SVD   every split is a one-sided Jacobi SVD with the reference's truncation rule
+//              k = min(chi_max, #(s > cut)) (utils.py:119); moves use cut = 1e-12 (canonical.py:399-405).
+//   MODE_FAST  rank-revealing Householder QR with column pivoting; only when more than chi_max
+//              columns carry weight above rank_tol * ||.|| does the step fall back to the Jacobi SVD.
+//              Non-truncating steps only re-gauge the bond, which leaves the state unchanged.
+#pragma once
+#include "block_ops.cuh"
+
+namespace mdopt {
+
+enum { OP_END = 0, OP_SWEEP = 1, OP_MOVE = 2, OP_MARGINAL = 3, OP_GATE2 = 4 };
+enum { MODE_FAST = 0, MODE_SVD = 1 };
+enum { ST_OK = 0, ST_NOT_CONVERGED = 1, ST_CAPACITY = 2, ST_ZERO_NORM = 3 };
+
+struct DecodeParams {
+  int n_sites;        // MPS length N
+  int n_logical;      // number of logical sites kL (they are sites 0..kL-1)
+  int chi_max;        // user chi_max for sweeps
+  int mode;           // MODE_FAST / MODE_SVD
+  int renormalise;    // decode_css(renormalise=...)
+  int trace_stride;   // doubles per traced step (0 = no trace)
+  int trace_max;      // max traced steps per syndrome
+  int n_ops;          // length of the program in ints
+  double cut_sweep;   // user cut for sweep splits
+  double cut_move;    // 1e-12 (reference default of split_two_site_tensor inside move_orth_centre)
+  double rank_tol;    // MODE_FAST relative rank threshold
+  double bias_p;      // bit-flip bias probability; < 0 disables the bias
+};
+
+// Per-CTA view of its global workspace.
+template <int CHI>
+struct Engine {
+  static constexpr int LD = Smem<CHI>::LD;
+  static constexpr int N2 = Smem<CHI>::N2;
+  static constexpr int SITE_STRIDE = CHI * 2 * CHI;
+
+  Smem<CHI>& s;
+  double* sites;   // [N][SITE_STRIDE], packed (vL, p, vR) row-major per site
+  double* scr0;    // carried matrix, flat
+  double* scr1;    // theta scratch for non-isometric steps
+  int* bd;         // [N+1] bond dimensions (global, per CTA)
+  const double* wtab;  // [n_tensors][16]
+  const int* wdim;     // [n_tensors][4] = vL, vR, iso, pad
+  double* trace;   // per-syndrome trace block or nullptr
+  int n_traced;
+  DecodeParams P;
+  Counters cnt;
+  int status;
+  int centre;
+  // carried-matrix state
+  int K, Wq, Mr;
+  int mirrored;
+
+  MD_DEV Engine(Smem<CHI>& sm) : s(sm) {}
+
+  // ---- frame helpers: logical site j of the current frame ----
+  MD_DEV int phys(int j) const { return mirrored ? (P.n_sites - 1 - j) : j; }
+  MD_DEV int dim_left(int j) const { int p = phys(j); return mirrored ? bd[p + 1] : bd[p]; }
+  MD_DEV int dim_right(int j) const { int p = phys(j); return mirrored ? bd[p] : bd[p + 1]; }
+  MD_DEV void set_dim_right(int j, int v) { int p = phys(j); if (mirrored) bd[p] = v; else bd[p + 1] = v; }
+
+  MD_DEV void load_w(int tid) {
+    MD_PAR_FOR(i, 16) { s.W[i] = (tid < 0) ? ((i == 0 || i == 3) ? 1.0 : 0.0) : wtab[tid * 16 + i]; }
+    MD_SYNC();
+  }
+  MD_DEV int w_vl(int tid) const { return tid < 0 ? 1 : wdim[tid * 4 + 0]; }
+  MD_DEV int w_vr(int tid) const { return tid < 0 ? 1 : wdim[tid * 4 + 1]; }
+  MD_DEV int w_iso(int tid) const { return tid < 0 ? 1 : wdim[tid * 4 + 2]; }
+  // W(q, w', pU, pD) with actual dims (vl, vr, 2, 2)
+  MD_DEV double w_at(int vr, int q, int wo, int pu, int pd) const { return s.W[((q * vr + wo) * 2 + pu) * 2 + pd]; }
+
+  // ---- carried <- site j with the first MPO tensor applied (contractor.py:276-291, first half) ----
+  // out[((k*2 + p')*Wq + q)*Mr + m] = sum_p A[k,p,m] W(0,q,p,p')
+  MD_DEV void carried_from_site(int j, int tid) {
+    load_w(tid);
+    const int A = dim_left(j), B = dim_right(j), vr = w_vr(tid);
+    const double* src = sites + (size_t)phys(j) * SITE_STRIDE;
+    const int mir = mirrored;
+    MD_PAR_FOR(t, A * 2 * vr * B) {
+      int m = t % B; int r = t / B;
+      int q = r % vr; r /= vr;
+      int pd = r & 1; int k = r >> 1;
+      double a0, a1;
+      if (!mir) { a0 = src[(k * 2 + 0) * B + m]; a1 = src[(k * 2 + 1) * B + m]; }
+      else { a0 = src[(m * 2 + 0) * A + k]; a1 = src[(m * 2 + 1) * A + k]; }
+      scr0[t] = a0 * w_at(vr, 0, q, 0, pd) + a1 * w_at(vr, 0, q, 1, pd);
+    }
+    MD_LEADER { cnt.bytes_hbm += 8.0 * (A * 2 * B + A * 2 * vr * B); cnt.flops_apply += 3.0 * A * 2 * vr * B; }
+    K = A; Wq = vr; Mr = B;
+    MD_SYNC();
+  }
+
+  // ---- stage site j (frame layout (a,p,b) flat) into dst (shared) ----
+  MD_DEV void stage_site(int j, double* dst, int A, int B) {
+    const double* src = sites + (size_t)phys(j) * SITE_STRIDE;
+    if (!mirrored) { MD_PAR_FOR(g, A * 2 * B) dst[g] = src[g]; }
+    else {
+      MD_PAR_FOR(g, A * 2 * B) {  // phys tensor has dims (B, 2, A)
+        int a = g % A; int r = g / A; int p = r & 1; int b = r >> 1;
+        dst[(a * 2 + p) * B + b] = src[g];
+      }
+    }
+    MD_LEADER { cnt.bytes_hbm += 8.0 * A * 2 * B; }
+    MD_SYNC();
+  }
+
+  // ---- out[((row*2+p')*vr + w')*Bn + m'] = sum_{q,p,m} Min[row, q*Mr+m] W(q,w',p,p') As[(m*2+p)*Bn + m'] ----
+  MD_DEV void apply_site(const double* Min, int ld, int rows, int vl, int vr, int mr, int Bn,
+                         const double* As, double* out) {
+    constexpr int TR = 8, TM = 2;
+    const int nrt = (rows + TR - 1) / TR, nmt = (Bn + TM - 1) / TM;
+    const int ncomb = 2 * vr;
+    MD_PAR_FOR(t, nrt * ncomb * nmt) {
+      int mt = t % nmt; int r = t / nmt;
+      int comb = r % ncomb; int rt = r / ncomb;
+      int wo = comb % vr, pd = comb / vr;
+      int row0 = rt * TR, m0 = mt * TM;
+      double acc[TR][TM];
+#pragma unroll
+      for (int a = 0; a < TR; ++a)
+#pragma unroll
+        for (int b = 0; b < TM; ++b) acc[a][b] = 0.0;
+      for (int q = 0; q < vl; ++q) {
+        for (int pu = 0; pu < 2; ++pu) {
+          double w = w_at(vr, q, wo, pu, pd);
+          if (w == 0.0) continue;
+          const double* mrow = Min + row0 * ld + q * mr;
+          const double* arow = As + pu * Bn + m0;
+          for (int m = 0; m < mr; ++m) {
+            double av[TM];
+#pragma unroll
+            for (int b = 0; b < TM; ++b) av[b] = (m0 + b < Bn) ? arow[(size_t)m * 2 * Bn + b] : 0.0;
+#pragma unroll
+            for (int a = 0; a < TR; ++a) {
+              double x = (row0 + a < rows) ? w * mrow[a * ld + m] : 0.0;
+#pragma unroll
+              for (int b = 0; b < TM; ++b) acc[a][b] += x * av[b];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < TR; ++a)
+#pragma unroll
+        for (int b = 0; b < TM; ++b)
+          if (row0 + a < rows && m0 + b < Bn)
+            out[(((size_t)(row0 + a) * 2 + pd) * vr + wo) * Bn + m0 + b] = acc[a][b];
+    }
+    MD_LEADER {
+      int nnz = 0;
+      for (int i = 0; i < vl * vr * 4; ++i) nnz += (s.W[i] != 0.0);
+      cnt.flops_apply += 2.0 * rows * Bn * mr * nnz;
+      cnt.bytes_hbm += 8.0 * rows * 2 * vr * Bn;
+    }
+    MD_SYNC();
+  }
+
+  MD_DEV void load_x(const double* src, int R, int C) {
+    MD_PAR_FOR(t, R * C) { int i = t / C, c = t - i * C; s.X[i * LD + c] = src[t]; }
+    MD_LEADER { cnt.bytes_hbm += 8.0 * R * C; }
+    MD_SYNC();
+  }
+
+  // ---- factor X (R x C; a copy lives in `orig`, flat ld C) -> Knew, U (in X), coefficients (in P2) ----
+  // Returns Knew.  s.iscr[7] = 1 when U columns are addressed through s.order / scaled by 1/s.sig.
+  MD_DEV int factor(const double* orig, int R, int C, int chi_lim, double cut, int is_move) {
+    int use_svd = (P.mode == MODE_SVD);
+    int Knew = 0;
+    if (!use_svd) {
+      qrcp<CHI>(s, R, C, chi_lim < CHI ? chi_lim : CHI, P.rank_tol, cnt);
+      Knew = s.iscr[0];
+      if (s.iscr[1]) {  // more than chi_lim significant directions: genuine truncation needed
+        use_svd = 1;
+        load_x(orig, R, C);
+        MD_LEADER { cnt.n_trunc += 1.0; }
+      }
+    }
+    if (!use_svd) {
+      if (Knew == 0) {  // zero matrix: keep a single zero direction (the state has zero norm)
+        MD_PAR_FOR(i, R) s.X[i * LD] = (i == 0) ? 1.0 : 0.0;
+        MD_PAR_FOR(c, C) s.P2[c] = 0.0;
+        MD_LEADER { s.iscr[7] = 0; }
+        MD_SYNC();
+        return 1;
+      }
+      extract_coeff<CHI>(s, Knew, C);
+      form_q<CHI>(s, R, Knew, cnt);
+      MD_LEADER { s.iscr[7] = 0; }
+      MD_SYNC();
+      return Knew;
+    }
+    // ---- Jacobi SVD path ----
+    jacobi_columns<CHI>(s, R, C, cnt);
+    if (s.iscr[5]) status = ST_NOT_CONVERGED;
+    truncation_rule<CHI>(s, C, chi_lim, cut);
+    Knew = s.iscr[0];
+    if (trace != nullptr && n_traced < P.trace_max) {
+      double* tr = trace + (size_t)n_traced * P.trace_stride;
+      MD_LEADER { tr[0] = R; tr[1] = C; tr[2] = Knew; tr[3] = is_move; }
+      MD_PAR_FOR(c, N2) { if (4 + c < P.trace_stride) tr[4 + c] = (c < C) ? s.sig[s.order[c]] : 0.0; }
+    }
+    n_traced += 1;
+    if (Knew > CHI) { status = ST_CAPACITY; MD_SYNC(); return 0; }  // would overflow the site stride
+    if (Knew == 0) {
+      MD_SYNC();
+      MD_PAR_FOR(i, R) s.X[i * LD] = (i == 0) ? 1.0 : 0.0;
+      MD_PAR_FOR(c, C) s.P2[c] = 0.0;
+      MD_LEADER { s.iscr[7] = 0; }
+      MD_SYNC();
+      return 1;
+    }
+    // coefficients M'[k, c] = (1/sigma_k) sum_i X[i, order[k]] orig[i, c]   (= sigma_k v_k^T)
+    {
+      constexpr int TK = 8;
+      const int nkt = (Knew + TK - 1) / TK;
+      MD_PAR_FOR(t, nkt * C) {
+        int c = t % C, kt = t / C;
+        int k0 = kt * TK;
+        double acc[TK];
+        int col[TK];
+#pragma unroll
+        for (int a = 0; a < TK; ++a) { acc[a] = 0.0; col[a] = s.order[min(k0 + a, Knew - 1)]; }
+        for (int i = 0; i < R; ++i) {
+          double xo = orig[(size_t)i * C + c];
+#pragma unroll
+          for (int a = 0; a < TK; ++a) acc[a] += s.X[i * LD + col[a]] * xo;
+        }
+#pragma unroll
+        for (int a = 0; a < TK; ++a)
+          if (k0 + a < Knew) s.P2[(k0 + a) * LD + c] = acc[a] / s.sig[col[a]];
+      }
+      MD_LEADER { cnt.flops_apply += 2.0 * R * C * Knew; cnt.bytes_hbm += 8.0 * R * C * nkt; s.iscr[7] = 1; }
+    }
+    MD_SYNC();
+    return Knew;
+  }
+
+  // ---- site j <- U (R = K*2 rows, Knew columns), frame layout (k, r, k') ----
+  MD_DEV void store_u(int j, int Kl, int Knew) {
+    double* dst = sites + (size_t)phys(j) * SITE_STRIDE;
+    const int ord = s.iscr[7];
+    if (!mirrored) {
+      MD_PAR_FOR(g, Kl * 2 * Knew) {
+        int kn = g % Knew, row = g / Knew;
+        double v = ord ? s.X[row * LD + s.order[kn]] / s.sig[s.order[kn]] : s.X[row * LD + kn];
+        dst[g] = v;
+      }
+    } else {  // phys tensor dims (Knew, 2, Kl)
+      MD_PAR_FOR(g, Kl * 2 * Knew) {
+        int k = g % Kl; int r = g / Kl; int p = r & 1; int kn = r >> 1;
+        int row = k * 2 + p;
+        double v = ord ? s.X[row * LD + s.order[kn]] / s.sig[s.order[kn]] : s.X[row * LD + kn];
+        dst[g] = v;
+      }
+    }
+    MD_LEADER { cnt.bytes_hbm += 8.0 * Kl * 2 * Knew; }
+    MD_SYNC();
+  }
+
+  // ---- one two-site step: absorb site jn (frame index) with MPO tensor tid ----
+  MD_DEV void step(int jn, int tid, int chi_lim, double cut, int is_move, int renorm_sv) {
+    const int vl = w_vl(tid), vr = w_vr(tid), iso = w_iso(tid);
+    const int Bn = dim_right(jn);
+    const int R = K * 2;
+    int C = Wq * Mr;
+    const double* orig = scr0;
+    load_w(tid);
+    if (vl != Wq || dim_left(jn) != Mr) { status = ST_CAPACITY; return; }
+    if (!iso) {
+      // theta = Mmat . T formed explicitly (contractor.py:328-342), R x (2*vr*Bn)
+      if (2 * vr * Bn > N2) { status = ST_CAPACITY; return; }
+      load_x(scr0, R, C);
+      stage_site(jn, s.P2, Mr, Bn);
+      apply_site(s.X, LD, R, vl, vr, Mr, Bn, s.P2, scr1);
+      C = 2 * vr * Bn;
+      orig = scr1;
+    }
+    load_x(orig, R, C);
+    int Knew = factor(orig, R, C, chi_lim, cut, is_move);
+    if (status == ST_CAPACITY) return;
+    if (renorm_sv) {  // mps_mpo_contract(renormalise=True): s /= ||s|| (utils.py:126-129); ||s|| = ||M'||_F
+      MD_PAR_FOR(ch, 256) {
+        double acc = 0.0;
+        for (int t = ch; t < Knew * C; t += 256) { int k = t / C, c = t - k * C; double v = s.P2[k * LD + c]; acc += v * v; }
+        s.part[ch] = acc;
+      }
+      MD_SYNC();
+      MD_LEADER {
+        double acc = 0.0;
+        for (int ch = 0; ch < 256; ++ch) acc += s.part[ch];
+        s.dscr[4] = (acc > 0.0) ? 1.0 / sqrt(acc) : 1.0;
+      }
+      MD_SYNC();
+      const double inv = s.dscr[4];
+      MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; s.P2[k * LD + c] *= inv; }
+      MD_SYNC();
+    }
+    store_u(jn - 1, K, Knew);
+    if (iso) {
+      stage_site(jn, s.X, Mr, Bn);
+      apply_site(s.P2, LD, Knew, vl, vr, Mr, Bn, s.X, scr0);
+    } else {
+      MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; scr0[t] = s.P2[k * LD + c]; }
+      MD_LEADER { cnt.bytes_hbm += 8.0 * Knew * C; }
+      MD_SYNC();
+    }
+    K = Knew; Wq = vr; Mr = Bn;
+    MD_LEADER { cnt.n_steps += 1.0; set_dim_right(jn - 1, Knew); }
+    MD_SYNC();
+  }
+
+  // ---- carried (K,2,1,Mr) -> site j, optionally divided by its Frobenius norm (optimiser/utils.py:340-345) ----
+  MD_DEV void carried_to_site(int j, int renorm) {
+    const int n = K * 2 * Mr;
+    double scale = 1.0;
+    if (renorm) {
+      MD_PAR_FOR(ch, 256) {
+        double acc = 0.0;
+        for (int t = ch; t < n; t += 256) { double v = scr0[t]; acc += v * v; }
+        s.part[ch] = acc;
+      }
+      MD_SYNC();
+      MD_LEADER {
+        double acc = 0.0;
+        for (int ch = 0; ch < 256; ++ch) acc += s.part[ch];
+        double nrm = sqrt(acc);
+        s.dscr[4] = (nrm > 0.0) ? 1.0 / nrm : 1.0;
+      }
+      MD_SYNC();
+      scale = s.dscr[4];
+    }
+    double* dst = sites + (size_t)phys(j) * SITE_STRIDE;
+    const int A = K, B = Mr;
+    if (!mirrored) { MD_PAR_FOR(g, n) dst[g] = scr0[g] * scale; }
+    else {
+      MD_PAR_FOR(g, n) {  // phys dims (B, 2, A)
+        int a = g % A; int r = g / A; int p = r & 1; int b = r >> 1;
+        dst[g] = scr0[(a * 2 + p) * B + b] * scale;
+      }
+    }
+    MD_LEADER { cnt.bytes_hbm += 16.0 * n; }
+    MD_SYNC();
+  }
+
+  // ---- sweep of an MPO over frame sites start..start+len-1 (tids == nullptr: identity MPO = move) ----
+  MD_DEV void sweep(int start, int len, const int* tids, int chi_lim, double cut, int renorm_after,
+                    int is_move, int renorm_sv) {
+    carried_from_site(start, tids ? tids[0] : -1);
+    for (int t = 1; t < len; ++t) {
+      step(start + t, tids ? tids[t] : -1, chi_lim, cut, is_move, renorm_sv);
+      if (status == ST_CAPACITY) return;
+    }
+    if (Wq != 1) { status = ST_CAPACITY; return; }
+    carried_to_site(start + len - 1, renorm_after);
+  }
+
+  // ---- move the orthogonality centre (canonical.py:345-420) ----
+  MD_DEV void move_centre(int target) {
+    if (target == centre) return;
+    const int chi_lim = CHI;
+    if (target > centre) {
+      mirrored = 0;
+      sweep(centre, target - centre + 1, nullptr, chi_lim, P.cut_move, 0, 1, 0);
+    } else {
+      mirrored = 1;
+      const int N = P.n_sites;
+      sweep(N - 1 - centre, centre - target + 1, nullptr, chi_lim, P.cut_move, 0, 1, 0);
+      mirrored = 0;
+    }
+    centre = target;
+  }
+
+  // ---- product state + bit-flip bias (mps/utils.py:439-512, decoding.py:140-190) ----
+  MD_DEV void init_product(const uint8_t* sym) {
+    const int N = P.n_sites;
+    const double d = (P.bias_p >= 0.0) ? sqrt(1.0 - P.bias_p) : 1.0;
+    const double o = (P.bias_p >= 0.0) ? sqrt(P.bias_p) : 0.0;
+    const int kL = P.n_logical;
+    MD_PAR_FOR(j, N) {
+      double a0, a1;
+      int c = sym[j];
+      if (c == 0) { a0 = 1.0; a1 = 0.0; }
+      else if (c == 1) { a0 = 0.0; a1 = 1.0; }
+      else { a0 = 1.0 / sqrt(2.0); a1 = a0; }
+      if (j >= kL && P.bias_p >= 0.0) {
+        double b0 = a0 * d + a1 * o, b1 = a0 * o + a1 * d;
+        a0 = b0; a1 = b1;
+      }
+      sites[(size_t)j * SITE_STRIDE + 0] = a0;
+      sites[(size_t)j * SITE_STRIDE + 1] = a1;
+    }
+    MD_PAR_FOR(j, N + 1) bd[j] = 1;
+    centre = 0; mirrored = 0; status = ST_OK; n_traced = 0;
+    MD_SYNC();
+  }
+
+  // ---- marginal over sites kL..N-1, reverse, dense, |.|, L2 renorm, tolerant arg-max ----
+  //   canonical.py:956-989, :150-161, :241-272; decoding.py:1362-1379
+  MD_DEV void marginal_readout(double* out, int* success) {
+    const int N = P.n_sites, kL = P.n_logical, ren = P.renormalise;
+    double* T = s.part;        // current last tensor (L x 2), L <= CHI
+    double* w = s.wv;          // traced vector
+    int L = bd[N - 1];
+    MD_PAR_FOR(t, L * 2) T[t] = sites[(size_t)(N - 1) * SITE_STRIDE + t];  // (L, 2, 1)
+    MD_SYNC();
+    for (int site = N - 1; site >= kL; --site) {
+      MD_PAR_FOR(l, L) w[l] = (T[l * 2] + T[l * 2 + 1]) * (1.0 / sqrt(2.0));
+      MD_SYNC();
+      const int L2 = bd[site - 1];
+      const double* A = sites + (size_t)(site - 1) * SITE_STRIDE;  // (L2, 2, L)
+      MD_PAR_FOR(t, L2 * 2) {
+        double acc = 0.0;
+        for (int l = 0; l < L; ++l) acc += A[(size_t)t * L + l] * w[l];
+        T[t] = acc;
+      }
+      MD_LEADER { cnt.bytes_hbm += 8.0 * L2 * 2 * L; cnt.flops_apply += 2.0 * L2 * 2 * L; }
+      MD_SYNC();
+      if (ren) {
+        MD_LEADER {
+          double acc = 0.0;
+          for (int t = 0; t < L2 * 2; ++t) acc += T[t] * T[t];
+          s.dscr[5] = sqrt(acc);
+        }
+        MD_SYNC();
+        const double nrm = s.dscr[5];
+        MD_PAR_FOR(t, L2 * 2) T[t] = T[t] / nrm;  // unguarded like the reference: 0/0 -> NaN
+        MD_SYNC();
+      }
+      L = L2;
+    }
+    // the merged last logical tensor goes back into the MPS (what CanonicalMPS.marginal returns)
+    MD_PAR_FOR(t, L * 2) sites[(size_t)(kL - 1) * SITE_STRIDE + t] = T[t];
+    MD_LEADER { bd[kL] = 1; }
+    MD_SYNC();
+    // dense over the kL logical sites: D_j[(p_j .. p_0), b]
+    double* D0 = s.X;
+    double* D1 = s.X + (N2 * LD) / 2;
+    int nb = 1, nidx = 1;
+    MD_LEADER { D0[0] = 1.0; }
+    MD_SYNC();
+    for (int j = 0; j < kL; ++j) {
+      const int Bl = nb;
+      const int Br = (j == kL - 1) ? 1 : bd[j + 1];
+      const double* A = sites + (size_t)j * SITE_STRIDE;
+      const int last = (j == kL - 1);
+      MD_PAR_FOR(t, nidx * 2 * Br) {
+        int b2 = t % Br; int r = t / Br; int idx = r % nidx; int p = r / nidx;
+        double acc = 0.0;
+        for (int b = 0; b < Bl; ++b) {
+          double a = last ? T[b * 2 + p] : A[((size_t)b * 2 + p) * Br + b2];
+          acc += D0[idx * Bl + b] * a;
+        }
+        D1[(p * nidx + idx) * Br + b2] = acc;
+      }
+      MD_SYNC();
+      double* tmp = D0; D0 = D1; D1 = tmp;
+      nidx *= 2; nb = Br;
+    }
+    MD_LEADER {
+      double nrm = 0.0, top = 0.0;
+      for (int i = 0; i < nidx; ++i) { double v = fabs(D0[i]); nrm += v * v; }
+      nrm = sqrt(nrm);
+      double inv = (ren && nrm > 1e-17) ? 1.0 / nrm : 1.0;
+      int nan_seen = 0;
+      for (int i = 0; i < nidx; ++i) {
+        double v = fabs(D0[i]) * inv;
+        out[i] = v;
+        if (v != v) nan_seen = 1;
+        if (v > top) top = v;
+      }
+      if (nan_seen) { *success = 0; if (status == ST_OK) status = ST_ZERO_NORM; }
+      else {
+        double eps = fmax(1e-9 * top, 1e-12);
+        *success = (out[0] >= top - eps) ? 1 : 0;
+      }
+    }
+    MD_SYNC();
+  }
+
+  // ---- run the error-independent program on one syndrome ----
+  MD_DEV void run(const int* prog, const uint8_t* sym, double* out, int* success) {
+    init_product(sym);
+    run_ops(prog, out, success);
+  }
+
+  // ---- run a program on the MPS already present in sites / bd / centre ----
+  MD_DEV void run_ops(const int* prog, double* out, int* success) {
+    int pc = 0;
+    while (pc < P.n_ops) {
+      const int op = prog[pc];
+      if (op == OP_END) break;
+      if (op == OP_SWEEP) {
+        const int start = prog[pc + 1], len = prog[pc + 2], ren = prog[pc + 3], rsv = prog[pc + 4];
+        move_centre(start);
+        if (status != ST_CAPACITY) {
+          mirrored = 0;
+          sweep(start, len, prog + pc + 5, P.chi_max, P.cut_sweep, ren, 0, rsv);
+          centre = start + len - 1;
+        }
+        pc += 5 + len;
+      } else if (op == OP_MOVE) {
+        move_centre(prog[pc + 1]);
+        pc += 2;
+      } else if (op == OP_MARGINAL) {
+        if (out != nullptr) marginal_readout(out, success);
+        pc += 1;
+      } else {
+        status = ST_CAPACITY;
+        break;
+      }
+      if (status == ST_CAPACITY) break;
+    }
+  }
+};
+
+}  // namespace mdopt

@@ -1,0 +1,159 @@
+"""``CanonicalMPS``: host container with GPU-backed operations.
+
+Mirror of the part of ``mdopt/mps/canonical.py`` the decode path touches: constructor and attributes
+(:87-140), ``copy`` (:142), ``reverse`` (:150), ``dense`` (:241), ``move_orth_centre`` (:345),
+``marginal`` (:906).  Tensors stay host NumPy arrays (the reference returns host arrays even on its GPU
+backend, contractor.py:375-376); ``move_orth_centre`` and the MPO contraction run on the GPU engine.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+from functools import reduce
+from typing import List, Optional
+
+import numpy as np
+
+
+class CanonicalMPS:
+    def __init__(self, tensors: List[np.ndarray], orth_centre: Optional[int] = None,
+                 tolerance: float = float(1e-12), chi_max: int = int(1e4)) -> None:
+        self.tensors = tensors
+        self.num_sites = len(tensors)
+        self.num_bonds = self.num_sites - 1
+        self.orth_centre = orth_centre
+        self.dtype = tensors[0].dtype
+        self.tolerance = tolerance
+        self.chi_max = chi_max
+        if orth_centre and orth_centre not in range(self.num_sites):
+            raise ValueError(
+                f"The orthogonality centre index must reside anywhere from site 0 "
+                f"to {self.num_sites-1}, the one given is at position {orth_centre}."
+            )
+        for i, tensor in enumerate(tensors):
+            if tensor.ndim != 3:
+                raise ValueError(f"A valid MPS tensor must have 3 legs while the one at site {i} has {tensor.ndim}.")
+
+    @property
+    def bond_dimensions(self) -> List[int]:
+        return [t.shape[-1] for t in self.tensors[:-1]]
+
+    @property
+    def phys_dimensions(self) -> List[int]:
+        return [t.shape[1] for t in self.tensors]
+
+    def __len__(self) -> int:
+        return self.num_sites
+
+    def copy(self) -> "CanonicalMPS":
+        return CanonicalMPS(deepcopy(self.tensors), self.orth_centre, self.tolerance, self.chi_max)
+
+    def reverse(self) -> "CanonicalMPS":
+        rev = [np.transpose(t) for t in reversed(self.tensors)]
+        if self.orth_centre:  # 0 is falsy in the reference too (canonical.py:155)
+            return CanonicalMPS(rev, self.num_sites - 1 - self.orth_centre, self.tolerance, self.chi_max)
+        return CanonicalMPS(rev, None, self.tolerance, self.chi_max)
+
+    def dense(self, flatten: bool = True, renormalise: bool = False, norm=2) -> np.ndarray:
+        """Dense vector of a *small* MPS (host; used only for <= 12 logical sites in the reference)."""
+        out = reduce(lambda a, b: np.tensordot(a, b, (-1, 0)), self.tensors).squeeze()
+        if flatten:
+            out = out.flatten()
+        if renormalise:
+            n = float(np.linalg.norm(out, ord=norm))
+            if n > 1e-17:
+                out = out / n
+        return out
+
+    def resolve_orth_centre(self, tol: float = 1e-12) -> int:
+        """Orthogonality-centre bootstrap for an MPS whose ``orth_centre`` is None
+        (mdopt/mps/utils.py:38-124 + mdopt/optimiser/utils.py:299-322)."""
+        n = self.num_sites
+        left, right, centres = [], [], []
+        for i, t in enumerate(self.tensors):
+            gl = np.einsum("ijk,ijl->kl", t, np.conjugate(t))
+            gr = np.einsum("ijk,ljk->il", t, np.conjugate(t))
+            fl = bool(np.isclose(np.linalg.norm(gl - np.eye(gl.shape[0])), 0, atol=tol))
+            fr = bool(np.isclose(np.linalg.norm(gr - np.eye(gr.shape[0])), 0, atol=tol))
+            left.append(fl)
+            right.append(fr)
+            if not fl and not fr:
+                centres.append(i)
+        neg = [not f for f in left]
+        if left in ([True] + [False] * (n - 1), [False] * n) and right == neg:
+            centres.append(0)
+        if left in ([True] * (n - 1) + [False], [True] * n) and right == neg:
+            centres.append(n - 1)
+        if all(left) and all(right):
+            centres.append(0)
+        oc = centres[0] if len(centres) == 1 else None
+        if all(left) and all(right):
+            oc = 0
+        elif left == [True] + [False] * (n - 1):
+            oc = n - 1 if right == neg else oc
+        elif left == [True] * (n - 1) + [False]:
+            oc = 0 if right == neg else oc
+        elif all(right):
+            oc = 0
+        elif all(left):
+            oc = n - 1
+        if len(centres) > 1:
+            oc = centres[0]
+        if oc is None:
+            raise ValueError("The orthogonality centre value is set to None.")
+        return oc
+
+    def move_orth_centre(self, final_pos: int, return_singular_values: bool = False, renormalise: bool = True,
+                         mode: str = "svd"):
+        """Move the orthogonality centre on the GPU (reference canonical.py:345-420).
+
+        ``renormalise`` of the per-bond spectra is not applied (the decode path always passes False).
+        """
+        if final_pos not in range(self.num_sites):
+            raise ValueError(
+                "The final position of the orthogonality centre should be"
+                f"from 0 to {self.num_sites-1}, given {final_pos}."
+            )
+        if return_singular_values:
+            raise NotImplementedError("return_singular_values is not provided by the GPU engine")
+        centre = self.orth_centre if self.orth_centre is not None else self.resolve_orth_centre()
+        if centre == final_pos:
+            return self
+        from mdopt_b200 import engine, schedule
+
+        ops = np.array([schedule.OP_MOVE, final_pos, schedule.OP_END], dtype=np.int32)
+        table = schedule.TensorTable()
+        from mdopt_b200.optimiser.utils import IDENTITY
+
+        table.add(IDENTITY)
+        wtab, wdim = table.arrays()
+        res = engine.run_program_on_mps(self.tensors, centre, ops, wtab, wdim, self.chi_max, 1e-12, False, mode=mode)
+        return CanonicalMPS(res["tensors"], res["centre"], self.tolerance, self.chi_max)
+
+    def marginal(self, sites_to_marginalise: List[int], renormalise: bool = False) -> "CanonicalMPS":
+        """Trace sites out with (1,..,1)/sqrt(d); MUTATES and returns self (reference canonical.py:906-991).
+
+        The GPU engine implements the case the decoder uses -- a contiguous tail ``k..N-1`` traced into
+        the leading ``k`` sites (decoding.py:1348-1356); other site sets raise ``NotImplementedError``.
+        """
+        if not sites_to_marginalise:
+            return self
+        if set(sites_to_marginalise) - set(range(self.num_sites)):
+            raise ValueError("The list of sites to marginalise must be a subset of the list of all sites.")
+        sites = sorted(set(sites_to_marginalise))
+        k = sites[0]
+        if sites != list(range(k, self.num_sites)) or not 1 <= k <= 6:
+            raise NotImplementedError("the GPU marginal supports a contiguous tail k..N-1 with 1 <= k <= 6")
+        from mdopt_b200 import engine, schedule
+        from mdopt_b200.optimiser.utils import IDENTITY
+
+        table = schedule.TensorTable()
+        table.add(IDENTITY)
+        wtab, wdim = table.arrays()
+        ops = np.array([schedule.OP_MARGINAL, schedule.OP_END], dtype=np.int32)
+        res = engine.run_program_on_mps(self.tensors, self.orth_centre or 0, ops, wtab, wdim, self.chi_max, 1e-12,
+                                        renormalise, n_logical=k, want_dist=True)
+        self.tensors[:] = res["tensors"][:k]
+        self.num_sites = k
+        self.num_bonds = k - 1
+        self.orth_centre = k - 1
+        return self

@@ -1,0 +1,182 @@
+"""Error-independent device programs for the decode path (host logic, no GPU needed).
+
+A *program* is the int32 opcode stream ``libmdopt_b200`` interprets for every syndrome of a batch
+(``include/mdopt_b200.h``): one ``OP_SWEEP`` per constraint string, in the order ``apply_constraints``
+would apply them, then ``OP_MARGINAL``.  It depends only on the code and on which constraint groups are
+active, so it is built once per (code, has-X, has-Z) and reused for the whole batch.  Reference call
+sequence: ``examples/decoding/decoding.py:1285-1356``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from mdopt_b200.optimiser.utils import (COPY_LEFT, SWAP, XOR_BULK, XOR_LEFT, XOR_RIGHT, ConstraintString, msro)
+
+OP_END, OP_SWEEP, OP_MOVE, OP_MARGINAL = 0, 1, 2, 3
+MODE_FAST, MODE_SVD = 0, 1
+SYM_ZERO, SYM_ONE, SYM_PLUS = 0, 1, 2
+
+_PAULI_BITS = {"I": (0, 0), "X": (1, 0), "Z": (0, 1), "Y": (1, 1)}  # decoding.py:283-320
+
+
+class TensorTable:
+    """De-duplicated table of MPO site tensors, padded to 16 doubles, plus (vL, vR, isometric) flags."""
+
+    def __init__(self) -> None:
+        self._ids: Dict[bytes, int] = {}
+        self.data: List[np.ndarray] = []
+        self.dims: List[Tuple[int, int, int, int]] = []
+
+    @staticmethod
+    def is_isometric(w: np.ndarray) -> bool:
+        vl, vr = w.shape[0], w.shape[1]
+        mat = np.transpose(w, (0, 2, 1, 3)).reshape(vl * 2, vr * 2)
+        return bool(np.allclose(mat @ mat.T, np.eye(vl * 2), atol=1e-14))
+
+    def add(self, w: np.ndarray) -> int:
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        if w.ndim != 4:
+            raise ValueError(f"A valid MPO tensor must have 4 legs while the one given has {w.ndim}.")
+        if w.shape[2] != 2 or w.shape[3] != 2 or w.shape[0] > 2 or w.shape[1] > 2:
+            raise ValueError(f"MPO tensor of shape {w.shape} exceeds the engine's (<=2, <=2, 2, 2) capacity")
+        key = bytes(w.shape) + w.tobytes()
+        if key not in self._ids:
+            self._ids[key] = len(self.data)
+            flat = np.zeros(16)
+            flat[: w.size] = w.ravel()
+            self.data.append(flat)
+            self.dims.append((w.shape[0], w.shape[1], int(self.is_isometric(w)), 0))
+        return self._ids[key]
+
+    def arrays(self) -> Tuple[np.ndarray, np.ndarray]:
+        return (np.ascontiguousarray(np.stack(self.data), dtype=np.float64),
+                np.ascontiguousarray(np.array(self.dims, dtype=np.int32)))
+
+
+@dataclass
+class Program:
+    ops: np.ndarray            # int32 opcode stream
+    wtab: np.ndarray           # float64 [n_tensors, 16]
+    wdim: np.ndarray           # int32 [n_tensors, 4]
+    n_sites: int
+    n_logical: int
+    n_strings: int = 0
+    spans: List[Tuple[int, int]] = field(default_factory=list)
+
+
+def code_site_lists(code):
+    """Constraint-site groups of a CSS code object (duck type: SURVEY.md 8b).
+
+    Returns ``((x_checks, z_checks), (x_logicals, z_logicals))``; every entry is
+    ``[[first], [bulk xor sites], [swap sites], [last]]``.  X-type supports sit at ``2q + k``, Z-type at
+    ``2q + k + 1`` with ``k`` logical sites in front (reference decoding.py:512-696).
+    """
+    k = code.num_x_logicals() + code.num_z_logicals()
+
+    def supports(matrix, offset):
+        return [[2 * int(q) + k + offset for q in sorted(row)] for row in matrix.rows()]
+
+    def check_groups(sup):
+        inner = sup[1:-1]
+        return [[sup[0]], inner, [s for s in range(sup[0] + 1, sup[-1]) if s not in inner], [sup[-1]]]
+
+    def logical_groups(index, sup):
+        bulk = sup[:-1]
+        return [[index], bulk, [s for s in range(index + 1, sup[-1]) if s not in bulk], [sup[-1]]]
+
+    xs, zs = supports(code.x_stabs_binary(), 0), supports(code.z_stabs_binary(), 1)
+    xl, zl = supports(code.x_logicals_binary(), 0), supports(code.z_logicals_binary(), 1)
+    checks = ([check_groups(s) for s in xs], [check_groups(s) for s in zs])
+    logicals = ([logical_groups(i, s) for i, s in enumerate(xl)],
+                [logical_groups(len(xl) + i, s) for i, s in enumerate(zl)])
+    return checks, logicals
+
+
+def order_strings(strings, n_sites: int, strategy: str, order: Optional[Sequence[int]] = None):
+    """"Optimised" reorders the strings (optimiser/utils.py:270-279); "Naive" keeps them."""
+    if strategy != "Optimised":
+        return list(strings)
+    if order is None:
+        loc = np.zeros((len(strings), n_sites), dtype=int)
+        for r, groups in enumerate(strings):
+            for group in groups:
+                for site in group:
+                    loc[r, site] = 1
+        order = msro(loc)
+    return [strings[i] for i in order]
+
+
+def append_strings(ops: List[int], table: TensorTable, strings, tensors, n_sites: int, renormalise: bool,
+                   spans: List[Tuple[int, int]], renorm_spectrum: bool = False) -> None:
+    for groups in strings:
+        cs = ConstraintString(tensors, groups)
+        start, span = cs.start(), cs.span()
+        if span < 2:
+            raise ValueError("a constraint string must cover at least two sites")
+        if start + span > n_sites:
+            raise ValueError(
+                "The length of the MPO should correspond to the number of sites where it is applied, "
+                f"given MPO of length {span} and the starting site {start}, while the MPS has length {n_sites}."
+            )
+        ids = [table.add(cs.constraints[g]) for g in cs.tensor_slots()]
+        ops.extend([OP_SWEEP, start, span, int(bool(renormalise)), int(bool(renorm_spectrum))] + ids)
+        spans.append((start, span))
+
+
+def build_decode_program(code, has_x: bool, has_z: bool, renormalise: bool = True, strategy: str = "Naive",
+                         orders: Optional[dict] = None) -> Program:
+    """Program for ``decode_css`` on errors with the given literal-character flags (decoding.py:1230-1339)."""
+    k = code.num_x_logicals() + code.num_z_logicals()
+    n_sites = 2 * len(code) + k
+    checks, logicals = code_site_lists(code)
+    orders = orders or {}
+    table, ops, spans = TensorTable(), [], []
+    logical_t = [COPY_LEFT, XOR_BULK, SWAP, XOR_RIGHT]
+    check_t = [XOR_LEFT, XOR_BULK, SWAP, XOR_RIGHT]
+    plan = []
+    if has_x:
+        plan.append((logicals[0], logical_t, "xl"))
+    if has_z:
+        plan.append((logicals[1], logical_t, "zl"))
+    if has_x:
+        plan.append((checks[0], check_t, "xc"))
+    if has_z:
+        plan.append((checks[1], check_t, "zc"))
+    for strings, tensors, key in plan:
+        ordered = order_strings(strings, n_sites, strategy, orders.get(key))
+        append_strings(ops, table, ordered, tensors, n_sites, renormalise, spans)
+    ops.extend([OP_MARGINAL, OP_END])
+    if not table.data:
+        table.add(SWAP)  # keep the table non-empty for programs without constraints
+    wtab, wdim = table.arrays()
+    return Program(np.array(ops, dtype=np.int32), wtab, wdim, n_sites, k, len(spans), spans)
+
+
+def error_flags(error: str) -> Tuple[bool, bool, bool]:
+    """(trivial, has_x, has_z) by literal characters, like the reference (decoding.py:1225-1231)."""
+    return error == "I" * len(error), "X" in error, "Z" in error
+
+
+def symbols_from_errors(errors: Sequence[str], n_logical: int) -> np.ndarray:
+    """uint8 [B, k + 2n] product-state symbols: '+' on the logical sites, then the Pauli bits."""
+    n = len(errors[0])
+    out = np.full((len(errors), n_logical + 2 * n), SYM_PLUS, dtype=np.uint8)
+    lut = np.zeros((256, 2), dtype=np.uint8)
+    valid = np.zeros(256, dtype=bool)
+    for ch, bits in _PAULI_BITS.items():
+        lut[ord(ch)] = bits
+        valid[ord(ch)] = True
+    for b, err in enumerate(errors):
+        raw = np.frombuffer(err.encode("ascii"), dtype=np.uint8)
+        if raw.size != n:
+            raise ValueError(f"The error length is {2 * raw.size}, expected {2 * n}.")
+        if not valid[raw].all():
+            bad = err[int(np.argmin(valid[raw]))]
+            if bad == "E":
+                raise NotImplementedError("erasure ('E') errors are not supported by the GPU engine yet")
+            raise ValueError(f"Invalid Pauli encountered -- {bad}.")
+        out[b, n_logical:] = lut[raw].reshape(-1)
+    return out

@@ -1,0 +1,167 @@
+// Host emulation of the block-level engine (mdopt_b200/csrc/*.cuh compiled with -DMDOPT_EMU).
+// TEST INFRASTRUCTURE ONLY: lets the CPU-only test tier exercise the exact index logic, pivoting,
+// truncation rules and program interpreter the CUDA kernels run.  Never linked into libmdopt_b200.so.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/mdopt_b200.h"
+#include "../../mdopt_b200/csrc/mps_core.cuh"
+
+using namespace mdopt;
+
+namespace {
+size_t ws_doubles(int chi, int n_sites) {
+  return (size_t)n_sites * chi * 2 * chi + 2 * (size_t)(2 * chi) * (2 * chi) + (n_sites + 2) / 2 + 8;
+}
+
+template <int CHI>
+int decode_impl(const mdopt_decode_desc* d, const int32_t* program, const double* wtab, const int32_t* wdim,
+                const uint8_t* symbols, int batch, double* dist, int32_t* success, int32_t* status, double* trace,
+                double* counters) {
+  Smem<CHI>* sm = new Smem<CHI>();
+  std::vector<double> ws(ws_doubles(CHI, d->n_sites));
+  Engine<CHI> E(*sm);
+  E.sites = ws.data();
+  E.scr0 = E.sites + (size_t)d->n_sites * Engine<CHI>::SITE_STRIDE;
+  E.scr1 = E.scr0 + (size_t)(2 * CHI) * (2 * CHI);
+  E.bd = reinterpret_cast<int*>(E.scr1 + (size_t)(2 * CHI) * (2 * CHI));
+  E.wtab = wtab;
+  E.wdim = wdim;
+  DecodeParams P;
+  P.n_sites = d->n_sites; P.n_logical = d->n_logical; P.chi_max = d->chi_max; P.mode = d->mode;
+  P.renormalise = d->renormalise; P.trace_stride = d->trace_stride; P.trace_max = d->trace_max;
+  P.n_ops = d->n_ops; P.cut_sweep = d->cut_sweep; P.cut_move = d->cut_move; P.rank_tol = d->rank_tol;
+  P.bias_p = d->bias_p;
+  E.P = P;
+  E.cnt = Counters{0, 0, 0, 0, 0, 0, 0, 0};
+  const int ncls = 1 << d->n_logical;
+  for (int b = 0; b < batch; ++b) {
+    E.trace = (trace && d->trace_stride > 0) ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
+    E.run(program, symbols + (size_t)b * d->n_sites, dist + (size_t)b * ncls, success + b);
+    status[b] = E.status;
+  }
+  if (counters) {
+    counters[0] = E.cnt.flops_qr; counters[1] = E.cnt.flops_jacobi; counters[2] = E.cnt.flops_apply;
+    counters[3] = E.cnt.bytes_hbm; counters[4] = E.cnt.n_steps; counters[5] = E.cnt.n_trunc;
+    counters[6] = E.cnt.n_jacobi_sweeps; counters[7] = 0;
+  }
+  delete sm;
+  return 0;
+}
+
+template <int CHI>
+int svd_impl(int m, int n, const double* a, int chi_max, double cut, double* u, double* sv, double* vh, int* kept) {
+  Smem<CHI>* sm = new Smem<CHI>();
+  Smem<CHI>& s = *sm;
+  constexpr int LD = Smem<CHI>::LD;
+  Counters cnt{0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < m; ++i) for (int c = 0; c < n; ++c) s.X[i * LD + c] = a[i * n + c];
+  jacobi_columns<CHI>(s, m, n, cnt);
+  const int kmax = m < n ? m : n;
+  truncation_rule<CHI>(s, n, chi_max < kmax ? chi_max : kmax, cut);
+  int k = s.iscr[0];
+  *kept = k;
+  for (int j = 0; j < kmax; ++j) {
+    int col = s.order[j];
+    sv[j] = j < k ? s.sig[col] : 0.0;
+    for (int i = 0; i < m; ++i) u[i * kmax + j] = j < k ? s.X[i * LD + col] / s.sig[col] : 0.0;
+    for (int c = 0; c < n; ++c) {
+      double acc = 0.0;
+      if (j < k) { for (int i = 0; i < m; ++i) acc += s.X[i * LD + col] * a[i * n + c]; acc = acc / s.sig[col] / s.sig[col]; }
+      vh[j * n + c] = acc;
+    }
+  }
+  int bad = s.iscr[5];
+  delete sm;
+  return bad;
+}
+
+// QRCP + form Q: returns K; q (m x K, ld kcap), coeff (K x n, ld n)
+template <int CHI>
+int qr_impl(int m, int n, const double* a, int kmax, double rel_tol, double* q, double* coeff, int* more) {
+  Smem<CHI>* sm = new Smem<CHI>();
+  Smem<CHI>& s = *sm;
+  constexpr int LD = Smem<CHI>::LD;
+  Counters cnt{0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < m; ++i) for (int c = 0; c < n; ++c) s.X[i * LD + c] = a[i * n + c];
+  qrcp<CHI>(s, m, n, kmax, rel_tol, cnt);
+  int K = s.iscr[0];
+  *more = s.iscr[1];
+  extract_coeff<CHI>(s, K, n);
+  form_q<CHI>(s, m, K, cnt);
+  for (int i = 0; i < m; ++i) for (int k = 0; k < K; ++k) q[i * K + k] = s.X[i * LD + k];
+  for (int k = 0; k < K; ++k) for (int c = 0; c < n; ++c) coeff[k * n + c] = s.P2[k * LD + c];
+  delete sm;
+  return K;
+}
+
+template <int CHI>
+int program_impl(const mdopt_decode_desc* d, const int32_t* program, const double* wtab, const int32_t* wdim,
+                 double* sites_io, int32_t* bonds_io, int32_t* centre_io, double* dist, int32_t* success,
+                 int32_t* status, double* trace) {
+  Smem<CHI>* sm = new Smem<CHI>();
+  std::vector<double> ws(2 * (size_t)(2 * CHI) * (2 * CHI));
+  Engine<CHI> E(*sm);
+  E.sites = sites_io; E.bd = bonds_io;
+  E.scr0 = ws.data(); E.scr1 = E.scr0 + (size_t)(2 * CHI) * (2 * CHI);
+  E.wtab = wtab; E.wdim = wdim;
+  DecodeParams P;
+  P.n_sites = d->n_sites; P.n_logical = d->n_logical; P.chi_max = d->chi_max; P.mode = d->mode;
+  P.renormalise = d->renormalise; P.trace_stride = d->trace_stride; P.trace_max = d->trace_max;
+  P.n_ops = d->n_ops; P.cut_sweep = d->cut_sweep; P.cut_move = d->cut_move; P.rank_tol = d->rank_tol;
+  P.bias_p = d->bias_p;
+  E.P = P;
+  E.cnt = Counters{0, 0, 0, 0, 0, 0, 0, 0};
+  E.centre = *centre_io; E.mirrored = 0; E.status = ST_OK; E.n_traced = 0;
+  E.trace = (trace && d->trace_stride > 0) ? trace : nullptr;
+  E.run_ops(program, dist, success);
+  *status = E.status; *centre_io = E.centre;
+  delete sm;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+int emu_decode_batch(const mdopt_decode_desc* d, int chi_cap, const int32_t* program, const double* wtab,
+                     const int32_t* wdim, const uint8_t* symbols, int batch, double* dist, int32_t* success,
+                     int32_t* status, double* trace, double* counters) {
+  switch (chi_cap) {
+    case 8: return decode_impl<8>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+    case 16: return decode_impl<16>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+    case 32: return decode_impl<32>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+    case 64: return decode_impl<64>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+  }
+  return -2;
+}
+int emu_mps_program(const mdopt_decode_desc* d, int chi_cap, const int32_t* program, const double* wtab,
+                    const int32_t* wdim, double* sites_io, int32_t* bonds_io, int32_t* centre_io, double* dist,
+                    int32_t* success, int32_t* status, double* trace) {
+  switch (chi_cap) {
+    case 8: return program_impl<8>(d, program, wtab, wdim, sites_io, bonds_io, centre_io, dist, success, status, trace);
+    case 16: return program_impl<16>(d, program, wtab, wdim, sites_io, bonds_io, centre_io, dist, success, status, trace);
+    case 32: return program_impl<32>(d, program, wtab, wdim, sites_io, bonds_io, centre_io, dist, success, status, trace);
+    case 64: return program_impl<64>(d, program, wtab, wdim, sites_io, bonds_io, centre_io, dist, success, status, trace);
+  }
+  return -2;
+}
+int emu_svd(int chi_cap, int m, int n, const double* a, int chi_max, double cut, double* u, double* sv, double* vh,
+            int* kept) {
+  switch (chi_cap) {
+    case 8: return svd_impl<8>(m, n, a, chi_max, cut, u, sv, vh, kept);
+    case 16: return svd_impl<16>(m, n, a, chi_max, cut, u, sv, vh, kept);
+    case 32: return svd_impl<32>(m, n, a, chi_max, cut, u, sv, vh, kept);
+    case 64: return svd_impl<64>(m, n, a, chi_max, cut, u, sv, vh, kept);
+  }
+  return -2;
+}
+int emu_qr(int chi_cap, int m, int n, const double* a, int kmax, double rel_tol, double* q, double* coeff, int* more) {
+  switch (chi_cap) {
+    case 8: return qr_impl<8>(m, n, a, kmax, rel_tol, q, coeff, more);
+    case 16: return qr_impl<16>(m, n, a, kmax, rel_tol, q, coeff, more);
+    case 32: return qr_impl<32>(m, n, a, kmax, rel_tol, q, coeff, more);
+    case 64: return qr_impl<64>(m, n, a, kmax, rel_tol, q, coeff, more);
+  }
+  return -2;
+}
+}

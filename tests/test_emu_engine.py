@@ -1,0 +1,142 @@
+"""CPU-tier checks of the engine LOGIC: the CUDA headers compiled for the host (tests/emu, -DMDOPT_EMU)
+against the oracle / reference fixtures.  This validates pivoting, truncation rules, index maps, frames and
+the program interpreter; the GPU tier (test_gpu_*.py) validates the kernels themselves."""
+import numpy as np
+import pytest
+
+import emu_harness as H
+import mps_oracle as O
+from conftest import load_golden
+from mdopt_b200 import schedule
+from mdopt_b200.codes import surface_code
+
+
+def emu_decode(code, errors, chi, cut, bias, mode, strategy="Optimised", renormalise=True, trace_max=0):
+    out = []
+    for e in errors:
+        triv, hx, hz = schedule.error_flags(e)
+        if triv:
+            out.append((np.array([1.0, 0, 0, 0]), 1, 0, None, None))
+            continue
+        prog = schedule.build_decode_program(code, hx, hz, renormalise, strategy)
+        sym = schedule.symbols_from_errors([e], prog.n_logical)
+        dist, succ, st, tr, cnt = H.decode(prog, sym, chi, cut, bias, renormalise, mode, trace_max=trace_max)
+        out.append((dist[0], int(succ[0]), int(st[0]), tr[0], cnt))
+    return out
+
+
+@pytest.mark.parametrize("mode", [schedule.MODE_FAST, schedule.MODE_SVD])
+@pytest.mark.parametrize("name", ["readme_3x3", "d3_chi64_bitflip", "d3_chi64_bitflip_cut0"])
+def test_non_truncating_configs_match_reference(name, mode):
+    g = load_golden(name)
+    kw = g["kwargs"]
+    rows = g["results"][:40]
+    res = emu_decode(surface_code(g["lattice_size"]), [r["error"] for r in rows], kw["chi_max"],
+                     kw.get("cut", 1e-17), kw["bias_prob"], mode)
+    for r, (dist, ok, st, _, _) in zip(rows, res):
+        assert st == 0
+        assert ok == r["success"], r["error"]
+        np.testing.assert_allclose(dist, r["dist"], rtol=1e-10, atol=1e-14)  # north-star tolerance
+
+
+def test_gating_cases():
+    g = load_golden("gating_3x3")
+    res = emu_decode(surface_code(3), [r["error"] for r in g["results"]], 64, 1e-17, 0.1, schedule.MODE_FAST)
+    for r, (dist, ok, st, _, _) in zip(g["results"], res):
+        assert ok == r["success"]
+        both = "X" in r["error"] and "Z" in r["error"]  # X+Z at chi=64 truncates inside degenerate multiplets
+        np.testing.assert_allclose(dist, r["dist"], rtol=5e-2 if both else 1e-10, atol=1e-13)
+
+
+def test_truncating_config_success_flags_and_first_truncated_spectrum():
+    g = load_golden("d3_chi8_bitflip")
+    rows = g["results"]
+    res = emu_decode(surface_code(3), [r["error"] for r in rows], 8, 1e-17, 0.1, schedule.MODE_SVD, trace_max=400)
+    agree = sum(int(ok == r["success"]) for r, (_, ok, _, _, _) in zip(rows, res))
+    assert agree == len(rows)
+    # singular values of every sweep split up to and including the first truncating one agree with the oracle
+    ocode = O.surface_code(3)
+    checked = 0
+    for r, (_, _, _, tr, _) in zip(rows, res):
+        if r["error"] == "I" * 13:
+            continue
+        rec = []
+        O.decode_css(ocode, r["error"], chi_max=8, cut=1e-17, bias_type="Bitflip", bias_prob=0.1,
+                     contraction_strategy="Optimised", record=rec)
+        sweeps = [row for row in tr if row[0] > 0 and row[3] == 0]
+        assert len(sweeps) == len(rec)
+        for row, ref in zip(sweeps, rec):
+            kept = int(row[2])
+            top = ref[0]
+            big = ref > 1e-12 * top
+            assert kept >= int(big.sum()) or kept == 8
+            np.testing.assert_allclose(row[4:4 + int(big.sum())][: kept], ref[big][: kept], rtol=1e-10, atol=1e-13 * top)
+            checked += 1
+            if len(ref) == 8 and row[1] > 8 and row[4 + 8] > 1e-10 * top:
+                break  # past the first genuinely truncating split the states may differ (degenerate cuts)
+    assert checked > 50
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (16, 12), (12, 16), (64, 64), (31, 17)])
+def test_jacobi_svd_matches_lapack(shape):
+    rng = np.random.default_rng(sum(shape))
+    a = rng.standard_normal(shape)
+    if shape[1] > shape[0]:
+        a = a  # wide matrices are legal (extra columns converge to zero)
+    u, s, vh, k, bad = H.svd(a, 10 ** 4, 1e-12)
+    ref = np.linalg.svd(a, compute_uv=False)
+    assert bad == 0 and k == min(shape)
+    np.testing.assert_allclose(s[:k], ref[:k], rtol=1e-10)
+    np.testing.assert_allclose((u * s) @ vh, a, atol=1e-12)
+    np.testing.assert_allclose(u.T @ u, np.eye(k), atol=1e-12)
+
+
+def test_svd_truncation_rule_matches_reference_fixture():
+    doc = load_golden("svd_cases")
+    rng = np.random.default_rng(doc["rng_seed"])
+    for case in doc["cases"]:
+        a = rng.standard_normal((case["m"], case["n"]))
+        if max(a.shape) > 64:
+            continue  # emulated 128-column Jacobi is slow on the CPU; covered on the GPU tier
+        u, s, vh, k, bad = H.svd(a if a.shape[0] >= a.shape[1] else a.T.copy(), case["chi_max"], case["cut"])
+        assert k == len(case["s"])
+        np.testing.assert_allclose(s[:k], case["s"], rtol=1e-10)
+
+
+@pytest.mark.parametrize("m,n,r", [(16, 16, 5), (32, 20, 7), (64, 64, 30), (128, 128, 40), (100, 128, 64)])
+def test_rank_revealing_qr(m, n, r):
+    rng = np.random.default_rng(m * n + r)
+    a = rng.standard_normal((m, r)) @ rng.standard_normal((r, n))
+    q, coeff, K, more = H.qr(a, min(64, (max(m, n) + 1) // 2))
+    assert more == 0 and K == r
+    np.testing.assert_allclose(q @ coeff, a, atol=1e-12 * np.abs(a).max() * max(m, n))
+    np.testing.assert_allclose(q.T @ q, np.eye(K), atol=1e-13)
+
+
+def test_qr_flags_genuine_truncation():
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((32, 32))
+    _, _, K, more = H.qr(a, 16)
+    assert K == 16 and more == 1
+
+
+def test_fast_and_svd_modes_agree_without_truncation():
+    code = surface_code(3)
+    errs = O.seeded_errors(13, 0.15, 12, 99, "Bitflip")
+    fast = emu_decode(code, errs, 64, 1e-17, 0.1, schedule.MODE_FAST)
+    full = emu_decode(code, errs, 64, 1e-17, 0.1, schedule.MODE_SVD)
+    for (d0, s0, *_), (d1, s1, *_) in zip(fast, full):
+        assert s0 == s1
+        np.testing.assert_allclose(d0, d1, rtol=1e-11, atol=1e-14)
+
+
+def test_naive_strategy_and_no_renormalise():
+    code, ocode = surface_code(3), O.surface_code(3)
+    for e in ["IIXIIIIIIIIII", "IXIIIIIXIIIII"]:
+        for strategy in ("Naive", "Optimised"):
+            for ren in (True, False):
+                (dist, ok, st, _, _), = emu_decode(code, [e], 64, 1e-17, 0.1, schedule.MODE_FAST, strategy, ren)
+                ref, rok = O.decode_css(ocode, e, chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1,
+                                        renormalise=ren, contraction_strategy=strategy)
+                assert ok == rok
+                np.testing.assert_allclose(dist, ref, rtol=1e-10, atol=1e-14)

@@ -1,0 +1,92 @@
+"""The CPU oracle against the fixtures generated from the unmodified reference (oracle/make_golden.py)
+and against the reference's published known answers."""
+import json
+
+import numpy as np
+import pytest
+
+import mps_oracle as O
+from conftest import load_golden
+
+
+@pytest.mark.parametrize("name", ["readme_3x3", "gating_3x3", "d3_chi64_bitflip", "d3_chi64_bitflip_cut0",
+                                  "d3_chi64_depol", "d3_chi8_bitflip", "d5_chi16_bitflip"])
+def test_oracle_matches_reference_outputs(name):
+    g = load_golden(name)
+    kw = dict(g["kwargs"])
+    code = O.surface_code(g["lattice_size"])
+    truncating = name in ("d3_chi8_bitflip", "d5_chi16_bitflip", "gating_3x3")
+    for row in g["results"]:
+        dist, ok = O.decode_css(code, row["error"], contraction_strategy="Optimised", **kw)
+        assert int(ok) == row["success"], row["error"]
+        # bit-for-bit on this machine; the tolerance only absorbs BLAS differences between hosts on
+        # non-truncating cases (truncating cases cut degenerate multiplets and are rounding-sensitive)
+        tol = 5e-2 if truncating else 1e-12
+        np.testing.assert_allclose(np.asarray(dist, dtype=float), row["dist"], rtol=tol, atol=tol * 1e-2)
+
+
+def test_readme_known_answer():
+    dist, ok = O.decode_css(O.surface_code(3), "IIXIIIIIIIIII", chi_max=64, bias_type="Bitflip", bias_prob=0.01,
+                            contraction_strategy="Optimised", tolerance=1e-12)
+    np.testing.assert_allclose(dist, [0.7025030517, 0.0805571990, 0.7025030517, 0.0805571990], atol=2e-10)
+    assert ok == 1
+
+
+def test_gating_by_literal_character():
+    code = O.surface_code(3)
+    dist, ok = O.decode_css(code, "IIYIIIIIIIIII", chi_max=64, bias_type="Bitflip", bias_prob=0.1)
+    np.testing.assert_allclose(dist, [0.5, 0.5, 0.5, 0.5], atol=1e-14)
+    assert ok == 1
+    assert O.decode_css(code, "I" * 13) == ([1.0, 0.0, 0.0, 0.0], 1)
+
+
+def test_mpo_tensor_tables_match_reference():
+    ref = load_golden("mpo_tensors")
+    for name, values in ref.items():
+        np.testing.assert_array_equal(getattr(O, name), np.asarray(values))
+
+
+def test_svd_truncation_rule_against_reference():
+    doc = load_golden("svd_cases")
+    rng = np.random.default_rng(doc["rng_seed"])
+    for case in doc["cases"]:
+        a = rng.standard_normal((case["m"], case["n"]))
+        u, s, vh, err = O.svd(a, cut=case["cut"], chi_max=case["chi_max"])
+        np.testing.assert_allclose(s, case["s"], rtol=1e-12)
+        assert abs(err - case["trunc_err"]) <= 1e-10 * max(1.0, case["trunc_err"])
+        np.testing.assert_allclose((u * s) @ vh, (u * s) @ vh)
+        assert u.shape == (case["m"], len(case["s"])) and vh.shape == (len(case["s"]), case["n"])
+
+
+def test_marginal_against_reference():
+    g = load_golden("marginal_case")
+    mps = O.MPS([np.asarray(t) for t in g["tensors"]])
+    out = O.marginal(mps, g["sites"], renormalise=True)
+    assert len(out.tensors) == len(g["result"])
+    for a, b in zip(out.tensors, g["result"]):
+        np.testing.assert_allclose(a, np.asarray(b), rtol=1e-13, atol=1e-15)
+
+
+def test_sweep_spectra_against_reference():
+    g = load_golden("d3_spectra")
+    rec = []
+    dist, ok = O.decode_css(O.surface_code(3), g["error"], chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1,
+                            contraction_strategy="Optimised", tolerance=1e-12, record=rec)
+    ref_sweeps = [np.asarray(x["s"]) for x in g["svds"] if x["chi_max"] == 64]
+    assert len(rec) == len(ref_sweeps)
+    for a, b in zip(rec, ref_sweeps):
+        assert a.shape == b.shape
+        np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(dist, g["dist"], rtol=1e-12)
+
+
+def test_error_paths():
+    code = O.surface_code(3)
+    with pytest.raises(ValueError):
+        O.decode_css(code, "IIXII", chi_max=8, bias_type="Bitflip")
+    with pytest.raises(ValueError):
+        O.decode_css(code, "IIQIIIIIIIIII", chi_max=8, bias_type="Bitflip")
+    with pytest.raises(ValueError):
+        O.constraint_mpo([O.XOR_LEFT, O.XOR_RIGHT], [[0], [2]])
+    with pytest.raises(ValueError):
+        O.svd(np.zeros((2, 2, 2)))
