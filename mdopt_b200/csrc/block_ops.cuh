@@ -442,4 +442,182 @@ MD_DEV void truncation_rule(Smem<CHI>& s, int C, int chi_lim, double cut) {
   MD_SYNC();
 }
 
+
+#ifndef MDOPT_EMU
+// =================================================================================================
+// Device-only fast path: the same Householder QR with column pivoting, with the matrix held in
+// REGISTERS (4 threads per column, rows interleaved mod 4) and warp shuffles for every reduction.
+// Per reflector: one 4-lane serial section (pivot column -> v, tau), two CTA barriers, and an
+// embarrassingly parallel rank-1 update.  Reflectors are kept in shared memory (s.P2 viewed as
+// Vall[K][N2]) for the Q formation, which runs in registers with no barriers at all.
+//   in : orig (R x C, row-major ld C, global)
+//   out: s.X[k*LD + c] = coefficient of original column c on basis vector k  (k < K)
+//        s.P2 = Vall, s.tau;  s.iscr[0] = K, s.iscr[1] = genuine-truncation flag
+// Pivot rule and stop rule are identical to qrcp<> above (largest remaining column norm, ties to the
+// lowest column index; stop at rel_tol * largest initial norm or at kmax).
+// =================================================================================================
+template <int CHI>
+__device__ __forceinline__ void qrcp_reg(Smem<CHI>& s, const double* __restrict__ orig, int R, int C, int kmax,
+                                         double rel_tol, Counters& cnt) {
+  constexpr int LD = Smem<CHI>::LD;
+  constexpr int N2 = Smem<CHI>::N2;
+  constexpr int RPT = N2 / 4;  // rows per thread
+  const int tid = threadIdx.x;
+  const int col = tid >> 2, part = tid & 3, lane = tid & 31;
+  const unsigned gmask = 0xFu << (lane & ~3);
+  const bool col_ok = col < C;
+  double* Vall = s.P2;
+  double x[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    int r = 4 * i + part;
+    x[i] = (col_ok && r < R) ? orig[(size_t)r * C + col] : 0.0;
+  }
+  {
+    double nn = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) nn += x[i] * x[i];
+    nn += __shfl_xor_sync(0xffffffffu, nn, 1);
+    nn += __shfl_xor_sync(0xffffffffu, nn, 2);
+    if (part == 0) s.vn1[col] = col_ok ? sqrt(nn) : -1.0;
+  }
+  __syncthreads();
+  double thresh = 0.0;
+  const int jmax = min(R, C);
+  int K = 0, more = 0;
+  bool done = !col_ok;
+  for (int j = 0; j < jmax; ++j) {
+    // ---- pivot: arg-max of the remaining column norms, computed redundantly by every warp ----
+    double best = -1.0;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < N2; c += 32) {
+      double v = s.vn1[c];
+      if (v > best || (v == best && c < bi)) { best = v; bi = c; }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      double ov = __shfl_xor_sync(0xffffffffu, best, off);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (j == 0) thresh = best * rel_tol;
+    if (!(best > thresh)) break;
+    if (j >= kmax) { more = 1; break; }
+    const int pv = bi;
+    const int jp = j & 3, ji = j >> 2;
+    const bool owner = (col == pv);
+    if (owner) {
+      double a = 0.0, ss = 0.0;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        if (i == ji) a = x[i];
+        if (4 * i + part > j) ss += x[i] * x[i];
+      }
+      a = __shfl_sync(gmask, a, (lane & ~3) | jp);
+      ss += __shfl_xor_sync(gmask, ss, 1);
+      ss += __shfl_xor_sync(gmask, ss, 2);
+      double tau = 0.0, scal = 0.0, beta = a;
+      if (ss != 0.0) {
+        beta = -copysign(sqrt(a * a + ss), a);
+        tau = (beta - a) / beta;
+        scal = 1.0 / (a - beta);
+      }
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        int r = 4 * i + part;
+        double v = (r > j) ? x[i] * scal : ((r == j) ? 1.0 : 0.0);
+        Vall[j * N2 + r] = v;
+        if (r == j) x[i] = beta;
+        else if (r > j) x[i] = 0.0;
+      }
+      if (part == 0) s.tau[j] = tau;
+    }
+    __syncthreads();
+    {
+      // ---- apply H_j to every open column (done / padded columns run the arithmetic but keep x) ----
+      const double tau = s.tau[j];
+      const double* vj = Vall + j * N2 + part;
+      double w = 0.0;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) w += vj[4 * i] * x[i];
+      w += __shfl_xor_sync(0xffffffffu, w, 1);
+      w += __shfl_xor_sync(0xffffffffu, w, 2);
+      w *= tau;
+      double nn = 0.0;
+      const bool open = !done && !owner;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        double xn = x[i] - w * vj[4 * i];
+        if (open) x[i] = xn;
+        if (4 * i + part > j) nn += xn * xn;
+      }
+      nn += __shfl_xor_sync(0xffffffffu, nn, 1);
+      nn += __shfl_xor_sync(0xffffffffu, nn, 2);
+      if (part == 0) {
+        if (open) s.vn1[col] = sqrt(nn);
+        else if (owner) s.vn1[col] = -1.0;
+      }
+      if (owner) done = true;
+    }
+    __syncthreads();
+    K = j + 1;
+  }
+  if (!more) {
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      int r = 4 * i + part;
+      if (col_ok && r < K) s.X[r * LD + col] = x[i];
+    }
+  }
+  if (tid == 0) {
+    s.iscr[0] = K; s.iscr[1] = more;
+    double f = 2.0 * R * C;
+    for (int j = 0; j < K; ++j) f += 4.0 * (R - j) * (C - j - 1) + 3.0 * (R - j);
+    cnt.flops_qr += f;
+  }
+  __syncthreads();
+}
+
+// Q = H_0 ... H_{K-1} [I_K; 0] in registers (8 threads per column, rows interleaved mod 8), written to
+// s.P2 as a flat R x K matrix (ld K) after every thread has finished reading the reflectors from it.
+template <int CHI>
+__device__ __forceinline__ void form_q_reg(Smem<CHI>& s, int R, int K, Counters& cnt) {
+  constexpr int N2 = Smem<CHI>::N2;
+  constexpr int RPT = N2 / 8;
+  const int tid = threadIdx.x;
+  const int col = tid >> 3, part = tid & 7;
+  const double* Vall = s.P2;
+  double q[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) q[i] = (8 * i + part == col) ? 1.0 : 0.0;
+  for (int j = K - 1; j >= 0; --j) {
+    const double tau = s.tau[j];
+    const double* vj = Vall + j * N2 + part;
+    double w = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) w += vj[8 * i] * q[i];
+    w += __shfl_xor_sync(0xffffffffu, w, 1);
+    w += __shfl_xor_sync(0xffffffffu, w, 2);
+    w += __shfl_xor_sync(0xffffffffu, w, 4);
+    w *= tau;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) q[i] -= w * vj[8 * i];
+  }
+  __syncthreads();
+  if (col < K) {
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      int r = 8 * i + part;
+      if (r < R) s.P2[r * K + col] = q[i];
+    }
+  }
+  if (tid == 0) {
+    double f = 0.0;
+    for (int j = 0; j < K; ++j) f += 4.0 * (R - j) * (K - 1 - j) + 2.0 * (R - j);
+    cnt.flops_qr += f;
+  }
+  __syncthreads();
+}
+#endif  // !MDOPT_EMU
+
 }  // namespace mdopt

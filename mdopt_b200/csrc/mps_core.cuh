@@ -181,20 +181,42 @@ struct Engine {
 
   // ---- factor X (R x C; a copy lives in `orig`, flat ld C) -> Knew, U (in X), coefficients (in P2) ----
   // Returns Knew.  s.iscr[7] = 1 when U columns are addressed through s.order / scaled by 1/s.sig.
+  // Layout of the result (s.iscr[7]):
+  //   0  U = s.X[:, 0:K] (ld LD),               coefficients = s.P2 (ld LD)     [portable QR path]
+  //   1  U = s.X[:, order[k]] / sig[order[k]],   coefficients = s.P2 (ld LD)     [Jacobi SVD path]
+  //   2  U = s.P2 flat (ld K),                   coefficients = s.X rows (ld LD) [register QR path]
   MD_DEV int factor(const double* orig, int R, int C, int chi_lim, double cut, int is_move) {
     int use_svd = (P.mode == MODE_SVD);
     int Knew = 0;
+    const int kmax = chi_lim < CHI ? chi_lim : CHI;
     if (!use_svd) {
-      qrcp<CHI>(s, R, C, chi_lim < CHI ? chi_lim : CHI, P.rank_tol, cnt);
+#ifndef MDOPT_EMU
+      qrcp_reg<CHI>(s, orig, R, C, kmax, P.rank_tol, cnt);
+#else
+      load_x(orig, R, C);
+      qrcp<CHI>(s, R, C, kmax, P.rank_tol, cnt);
+#endif
       Knew = s.iscr[0];
       if (s.iscr[1]) {  // more than chi_lim significant directions: genuine truncation needed
         use_svd = 1;
-        load_x(orig, R, C);
         MD_LEADER { cnt.n_trunc += 1.0; }
       }
     }
     if (!use_svd) {
+#ifndef MDOPT_EMU
       if (Knew == 0) {  // zero matrix: keep a single zero direction (the state has zero norm)
+        MD_PAR_FOR(i, R) s.P2[i] = (i == 0) ? 1.0 : 0.0;
+        MD_PAR_FOR(c, C) s.X[c] = 0.0;
+        MD_LEADER { s.iscr[7] = 2; }
+        MD_SYNC();
+        return 1;
+      }
+      form_q_reg<CHI>(s, R, Knew, cnt);
+      MD_LEADER { s.iscr[7] = 2; }
+      MD_SYNC();
+      return Knew;
+#else
+      if (Knew == 0) {
         MD_PAR_FOR(i, R) s.X[i * LD] = (i == 0) ? 1.0 : 0.0;
         MD_PAR_FOR(c, C) s.P2[c] = 0.0;
         MD_LEADER { s.iscr[7] = 0; }
@@ -206,7 +228,9 @@ struct Engine {
       MD_LEADER { s.iscr[7] = 0; }
       MD_SYNC();
       return Knew;
+#endif
     }
+    load_x(orig, R, C);
     // ---- Jacobi SVD path ----
     jacobi_columns<CHI>(s, R, C, cnt);
     if (s.iscr[5]) status = ST_NOT_CONVERGED;
@@ -254,21 +278,23 @@ struct Engine {
   }
 
   // ---- site j <- U (R = K*2 rows, Knew columns), frame layout (k, r, k') ----
+  MD_DEV double u_at(int lay, int row, int kn, int Knew) const {
+    if (lay == 2) return s.P2[row * Knew + kn];
+    if (lay == 1) return s.X[row * LD + s.order[kn]] / s.sig[s.order[kn]];
+    return s.X[row * LD + kn];
+  }
   MD_DEV void store_u(int j, int Kl, int Knew) {
     double* dst = sites + (size_t)phys(j) * SITE_STRIDE;
-    const int ord = s.iscr[7];
+    const int lay = s.iscr[7];
     if (!mirrored) {
       MD_PAR_FOR(g, Kl * 2 * Knew) {
         int kn = g % Knew, row = g / Knew;
-        double v = ord ? s.X[row * LD + s.order[kn]] / s.sig[s.order[kn]] : s.X[row * LD + kn];
-        dst[g] = v;
+        dst[g] = u_at(lay, row, kn, Knew);
       }
     } else {  // phys tensor dims (Knew, 2, Kl)
       MD_PAR_FOR(g, Kl * 2 * Knew) {
         int k = g % Kl; int r = g / Kl; int p = r & 1; int kn = r >> 1;
-        int row = k * 2 + p;
-        double v = ord ? s.X[row * LD + s.order[kn]] / s.sig[s.order[kn]] : s.X[row * LD + kn];
-        dst[g] = v;
+        dst[g] = u_at(lay, k * 2 + p, kn, Knew);
       }
     }
     MD_LEADER { cnt.bytes_hbm += 8.0 * Kl * 2 * Knew; }
@@ -293,13 +319,15 @@ struct Engine {
       C = 2 * vr * Bn;
       orig = scr1;
     }
-    load_x(orig, R, C);
     int Knew = factor(orig, R, C, chi_lim, cut, is_move);
     if (status == ST_CAPACITY) return;
+    const int lay = s.iscr[7];
+    double* coef = (lay == 2) ? s.X : s.P2;                 // coefficients M' (Knew x C, ld LD)
+    double* stage = (lay == 2) ? (s.X + CHI * LD) : s.X;    // staging area for the next site tensor
     if (renorm_sv) {  // mps_mpo_contract(renormalise=True): s /= ||s|| (utils.py:126-129); ||s|| = ||M'||_F
       MD_PAR_FOR(ch, 256) {
         double acc = 0.0;
-        for (int t = ch; t < Knew * C; t += 256) { int k = t / C, c = t - k * C; double v = s.P2[k * LD + c]; acc += v * v; }
+        for (int t = ch; t < Knew * C; t += 256) { int k = t / C, c = t - k * C; double v = coef[k * LD + c]; acc += v * v; }
         s.part[ch] = acc;
       }
       MD_SYNC();
@@ -310,15 +338,15 @@ struct Engine {
       }
       MD_SYNC();
       const double inv = s.dscr[4];
-      MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; s.P2[k * LD + c] *= inv; }
+      MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; coef[k * LD + c] *= inv; }
       MD_SYNC();
     }
     store_u(jn - 1, K, Knew);
     if (iso) {
-      stage_site(jn, s.X, Mr, Bn);
-      apply_site(s.P2, LD, Knew, vl, vr, Mr, Bn, s.X, scr0);
+      stage_site(jn, stage, Mr, Bn);
+      apply_site(coef, LD, Knew, vl, vr, Mr, Bn, stage, scr0);
     } else {
-      MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; scr0[t] = s.P2[k * LD + c]; }
+      MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; scr0[t] = coef[k * LD + c]; }
       MD_LEADER { cnt.bytes_hbm += 8.0 * Knew * C; }
       MD_SYNC();
     }

@@ -44,8 +44,14 @@ def css_code_logicals_sites(code):
     return schedule.code_site_lists(code)[1]
 
 
+def _code_key(code) -> Tuple:
+    """Structural identity of a code object (object ids are recycled once a code is garbage collected)."""
+    mats = (code.x_stabs_binary(), code.z_stabs_binary(), code.x_logicals_binary(), code.z_logicals_binary())
+    return (len(code),) + tuple(tuple(tuple(int(c) for c in row) for row in m.rows()) for m in mats)
+
+
 def _program_for(code, has_x, has_z, renormalise, strategy, orders) -> schedule.Program:
-    key = (id(code), has_x, has_z, bool(renormalise), strategy,
+    key = (_code_key(code), has_x, has_z, bool(renormalise), strategy,
            None if not orders else tuple(sorted((k, tuple(v)) for k, v in orders.items())))
     if key not in _PROGRAM_CACHE:
         _PROGRAM_CACHE[key] = schedule.build_decode_program(code, has_x, has_z, renormalise, strategy, orders)
