@@ -276,6 +276,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": counters["bytes"],
                          "achieved_gbs": counters["bytes"] / kernel_s / 1e9,
                          "steps_per_launch": counters["steps"], "truncating_steps": counters["truncating_steps"],
+                         "cycle_split": {k2: counters[k2] for k2 in counters if k2.startswith("cyc_")},
+                         "qr_reflectors": counters["qr_reflectors"], "jacobi_sweeps": counters["jacobi_sweeps"],
                          "reference_algorithm_equiv_tflops": REF_FLOP_PER_NONTRIVIAL * len(nontriv) / kernel_s / 1e12},
             "clocks": sampler.summary(),
             "counts": {"decoded": int(counts[0]), "success": int(counts[1]), "nan": int(counts[2]),

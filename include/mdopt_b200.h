@@ -87,8 +87,10 @@ size_t mdopt_decode_workspace_bytes(int chi_cap, int n_sites, int n_ctas);
  *   success   int32[batch]            out: tolerant arg-max flag (device)
  *   status    int32[batch]            out: MDOPT_ST_* (device)
  *   trace     double[batch*trace_max*trace_stride] or NULL (device)
- *   counters  double[8] or NULL       out: summed work counters {flops_qr, flops_jacobi, flops_apply,
- *                                     bytes, steps, truncating steps, jacobi sweeps, 0} (device)
+ *   counters  double[16] or NULL      out: summed work counters {flops_qr, flops_jacobi, flops_apply,
+ *                                     bytes, steps, truncating steps, jacobi sweeps, qr reflectors, then
+ *                                     leader-thread cycle counts: qr, form_q, jacobi, apply, io, coef,
+ *                                     total, 0} (device)
  *   workspace mdopt_decode_workspace_bytes() bytes (device)
  */
 int mdopt_decode_batch_device(const mdopt_decode_desc* desc, int chi_cap, int n_ctas, const int32_t* program,

@@ -46,7 +46,47 @@ struct Counters {
   double n_steps;       // two-site steps (sweep + move)
   double n_trunc;       // steps that needed the truncating SVD
   double n_jacobi_sweeps;
-  double pad;
+  double n_qr_reflectors;
+  // leader-thread clock64() deltas per phase (device build only)
+  double cyc_qr, cyc_formq, cyc_jacobi, cyc_apply, cyc_io, cyc_coef, cyc_total, cyc_pad;
+};
+
+#ifdef MDOPT_EMU
+#define MD_CLOCK() 0ll
+#else
+#define MD_CLOCK() clock64()
+#endif
+
+struct DecodeParams {
+  int n_sites;        // MPS length N
+  int n_logical;      // number of logical sites kL (they are sites 0..kL-1)
+  int chi_max;        // user chi_max for sweeps
+  int mode;           // MODE_FAST / MODE_SVD
+  int renormalise;    // decode_css(renormalise=...)
+  int trace_stride;   // doubles per traced step (0 = no trace)
+  int trace_max;      // max traced steps per syndrome
+  int n_ops;          // length of the program in ints
+  double cut_sweep;   // user cut for sweep splits
+  double cut_move;    // 1e-12 (reference default of split_two_site_tensor inside move_orth_centre)
+  double rank_tol;    // MODE_FAST relative rank threshold
+  double bias_p;      // bit-flip bias probability; < 0 disables the bias
+};
+
+// Persistent per-CTA engine state (shared memory; see Engine in mps_core.cuh).
+struct EngineState {
+  double* sites;       // [N][SITE_STRIDE], packed (vL, p, vR) row-major per site
+  double* scr0;        // carried matrix, flat (global, L2-resident)
+  double* scr1;        // theta scratch for non-isometric steps
+  int* bd;             // [N+1] bond dimensions (global, per CTA)
+  const double* wtab;  // [n_tensors][16]
+  const int* wdim;     // [n_tensors][4] = vL, vR, iso, pad
+  double* trace;       // per-syndrome trace block or nullptr
+  DecodeParams P;
+  int n_traced;
+  int status;
+  int centre;
+  int K, Wq, Mr;       // carried-matrix dimensions: M(K, 2, Wq, Mr)
+  int mirrored;        // frame: 0 normal, 1 mirrored (moving the centre left)
 };
 
 template <int CHI>
@@ -64,6 +104,8 @@ struct Smem {
   static constexpr int NFLAG = (N2 > 32) ? N2 : 32;
   int perm[N2], order[N2], flag[NFLAG];
   int iscr[16];
+  Counters cnt;   // leader-only work counters of this CTA
+  EngineState st;
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -74,7 +116,7 @@ struct Smem {
 //   residual above the threshold (i.e. a genuine truncation is required).
 // -------------------------------------------------------------------------------------------------
 template <int CHI>
-MD_DEV void qrcp(Smem<CHI>& s, int R, int C, int kmax, double rel_tol, Counters& cnt) {
+MD_DEV void qrcp(Smem<CHI>& s, int R, int C, int kmax, double rel_tol) {
   constexpr int LD = Smem<CHI>::LD;
   constexpr int N2 = Smem<CHI>::N2;
   double* X = s.X;
@@ -99,7 +141,7 @@ MD_DEV void qrcp(Smem<CHI>& s, int R, int C, int kmax, double rel_tol, Counters&
     for (int c = 0; c < C; ++c) mx = fmax(mx, s.vn1[c]);
     s.dscr[0] = mx * rel_tol;  // absolute stop threshold
     s.iscr[0] = 0; s.iscr[1] = 0;
-    cnt.flops_qr += 2.0 * R * C;
+    s.cnt.flops_qr += 2.0 * R * C;
   }
   MD_SYNC();
   const double thresh = s.dscr[0];
@@ -157,7 +199,7 @@ MD_DEV void qrcp(Smem<CHI>& s, int R, int C, int kmax, double rel_tol, Counters&
       }
       s.tau[j] = tau; s.dscr[1] = scal;
       X[j * LD + j] = beta;
-      cnt.flops_qr += 4.0 * (R - j) * (C - j - 1) + 3.0 * (R - j);
+      s.cnt.flops_qr += 4.0 * (R - j) * (C - j - 1) + 3.0 * (R - j);
     }
     MD_SYNC();
     const double tau = s.tau[j];
@@ -238,7 +280,7 @@ MD_DEV void extract_coeff(Smem<CHI>& s, int K, int C) {
 
 // Form the first K columns of Q in place over the reflectors (LAPACK dorg2r data flow).
 template <int CHI>
-MD_DEV void form_q(Smem<CHI>& s, int R, int K, Counters& cnt) {
+MD_DEV void form_q(Smem<CHI>& s, int R, int K) {
   constexpr int LD = Smem<CHI>::LD;
   constexpr int N2 = Smem<CHI>::N2;
   double* X = s.X;
@@ -281,7 +323,7 @@ MD_DEV void form_q(Smem<CHI>& s, int R, int K, Counters& cnt) {
       else v = -tau * X[i * LD + j];
       X[i * LD + j] = v;
     }
-    MD_LEADER { cnt.flops_qr += 4.0 * len * nt + 2.0 * len; }
+    MD_LEADER { s.cnt.flops_qr += 4.0 * len * nt + 2.0 * len; }
     MD_SYNC();
   }
 }
@@ -293,7 +335,7 @@ MD_DEV void form_q(Smem<CHI>& s, int R, int K, Counters& cnt) {
 //   index).  Returns the number of sweeps in s.iscr[4]; s.iscr[5] = 1 when it did not converge.
 // -------------------------------------------------------------------------------------------------
 template <int CHI>
-MD_DEV void jacobi_columns(Smem<CHI>& s, int R, int C, Counters& cnt, int max_sweeps = 60) {
+MD_DEV void jacobi_columns(Smem<CHI>& s, int R, int C, int max_sweeps = 60) {
   constexpr int LD = Smem<CHI>::LD;
   constexpr int N2 = Smem<CHI>::N2;
   double* X = s.X;
@@ -382,7 +424,7 @@ MD_DEV void jacobi_columns(Smem<CHI>& s, int R, int C, Counters& cnt, int max_sw
         int nrot = 0;
         for (int k = 0; k < npair; ++k) nrot += s.flag[k];
         s.iscr[6] += nrot;
-        cnt.flops_jacobi += 6.0 * R * npair + 6.0 * R * nrot;
+        s.cnt.flops_jacobi += 6.0 * R * npair + 6.0 * R * nrot;
       }
       MD_SYNC();
     }
@@ -416,8 +458,8 @@ MD_DEV void jacobi_columns(Smem<CHI>& s, int R, int C, Counters& cnt, int max_sw
   }
   MD_LEADER {
     s.iscr[4] = sweeps; s.iscr[5] = converged ? 0 : 1;
-    cnt.n_jacobi_sweeps += sweeps;
-    cnt.flops_jacobi += 2.0 * R * C;
+    s.cnt.n_jacobi_sweeps += sweeps;
+    s.cnt.flops_jacobi += 2.0 * R * C;
   }
   MD_SYNC();
 }
@@ -457,35 +499,38 @@ MD_DEV void truncation_rule(Smem<CHI>& s, int C, int chi_lim, double cut) {
 // lowest column index; stop at rel_tol * largest initial norm or at kmax).
 // =================================================================================================
 template <int CHI>
-__device__ __forceinline__ void qrcp_reg(Smem<CHI>& s, const double* __restrict__ orig, int R, int C, int kmax,
-                                         double rel_tol, Counters& cnt) {
+__device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, int C, int kmax, double rel_tol) {
   constexpr int LD = Smem<CHI>::LD;
   constexpr int N2 = Smem<CHI>::N2;
-  constexpr int RPT = N2 / 4;  // rows per thread
+  constexpr int RPT = N2 / 4;               // register rows per thread
+  constexpr int CH = RPT < 8 ? RPT : 8;     // register rows per chunk
+  constexpr int NCHK = RPT / CH;            // chunk c covers matrix rows [4*CH*c, 4*CH*(c+1))
+  // register slot idx = 2*i2 + e holds matrix row 8*i2 + 2*part + e (pairs of rows -> 16-byte LDS of v)
   const int tid = threadIdx.x;
   const int col = tid >> 2, part = tid & 3, lane = tid & 31;
-  const unsigned gmask = 0xFu << (lane & ~3);
   const bool col_ok = col < C;
   double* Vall = s.P2;
   double x[RPT];
 #pragma unroll
-  for (int i = 0; i < RPT; ++i) {
-    int r = 4 * i + part;
-    x[i] = (col_ok && r < R) ? orig[(size_t)r * C + col] : 0.0;
+  for (int idx = 0; idx < RPT; ++idx) {
+    int r = 8 * (idx >> 1) + 2 * part + (idx & 1);
+    x[idx] = (col_ok && r < R) ? orig[(size_t)r * C + col] : 0.0;
   }
+  double nrm_me;  // norm of the not-yet-eliminated part of this thread group's column
   {
     double nn = 0.0;
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) nn += x[i] * x[i];
+    for (int idx = 0; idx < RPT; ++idx) nn += x[idx] * x[idx];
     nn += __shfl_xor_sync(0xffffffffu, nn, 1);
     nn += __shfl_xor_sync(0xffffffffu, nn, 2);
-    if (part == 0) s.vn1[col] = col_ok ? sqrt(nn) : -1.0;
+    nrm_me = sqrt(nn);
+    if (part == 0) s.vn1[col] = col_ok ? nrm_me : -1.0;
   }
   __syncthreads();
   double thresh = 0.0;
   const int jmax = min(R, C);
   int K = 0, more = 0;
-  bool done = !col_ok;
+  bool open = col_ok;
   for (int j = 0; j < jmax; ++j) {
     // ---- pivot: arg-max of the remaining column norms, computed redundantly by every warp ----
     double best = -1.0;
@@ -503,77 +548,106 @@ __device__ __forceinline__ void qrcp_reg(Smem<CHI>& s, const double* __restrict_
     if (j == 0) thresh = best * rel_tol;
     if (!(best > thresh)) break;
     if (j >= kmax) { more = 1; break; }
-    const int pv = bi;
-    const int jp = j & 3, ji = j >> 2;
-    const bool owner = (col == pv);
+    const bool owner = (col == bi);
     if (owner) {
-      double a = 0.0, ss = 0.0;
+      // pivot row entry a = x[row j]; beta = -sign(a) * ||x[j:]||  (the norm is already known)
+      const int jslot = ((j >> 3) << 1) | (j & 1), jpart = (j >> 1) & 3;
+      double a = 0.0;
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        if (i == ji) a = x[i];
-        if (4 * i + part > j) ss += x[i] * x[i];
-      }
-      a = __shfl_sync(gmask, a, (lane & ~3) | jp);
-      ss += __shfl_xor_sync(gmask, ss, 1);
-      ss += __shfl_xor_sync(gmask, ss, 2);
-      double tau = 0.0, scal = 0.0, beta = a;
-      if (ss != 0.0) {
-        beta = -copysign(sqrt(a * a + ss), a);
-        tau = (beta - a) / beta;
-        scal = 1.0 / (a - beta);
-      }
+      for (int idx = 0; idx < RPT; ++idx)
+        if (idx == jslot) a = x[idx];
+      a = __shfl_sync(0xFu << (lane & ~3), a, (lane & ~3) | jpart);
+      const double beta = -copysign(nrm_me, a);
+      const double d = a - beta;
+      const double inv = 1.0 / (beta * d);
+      const double tau = -d * d * inv;   // (beta - a) / beta
+      const double scal = beta * inv;    // 1 / (a - beta)
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        int r = 4 * i + part;
-        double v = (r > j) ? x[i] * scal : ((r == j) ? 1.0 : 0.0);
-        Vall[j * N2 + r] = v;
-        if (r == j) x[i] = beta;
-        else if (r > j) x[i] = 0.0;
+      for (int i2 = 0; i2 < RPT / 2; ++i2) {
+        const int r0 = 8 * i2 + 2 * part;
+        double2 v;
+        v.x = (r0 > j) ? x[2 * i2] * scal : ((r0 == j) ? 1.0 : 0.0);
+        v.y = (r0 + 1 > j) ? x[2 * i2 + 1] * scal : ((r0 + 1 == j) ? 1.0 : 0.0);
+        *reinterpret_cast<double2*>(Vall + j * N2 + r0) = v;
+        if (r0 == j) x[2 * i2] = beta; else if (r0 > j) x[2 * i2] = 0.0;
+        if (r0 + 1 == j) x[2 * i2 + 1] = beta; else if (r0 + 1 > j) x[2 * i2 + 1] = 0.0;
       }
       if (part == 0) s.tau[j] = tau;
+      open = false;
     }
     __syncthreads();
-    {
-      // ---- apply H_j to every open column (done / padded columns run the arithmetic but keep x) ----
+    if (__any_sync(0xffffffffu, open)) {
+      // ---- apply H_j.  Closed columns are invariant (their entries below their own pivot row are exactly
+      //      zero, so v.x == 0); only the pivot column itself must be masked.  Row chunks entirely above
+      //      the pivot row or below the matrix are skipped (warp-uniform). ----
       const double tau = s.tau[j];
-      const double* vj = Vall + j * N2 + part;
+      const double2* vj = reinterpret_cast<const double2*>(Vall + j * N2 + 2 * part);
       double w = 0.0;
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) w += vj[4 * i] * x[i];
+      for (int c = 0; c < NCHK; ++c) {
+        if (4 * CH * (c + 1) > j && 4 * CH * c < R) {
+          double w0 = 0.0, w1 = 0.0;
+#pragma unroll
+          for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
+            const double2 v = vj[4 * i2];
+            w0 += v.x * x[2 * i2];
+            w1 += v.y * x[2 * i2 + 1];
+          }
+          w += w0 + w1;
+        }
+      }
       w += __shfl_xor_sync(0xffffffffu, w, 1);
       w += __shfl_xor_sync(0xffffffffu, w, 2);
-      w *= tau;
+      w = owner ? 0.0 : w * tau;
       double nn = 0.0;
-      const bool open = !done && !owner;
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        double xn = x[i] - w * vj[4 * i];
-        if (open) x[i] = xn;
-        if (4 * i + part > j) nn += xn * xn;
+      for (int c = 0; c < NCHK; ++c) {
+        if (4 * CH * (c + 1) > j && 4 * CH * c < R) {
+          double s0 = 0.0, s1 = 0.0;
+          if (4 * CH * c > j) {  // every row of the chunk is below the pivot row
+#pragma unroll
+            for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
+              const double2 v = vj[4 * i2];
+              const double xa = x[2 * i2] - w * v.x, xb = x[2 * i2 + 1] - w * v.y;
+              x[2 * i2] = xa; x[2 * i2 + 1] = xb;
+              s0 += xa * xa; s1 += xb * xb;
+            }
+          } else {
+#pragma unroll
+            for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
+              const int r0 = 8 * i2 + 2 * part;
+              const double2 v = vj[4 * i2];
+              const double xa = x[2 * i2] - w * v.x, xb = x[2 * i2 + 1] - w * v.y;
+              x[2 * i2] = xa; x[2 * i2 + 1] = xb;
+              if (r0 > j) s0 += xa * xa;
+              if (r0 + 1 > j) s1 += xb * xb;
+            }
+          }
+          nn += s0 + s1;
+        }
       }
       nn += __shfl_xor_sync(0xffffffffu, nn, 1);
       nn += __shfl_xor_sync(0xffffffffu, nn, 2);
-      if (part == 0) {
-        if (open) s.vn1[col] = sqrt(nn);
-        else if (owner) s.vn1[col] = -1.0;
-      }
-      if (owner) done = true;
+      nrm_me = sqrt(nn);
+      if (part == 0 && open) s.vn1[col] = nrm_me;
     }
+    if (owner && part == 0) s.vn1[col] = -1.0;  // closed; written after the barrier so no warp's arg-max races it
     __syncthreads();
     K = j + 1;
   }
   if (!more) {
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-      int r = 4 * i + part;
-      if (col_ok && r < K) s.X[r * LD + col] = x[i];
+    for (int idx = 0; idx < RPT; ++idx) {
+      int r = 8 * (idx >> 1) + 2 * part + (idx & 1);
+      if (col_ok && r < K) s.X[r * LD + col] = x[idx];
     }
   }
   if (tid == 0) {
     s.iscr[0] = K; s.iscr[1] = more;
     double f = 2.0 * R * C;
     for (int j = 0; j < K; ++j) f += 4.0 * (R - j) * (C - j - 1) + 3.0 * (R - j);
-    cnt.flops_qr += f;
+    s.cnt.flops_qr += f;
+    s.cnt.n_qr_reflectors += K;
   }
   __syncthreads();
 }
@@ -581,40 +655,187 @@ __device__ __forceinline__ void qrcp_reg(Smem<CHI>& s, const double* __restrict_
 // Q = H_0 ... H_{K-1} [I_K; 0] in registers (8 threads per column, rows interleaved mod 8), written to
 // s.P2 as a flat R x K matrix (ld K) after every thread has finished reading the reflectors from it.
 template <int CHI>
-__device__ __forceinline__ void form_q_reg(Smem<CHI>& s, int R, int K, Counters& cnt) {
+__device__ __noinline__ void form_q_reg(Smem<CHI>& s, int R, int K) {
   constexpr int N2 = Smem<CHI>::N2;
-  constexpr int RPT = N2 / 8;
+  constexpr int RPT = N2 / 8;               // register rows per thread
+  constexpr int CH = RPT < 8 ? RPT : 8;
+  constexpr int NCHK = RPT / CH;            // chunk c covers matrix rows [8*CH*c, 8*CH*(c+1))
+  // register slot idx = 2*i2 + e holds matrix row 16*i2 + 2*part + e
   const int tid = threadIdx.x;
   const int col = tid >> 3, part = tid & 7;
+  const int warp_col0 = (tid >> 5) * 4;     // first of the 4 columns this warp owns
   const double* Vall = s.P2;
   double q[RPT];
 #pragma unroll
-  for (int i = 0; i < RPT; ++i) q[i] = (8 * i + part == col) ? 1.0 : 0.0;
-  for (int j = K - 1; j >= 0; --j) {
+  for (int idx = 0; idx < RPT; ++idx) q[idx] = (16 * (idx >> 1) + 2 * part + (idx & 1) == col) ? 1.0 : 0.0;
+  // H_j leaves e_c untouched for j > c, so a warp starts at its largest column index
+  const int jstart = (warp_col0 < K) ? min(K - 1, warp_col0 + 3) : -1;
+  for (int j = jstart; j >= 0; --j) {
     const double tau = s.tau[j];
-    const double* vj = Vall + j * N2 + part;
+    const double2* vj = reinterpret_cast<const double2*>(Vall + j * N2 + 2 * part);
     double w = 0.0;
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) w += vj[8 * i] * q[i];
+    for (int c = 0; c < NCHK; ++c) {
+      if (8 * CH * (c + 1) > j && 8 * CH * c < R) {
+        double w0 = 0.0, w1 = 0.0;
+#pragma unroll
+        for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
+          const double2 v = vj[8 * i2];
+          w0 += v.x * q[2 * i2];
+          w1 += v.y * q[2 * i2 + 1];
+        }
+        w += w0 + w1;
+      }
+    }
     w += __shfl_xor_sync(0xffffffffu, w, 1);
     w += __shfl_xor_sync(0xffffffffu, w, 2);
     w += __shfl_xor_sync(0xffffffffu, w, 4);
     w *= tau;
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) q[i] -= w * vj[8 * i];
+    for (int c = 0; c < NCHK; ++c) {
+      if (8 * CH * (c + 1) > j && 8 * CH * c < R) {
+#pragma unroll
+        for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
+          const double2 v = vj[8 * i2];
+          q[2 * i2] -= w * v.x;
+          q[2 * i2 + 1] -= w * v.y;
+        }
+      }
+    }
   }
   __syncthreads();
   if (col < K) {
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-      int r = 8 * i + part;
-      if (r < R) s.P2[r * K + col] = q[i];
+    for (int idx = 0; idx < RPT; ++idx) {
+      int r = 16 * (idx >> 1) + 2 * part + (idx & 1);
+      if (r < R) s.P2[r * K + col] = q[idx];
     }
   }
   if (tid == 0) {
     double f = 0.0;
     for (int j = 0; j < K; ++j) f += 4.0 * (R - j) * (K - 1 - j) + 2.0 * (R - j);
-    cnt.flops_qr += f;
+    s.cnt.flops_qr += f;
+  }
+  __syncthreads();
+}
+
+// One-sided Jacobi, device version: 8 lanes per column pair, both columns of the pair in registers for
+// the round (load, 3 dot products reduced by shuffles, rotation, store), one CTA barrier per round.
+// Same round-robin order, rotation formula, thresholds and outputs as jacobi_columns<> above.
+template <int CHI>
+__device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int max_sweeps) {
+  constexpr int LD = Smem<CHI>::LD;
+  constexpr int N2 = Smem<CHI>::N2;
+  constexpr int RPT = N2 / 8;  // register rows per lane; slot idx holds matrix row 8*idx + sub
+  double* X = s.X;
+  const int tid = threadIdx.x;
+  const int slot = tid >> 3, sub = tid & 7;
+  const int n = (C + 1) & ~1;
+  const int npair = n / 2;
+  const double tol = EPS * sqrt((double)R);
+  const double tol2 = tol * tol;
+  const int per = (R + NCH - 1) / NCH;
+  // squared-norm floor below which a column counts as numerically zero
+  MD_PAR_FOR(t, NCH * C) {
+    int ch = t / C, c = t - ch * C;
+    int i0 = ch * per, i1 = min(R, i0 + per);
+    double acc = 0.0;
+    for (int i = i0; i < i1; ++i) { double v = X[i * LD + c]; acc += v * v; }
+    s.part[ch * N2 + c] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mx = 0.0;
+    for (int c = 0; c < C; ++c) {
+      double acc = 0.0;
+      for (int ch = 0; ch < NCH; ++ch) acc += s.part[ch * N2 + c];
+      mx = fmax(mx, acc);
+    }
+    s.dscr[6] = mx * (4.0 * EPS) * (4.0 * EPS);
+  }
+  __syncthreads();
+  const double floor2 = s.dscr[6];
+  int sweeps = 0;
+  int converged = (C < 2);
+  while (!converged && sweeps < max_sweeps) {
+    if (tid == 0) s.iscr[6] = 0;
+    __syncthreads();
+    for (int rnd = 0; rnd < n - 1; ++rnd) {
+      if (slot < npair) {
+        int a, b;
+        if (slot == 0) { a = n - 1; b = rnd; }
+        else { a = (rnd + slot) % (n - 1); b = (rnd - slot + (n - 1)) % (n - 1); }
+        if (a < C && b < C) {  // uniform over the 8 lanes of the slot
+          double xa[RPT], xb[RPT];
+          double saa = 0.0, sbb = 0.0, sab = 0.0;
+#pragma unroll
+          for (int idx = 0; idx < RPT; ++idx) {
+            const int r = 8 * idx + sub;
+            const bool ok = r < R;
+            xa[idx] = ok ? X[r * LD + a] : 0.0;
+            xb[idx] = ok ? X[r * LD + b] : 0.0;
+            saa += xa[idx] * xa[idx]; sbb += xb[idx] * xb[idx]; sab += xa[idx] * xb[idx];
+          }
+          const unsigned m = 0xFFu << ((tid & 31) & ~7);
+#pragma unroll
+          for (int off = 1; off < 8; off <<= 1) {
+            saa += __shfl_xor_sync(m, saa, off);
+            sbb += __shfl_xor_sync(m, sbb, off);
+            sab += __shfl_xor_sync(m, sab, off);
+          }
+          if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) {
+            const double zeta = (sbb - saa) / (2.0 * sab);
+            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double c = rsqrt(1.0 + t * t);
+            const double sn = c * t;
+#pragma unroll
+            for (int idx = 0; idx < RPT; ++idx) {
+              const int r = 8 * idx + sub;
+              if (r < R) {
+                X[r * LD + a] = c * xa[idx] - sn * xb[idx];
+                X[r * LD + b] = sn * xa[idx] + c * xb[idx];
+              }
+            }
+            if (sub == 0) atomicAdd(&s.iscr[6], 1);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    ++sweeps;
+    const int nrot = s.iscr[6];
+    converged = (nrot == 0);
+    if (tid == 0) s.cnt.flops_jacobi += 6.0 * R * npair * (n - 1) + 6.0 * R * nrot;
+    __syncthreads();
+  }
+  // singular values = column norms; order by value (descending), ties by column index
+  MD_PAR_FOR(t, NCH * C) {
+    int ch = t / C, c = t - ch * C;
+    int i0 = ch * per, i1 = min(R, i0 + per);
+    double acc = 0.0;
+    for (int i = i0; i < i1; ++i) { double v = X[i * LD + c]; acc += v * v; }
+    s.part[ch * N2 + c] = acc;
+  }
+  __syncthreads();
+  MD_PAR_FOR(c, C) {
+    double acc = 0.0;
+    for (int ch = 0; ch < NCH; ++ch) acc += s.part[ch * N2 + c];
+    s.sig[c] = sqrt(acc);
+  }
+  __syncthreads();
+  MD_PAR_FOR(c, C) {
+    double v = s.sig[c];
+    int pos = 0;
+    for (int o = 0; o < C; ++o) {
+      double w = s.sig[o];
+      pos += (w > v) || (w == v && o < c);
+    }
+    s.order[pos] = c;
+  }
+  if (tid == 0) {
+    s.iscr[4] = sweeps; s.iscr[5] = converged ? 0 : 1;
+    s.cnt.n_jacobi_sweeps += sweeps;
+    s.cnt.flops_jacobi += 2.0 * R * C;
   }
   __syncthreads();
 }

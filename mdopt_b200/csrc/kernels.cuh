@@ -36,16 +36,20 @@ decode_kernel(DecodeParams P, const int* __restrict__ prog, const double* __rest
   Smem<CHI>& s = *reinterpret_cast<Smem<CHI>*>(smem_raw);
   __shared__ int next_item;
   Engine<CHI> E(s);
-  const size_t stride = ws_doubles_per_cta(CHI, P.n_sites);
-  double* base = ws + (size_t)blockIdx.x * stride;
-  E.sites = base;
-  E.scr0 = base + (size_t)P.n_sites * Engine<CHI>::SITE_STRIDE;
-  E.scr1 = E.scr0 + (size_t)(2 * CHI) * (2 * CHI);
-  E.bd = reinterpret_cast<int*>(E.scr1 + (size_t)(2 * CHI) * (2 * CHI));
-  E.wtab = wtab;
-  E.wdim = wdim;
-  E.P = P;
-  E.cnt = Counters{0, 0, 0, 0, 0, 0, 0, 0};
+  if (threadIdx.x == 0) {
+    const size_t stride = ws_doubles_per_cta(CHI, P.n_sites);
+    double* base = ws + (size_t)blockIdx.x * stride;
+    EngineState& st = s.st;
+    st.sites = base;
+    st.scr0 = base + (size_t)P.n_sites * Engine<CHI>::SITE_STRIDE;
+    st.scr1 = st.scr0 + (size_t)(2 * CHI) * (2 * CHI);
+    st.bd = reinterpret_cast<int*>(st.scr1 + (size_t)(2 * CHI) * (2 * CHI));
+    st.wtab = wtab;
+    st.wdim = wdim;
+    st.P = P;
+    s.cnt = Counters{};
+  }
+  __syncthreads();
   const int ncls = 1 << P.n_logical;
   while (true) {
     if (threadIdx.x == 0) next_item = atomicAdd(work_counter, 1);
@@ -53,11 +57,13 @@ decode_kernel(DecodeParams P, const int* __restrict__ prog, const double* __rest
     const int b = next_item;
     __syncthreads();
     if (b >= batch) break;
-    E.trace = trace ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
+    if (threadIdx.x == 0) s.st.trace = trace ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
+    __syncthreads();
     E.run(prog, syms + (size_t)b * P.n_sites, dist + (size_t)b * ncls, success + b);
+    __syncthreads();
     if (threadIdx.x == 0) {
-      status[b] = E.status;
-      if (E.status == ST_CAPACITY) {
+      status[b] = s.st.status;
+      if (s.st.status == ST_CAPACITY) {
         for (int i = 0; i < ncls; ++i) dist[(size_t)b * ncls + i] = nan("");
         success[b] = 0;
       }
@@ -65,13 +71,21 @@ decode_kernel(DecodeParams P, const int* __restrict__ prog, const double* __rest
     __syncthreads();
   }
   if (threadIdx.x == 0 && counters) {
-    atomicAdd(counters + 0, E.cnt.flops_qr);
-    atomicAdd(counters + 1, E.cnt.flops_jacobi);
-    atomicAdd(counters + 2, E.cnt.flops_apply);
-    atomicAdd(counters + 3, E.cnt.bytes_hbm);
-    atomicAdd(counters + 4, E.cnt.n_steps);
-    atomicAdd(counters + 5, E.cnt.n_trunc);
-    atomicAdd(counters + 6, E.cnt.n_jacobi_sweeps);
+    atomicAdd(counters + 0, s.cnt.flops_qr);
+    atomicAdd(counters + 1, s.cnt.flops_jacobi);
+    atomicAdd(counters + 2, s.cnt.flops_apply);
+    atomicAdd(counters + 3, s.cnt.bytes_hbm);
+    atomicAdd(counters + 4, s.cnt.n_steps);
+    atomicAdd(counters + 5, s.cnt.n_trunc);
+    atomicAdd(counters + 6, s.cnt.n_jacobi_sweeps);
+    atomicAdd(counters + 7, s.cnt.n_qr_reflectors);
+    atomicAdd(counters + 8, s.cnt.cyc_qr);
+    atomicAdd(counters + 9, s.cnt.cyc_formq);
+    atomicAdd(counters + 10, s.cnt.cyc_jacobi);
+    atomicAdd(counters + 11, s.cnt.cyc_apply);
+    atomicAdd(counters + 12, s.cnt.cyc_io);
+    atomicAdd(counters + 13, s.cnt.cyc_coef);
+    atomicAdd(counters + 14, s.cnt.cyc_total);
   }
 }
 
@@ -89,17 +103,22 @@ mps_program_kernel(DecodeParams P, const int* __restrict__ prog, const double* _
   Engine<CHI> E(s);
   const int ncls = 1 << P.n_logical;
   for (int b = blockIdx.x; b < batch; b += gridDim.x) {
-    E.sites = sites_io + (size_t)b * P.n_sites * Engine<CHI>::SITE_STRIDE;
-    E.bd = bonds_io + (size_t)b * (P.n_sites + 1);
-    E.scr0 = ws + (size_t)blockIdx.x * 2 * (2 * CHI) * (2 * CHI);
-    E.scr1 = E.scr0 + (size_t)(2 * CHI) * (2 * CHI);
-    E.wtab = wtab; E.wdim = wdim; E.P = P;
-    E.cnt = Counters{0, 0, 0, 0, 0, 0, 0, 0};
-    E.centre = centre_io[b]; E.mirrored = 0; E.status = ST_OK; E.n_traced = 0;
-    E.trace = trace ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      EngineState& st = s.st;
+      st.sites = sites_io + (size_t)b * P.n_sites * Engine<CHI>::SITE_STRIDE;
+      st.bd = bonds_io + (size_t)b * (P.n_sites + 1);
+      st.scr0 = ws + (size_t)blockIdx.x * 2 * (2 * CHI) * (2 * CHI);
+      st.scr1 = st.scr0 + (size_t)(2 * CHI) * (2 * CHI);
+      st.wtab = wtab; st.wdim = wdim; st.P = P;
+      s.cnt = Counters{};
+      st.centre = centre_io[b]; st.mirrored = 0; st.status = ST_OK; st.n_traced = 0;
+      st.trace = trace ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
+    }
     __syncthreads();
     E.run_ops(prog, dist ? dist + (size_t)b * ncls : nullptr, success ? success + b : nullptr);
-    if (threadIdx.x == 0) { status[b] = E.status; centre_io[b] = E.centre; }
+    __syncthreads();
+    if (threadIdx.x == 0) { status[b] = s.st.status; centre_io[b] = s.st.centre; }
     __syncthreads();
   }
 }
@@ -114,13 +133,12 @@ svd_kernel(int batch, int m, int n, const double* __restrict__ a, int chi_max, d
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<CHI>& s = *reinterpret_cast<Smem<CHI>*>(smem_raw);
   constexpr int LD = Smem<CHI>::LD;
-  Counters cnt{0, 0, 0, 0, 0, 0, 0, 0};
   const int kmax = min(m, n);
   for (int b = blockIdx.x; b < batch; b += gridDim.x) {
     const double* ab = a + (size_t)b * m * n;
     MD_PAR_FOR(t, m * n) { int i = t / n, c = t - i * n; s.X[i * LD + c] = ab[t]; }
     MD_SYNC();
-    jacobi_columns<CHI>(s, m, n, cnt);
+    jacobi_columns_dev<CHI>(s, m, n, 60);
     truncation_rule<CHI>(s, n, min(chi_max, kmax), cut);
     const int k = s.iscr[0];
     const double scale = (renormalise && s.dscr[3] > 0.0) ? 1.0 / s.dscr[3] : 1.0;
@@ -164,7 +182,6 @@ site_apply_kernel(int batch, int rows, int vl, int vr, int mr, int bn, const dou
   Smem<CHI>& s = *reinterpret_cast<Smem<CHI>*>(smem_raw);
   constexpr int LD = Smem<CHI>::LD;
   Engine<CHI> E(s);
-  E.cnt = Counters{0, 0, 0, 0, 0, 0, 0, 0};
   const int cin = vl * mr;
   MD_PAR_FOR(i, 16) { s.W[i] = (i < vl * vr * 4) ? w[i] : 0.0; }
   for (int b = blockIdx.x; b < batch; b += gridDim.x) {
@@ -216,7 +233,7 @@ int launch_decode(const mdopt_decode_desc* d, int n_ctas, const int32_t* program
   e = cudaMemsetAsync(work_counter, 0, 256, st);
   if (e != cudaSuccess) return (int)e;
   if (counters) {
-    e = cudaMemsetAsync(counters, 0, 8 * sizeof(double), st);
+    e = cudaMemsetAsync(counters, 0, 16 * sizeof(double), st);
     if (e != cudaSuccess) return (int)e;
   }
   const int grid = batch < n_ctas ? batch : n_ctas;

@@ -30,22 +30,8 @@ enum { OP_END = 0, OP_SWEEP = 1, OP_MOVE = 2, OP_MARGINAL = 3, OP_GATE2 = 4 };
 enum { MODE_FAST = 0, MODE_SVD = 1 };
 enum { ST_OK = 0, ST_NOT_CONVERGED = 1, ST_CAPACITY = 2, ST_ZERO_NORM = 3 };
 
-struct DecodeParams {
-  int n_sites;        // MPS length N
-  int n_logical;      // number of logical sites kL (they are sites 0..kL-1)
-  int chi_max;        // user chi_max for sweeps
-  int mode;           // MODE_FAST / MODE_SVD
-  int renormalise;    // decode_css(renormalise=...)
-  int trace_stride;   // doubles per traced step (0 = no trace)
-  int trace_max;      // max traced steps per syndrome
-  int n_ops;          // length of the program in ints
-  double cut_sweep;   // user cut for sweep splits
-  double cut_move;    // 1e-12 (reference default of split_two_site_tensor inside move_orth_centre)
-  double rank_tol;    // MODE_FAST relative rank threshold
-  double bias_p;      // bit-flip bias probability; < 0 disables the bias
-};
-
-// Per-CTA view of its global workspace.
+// Per-CTA engine.  All persistent state lives in shared memory (s.st) so that it costs no registers in
+// the register-resident QR loops; the Engine object itself is just the reference to the CTA's Smem.
 template <int CHI>
 struct Engine {
   static constexpr int LD = Smem<CHI>::LD;
@@ -53,47 +39,33 @@ struct Engine {
   static constexpr int SITE_STRIDE = CHI * 2 * CHI;
 
   Smem<CHI>& s;
-  double* sites;   // [N][SITE_STRIDE], packed (vL, p, vR) row-major per site
-  double* scr0;    // carried matrix, flat
-  double* scr1;    // theta scratch for non-isometric steps
-  int* bd;         // [N+1] bond dimensions (global, per CTA)
-  const double* wtab;  // [n_tensors][16]
-  const int* wdim;     // [n_tensors][4] = vL, vR, iso, pad
-  double* trace;   // per-syndrome trace block or nullptr
-  int n_traced;
-  DecodeParams P;
-  Counters cnt;
-  int status;
-  int centre;
-  // carried-matrix state
-  int K, Wq, Mr;
-  int mirrored;
+  EngineState& st;
 
-  MD_DEV Engine(Smem<CHI>& sm) : s(sm) {}
+  MD_DEV Engine(Smem<CHI>& sm) : s(sm), st(sm.st) {}
 
   // ---- frame helpers: logical site j of the current frame ----
-  MD_DEV int phys(int j) const { return mirrored ? (P.n_sites - 1 - j) : j; }
-  MD_DEV int dim_left(int j) const { int p = phys(j); return mirrored ? bd[p + 1] : bd[p]; }
-  MD_DEV int dim_right(int j) const { int p = phys(j); return mirrored ? bd[p] : bd[p + 1]; }
-  MD_DEV void set_dim_right(int j, int v) { int p = phys(j); if (mirrored) bd[p] = v; else bd[p + 1] = v; }
+  MD_DEV int phys(int j) const { return st.mirrored ? (st.P.n_sites - 1 - j) : j; }
+  MD_DEV int dim_left(int j) const { int p = phys(j); return st.mirrored ? st.bd[p + 1] : st.bd[p]; }
+  MD_DEV int dim_right(int j) const { int p = phys(j); return st.mirrored ? st.bd[p] : st.bd[p + 1]; }
+  MD_DEV void set_dim_right(int j, int v) { int p = phys(j); if (st.mirrored) st.bd[p] = v; else st.bd[p + 1] = v; }
 
   MD_DEV void load_w(int tid) {
-    MD_PAR_FOR(i, 16) { s.W[i] = (tid < 0) ? ((i == 0 || i == 3) ? 1.0 : 0.0) : wtab[tid * 16 + i]; }
+    MD_PAR_FOR(i, 16) { s.W[i] = (tid < 0) ? ((i == 0 || i == 3) ? 1.0 : 0.0) : st.wtab[tid * 16 + i]; }
     MD_SYNC();
   }
-  MD_DEV int w_vl(int tid) const { return tid < 0 ? 1 : wdim[tid * 4 + 0]; }
-  MD_DEV int w_vr(int tid) const { return tid < 0 ? 1 : wdim[tid * 4 + 1]; }
-  MD_DEV int w_iso(int tid) const { return tid < 0 ? 1 : wdim[tid * 4 + 2]; }
+  MD_DEV int w_vl(int tid) const { return tid < 0 ? 1 : st.wdim[tid * 4 + 0]; }
+  MD_DEV int w_vr(int tid) const { return tid < 0 ? 1 : st.wdim[tid * 4 + 1]; }
+  MD_DEV int w_iso(int tid) const { return tid < 0 ? 1 : st.wdim[tid * 4 + 2]; }
   // W(q, w', pU, pD) with actual dims (vl, vr, 2, 2)
   MD_DEV double w_at(int vr, int q, int wo, int pu, int pd) const { return s.W[((q * vr + wo) * 2 + pu) * 2 + pd]; }
 
   // ---- carried <- site j with the first MPO tensor applied (contractor.py:276-291, first half) ----
-  // out[((k*2 + p')*Wq + q)*Mr + m] = sum_p A[k,p,m] W(0,q,p,p')
+  // out[((k*2 + p')*st.Wq + q)*st.Mr + m] = sum_p A[k,p,m] W(0,q,p,p')
   MD_DEV void carried_from_site(int j, int tid) {
     load_w(tid);
     const int A = dim_left(j), B = dim_right(j), vr = w_vr(tid);
-    const double* src = sites + (size_t)phys(j) * SITE_STRIDE;
-    const int mir = mirrored;
+    const double* src = st.sites + (size_t)phys(j) * SITE_STRIDE;
+    const int mir = st.mirrored;
     MD_PAR_FOR(t, A * 2 * vr * B) {
       int m = t % B; int r = t / B;
       int q = r % vr; r /= vr;
@@ -101,28 +73,29 @@ struct Engine {
       double a0, a1;
       if (!mir) { a0 = src[(k * 2 + 0) * B + m]; a1 = src[(k * 2 + 1) * B + m]; }
       else { a0 = src[(m * 2 + 0) * A + k]; a1 = src[(m * 2 + 1) * A + k]; }
-      scr0[t] = a0 * w_at(vr, 0, q, 0, pd) + a1 * w_at(vr, 0, q, 1, pd);
+      st.scr0[t] = a0 * w_at(vr, 0, q, 0, pd) + a1 * w_at(vr, 0, q, 1, pd);
     }
-    MD_LEADER { cnt.bytes_hbm += 8.0 * (A * 2 * B + A * 2 * vr * B); cnt.flops_apply += 3.0 * A * 2 * vr * B; }
-    K = A; Wq = vr; Mr = B;
+    MD_LEADER { s.cnt.bytes_hbm += 8.0 * (A * 2 * B + A * 2 * vr * B); s.cnt.flops_apply += 3.0 * A * 2 * vr * B; }
+    MD_SYNC();
+    MD_LEADER { st.K = A; st.Wq = vr; st.Mr = B; }
     MD_SYNC();
   }
 
   // ---- stage site j (frame layout (a,p,b) flat) into dst (shared) ----
   MD_DEV void stage_site(int j, double* dst, int A, int B) {
-    const double* src = sites + (size_t)phys(j) * SITE_STRIDE;
-    if (!mirrored) { MD_PAR_FOR(g, A * 2 * B) dst[g] = src[g]; }
+    const double* src = st.sites + (size_t)phys(j) * SITE_STRIDE;
+    if (!st.mirrored) { MD_PAR_FOR(g, A * 2 * B) dst[g] = src[g]; }
     else {
       MD_PAR_FOR(g, A * 2 * B) {  // phys tensor has dims (B, 2, A)
         int a = g % A; int r = g / A; int p = r & 1; int b = r >> 1;
         dst[(a * 2 + p) * B + b] = src[g];
       }
     }
-    MD_LEADER { cnt.bytes_hbm += 8.0 * A * 2 * B; }
+    MD_LEADER { s.cnt.bytes_hbm += 8.0 * A * 2 * B; }
     MD_SYNC();
   }
 
-  // ---- out[((row*2+p')*vr + w')*Bn + m'] = sum_{q,p,m} Min[row, q*Mr+m] W(q,w',p,p') As[(m*2+p)*Bn + m'] ----
+  // ---- out[((row*2+p')*vr + w')*Bn + m'] = sum_{q,p,m} Min[row, q*st.Mr+m] W(q,w',p,p') As[(m*2+p)*Bn + m'] ----
   MD_DEV void apply_site(const double* Min, int ld, int rows, int vl, int vr, int mr, int Bn,
                          const double* As, double* out) {
     constexpr int TR = 8, TM = 2;
@@ -167,39 +140,41 @@ struct Engine {
     MD_LEADER {
       int nnz = 0;
       for (int i = 0; i < vl * vr * 4; ++i) nnz += (s.W[i] != 0.0);
-      cnt.flops_apply += 2.0 * rows * Bn * mr * nnz;
-      cnt.bytes_hbm += 8.0 * rows * 2 * vr * Bn;
+      s.cnt.flops_apply += 2.0 * rows * Bn * mr * nnz;
+      s.cnt.bytes_hbm += 8.0 * rows * 2 * vr * Bn;
     }
     MD_SYNC();
   }
 
   MD_DEV void load_x(const double* src, int R, int C) {
     MD_PAR_FOR(t, R * C) { int i = t / C, c = t - i * C; s.X[i * LD + c] = src[t]; }
-    MD_LEADER { cnt.bytes_hbm += 8.0 * R * C; }
+    MD_LEADER { s.cnt.bytes_hbm += 8.0 * R * C; }
     MD_SYNC();
   }
 
   // ---- factor X (R x C; a copy lives in `orig`, flat ld C) -> Knew, U (in X), coefficients (in P2) ----
   // Returns Knew.  s.iscr[7] = 1 when U columns are addressed through s.order / scaled by 1/s.sig.
   // Layout of the result (s.iscr[7]):
-  //   0  U = s.X[:, 0:K] (ld LD),               coefficients = s.P2 (ld LD)     [portable QR path]
+  //   0  U = s.X[:, 0:st.K] (ld LD),               coefficients = s.P2 (ld LD)     [portable QR path]
   //   1  U = s.X[:, order[k]] / sig[order[k]],   coefficients = s.P2 (ld LD)     [Jacobi SVD path]
-  //   2  U = s.P2 flat (ld K),                   coefficients = s.X rows (ld LD) [register QR path]
+  //   2  U = s.P2 flat (ld st.K),                   coefficients = s.X rows (ld LD) [register QR path]
   MD_DEV int factor(const double* orig, int R, int C, int chi_lim, double cut, int is_move) {
-    int use_svd = (P.mode == MODE_SVD);
+    int use_svd = (st.P.mode == MODE_SVD);
     int Knew = 0;
     const int kmax = chi_lim < CHI ? chi_lim : CHI;
     if (!use_svd) {
 #ifndef MDOPT_EMU
-      qrcp_reg<CHI>(s, orig, R, C, kmax, P.rank_tol, cnt);
+      long long t0 = MD_CLOCK();
+      qrcp_reg<CHI>(s, orig, R, C, kmax, st.P.rank_tol);
+      MD_LEADER { s.cnt.cyc_qr += (double)(MD_CLOCK() - t0); }
 #else
       load_x(orig, R, C);
-      qrcp<CHI>(s, R, C, kmax, P.rank_tol, cnt);
+      qrcp<CHI>(s, R, C, kmax, st.P.rank_tol);
 #endif
       Knew = s.iscr[0];
       if (s.iscr[1]) {  // more than chi_lim significant directions: genuine truncation needed
         use_svd = 1;
-        MD_LEADER { cnt.n_trunc += 1.0; }
+        MD_LEADER { s.cnt.n_trunc += 1.0; }
       }
     }
     if (!use_svd) {
@@ -211,8 +186,9 @@ struct Engine {
         MD_SYNC();
         return 1;
       }
-      form_q_reg<CHI>(s, R, Knew, cnt);
-      MD_LEADER { s.iscr[7] = 2; }
+      long long t1 = MD_CLOCK();
+      form_q_reg<CHI>(s, R, Knew);
+      MD_LEADER { s.iscr[7] = 2; s.cnt.cyc_formq += (double)(MD_CLOCK() - t1); }
       MD_SYNC();
       return Knew;
 #else
@@ -224,7 +200,7 @@ struct Engine {
         return 1;
       }
       extract_coeff<CHI>(s, Knew, C);
-      form_q<CHI>(s, R, Knew, cnt);
+      form_q<CHI>(s, R, Knew);
       MD_LEADER { s.iscr[7] = 0; }
       MD_SYNC();
       return Knew;
@@ -232,17 +208,26 @@ struct Engine {
     }
     load_x(orig, R, C);
     // ---- Jacobi SVD path ----
-    jacobi_columns<CHI>(s, R, C, cnt);
-    if (s.iscr[5]) status = ST_NOT_CONVERGED;
+    long long tj = MD_CLOCK();
+#ifndef MDOPT_EMU
+    jacobi_columns_dev<CHI>(s, R, C, 60);
+#else
+    jacobi_columns<CHI>(s, R, C);
+#endif
+    MD_LEADER { s.cnt.cyc_jacobi += (double)(MD_CLOCK() - tj); }
+    long long tc = MD_CLOCK();
+    if (s.iscr[5]) st.status = ST_NOT_CONVERGED;
     truncation_rule<CHI>(s, C, chi_lim, cut);
     Knew = s.iscr[0];
-    if (trace != nullptr && n_traced < P.trace_max) {
-      double* tr = trace + (size_t)n_traced * P.trace_stride;
+    if (st.trace != nullptr && st.n_traced < st.P.trace_max) {
+      double* tr = st.trace + (size_t)st.n_traced * st.P.trace_stride;
       MD_LEADER { tr[0] = R; tr[1] = C; tr[2] = Knew; tr[3] = is_move; }
-      MD_PAR_FOR(c, N2) { if (4 + c < P.trace_stride) tr[4 + c] = (c < C) ? s.sig[s.order[c]] : 0.0; }
+      MD_PAR_FOR(c, N2) { if (4 + c < st.P.trace_stride) tr[4 + c] = (c < C) ? s.sig[s.order[c]] : 0.0; }
     }
-    n_traced += 1;
-    if (Knew > CHI) { status = ST_CAPACITY; MD_SYNC(); return 0; }  // would overflow the site stride
+    MD_SYNC();
+    MD_LEADER { st.n_traced += 1; }
+    MD_SYNC();
+    if (Knew > CHI) { st.status = ST_CAPACITY; MD_SYNC(); return 0; }  // would overflow the site stride
     if (Knew == 0) {
       MD_SYNC();
       MD_PAR_FOR(i, R) s.X[i * LD] = (i == 0) ? 1.0 : 0.0;
@@ -271,22 +256,23 @@ struct Engine {
         for (int a = 0; a < TK; ++a)
           if (k0 + a < Knew) s.P2[(k0 + a) * LD + c] = acc[a] / s.sig[col[a]];
       }
-      MD_LEADER { cnt.flops_apply += 2.0 * R * C * Knew; cnt.bytes_hbm += 8.0 * R * C * nkt; s.iscr[7] = 1; }
+      MD_LEADER { s.cnt.flops_apply += 2.0 * R * C * Knew; s.cnt.bytes_hbm += 8.0 * R * C * nkt; s.iscr[7] = 1; }
     }
     MD_SYNC();
+    MD_LEADER { s.cnt.cyc_coef += (double)(MD_CLOCK() - tc); }
     return Knew;
   }
 
-  // ---- site j <- U (R = K*2 rows, Knew columns), frame layout (k, r, k') ----
+  // ---- site j <- U (R = st.K*2 rows, Knew columns), frame layout (k, r, k') ----
   MD_DEV double u_at(int lay, int row, int kn, int Knew) const {
     if (lay == 2) return s.P2[row * Knew + kn];
     if (lay == 1) return s.X[row * LD + s.order[kn]] / s.sig[s.order[kn]];
     return s.X[row * LD + kn];
   }
   MD_DEV void store_u(int j, int Kl, int Knew) {
-    double* dst = sites + (size_t)phys(j) * SITE_STRIDE;
+    double* dst = st.sites + (size_t)phys(j) * SITE_STRIDE;
     const int lay = s.iscr[7];
-    if (!mirrored) {
+    if (!st.mirrored) {
       MD_PAR_FOR(g, Kl * 2 * Knew) {
         int kn = g % Knew, row = g / Knew;
         dst[g] = u_at(lay, row, kn, Knew);
@@ -297,7 +283,7 @@ struct Engine {
         dst[g] = u_at(lay, k * 2 + p, kn, Knew);
       }
     }
-    MD_LEADER { cnt.bytes_hbm += 8.0 * Kl * 2 * Knew; }
+    MD_LEADER { s.cnt.bytes_hbm += 8.0 * Kl * 2 * Knew; }
     MD_SYNC();
   }
 
@@ -305,22 +291,22 @@ struct Engine {
   MD_DEV void step(int jn, int tid, int chi_lim, double cut, int is_move, int renorm_sv) {
     const int vl = w_vl(tid), vr = w_vr(tid), iso = w_iso(tid);
     const int Bn = dim_right(jn);
-    const int R = K * 2;
-    int C = Wq * Mr;
-    const double* orig = scr0;
+    const int R = st.K * 2;
+    int C = st.Wq * st.Mr;
+    const double* orig = st.scr0;
     load_w(tid);
-    if (vl != Wq || dim_left(jn) != Mr) { status = ST_CAPACITY; return; }
+    if (vl != st.Wq || dim_left(jn) != st.Mr) { st.status = ST_CAPACITY; return; }
     if (!iso) {
       // theta = Mmat . T formed explicitly (contractor.py:328-342), R x (2*vr*Bn)
-      if (2 * vr * Bn > N2) { status = ST_CAPACITY; return; }
-      load_x(scr0, R, C);
-      stage_site(jn, s.P2, Mr, Bn);
-      apply_site(s.X, LD, R, vl, vr, Mr, Bn, s.P2, scr1);
+      if (2 * vr * Bn > N2) { st.status = ST_CAPACITY; return; }
+      load_x(st.scr0, R, C);
+      stage_site(jn, s.P2, st.Mr, Bn);
+      apply_site(s.X, LD, R, vl, vr, st.Mr, Bn, s.P2, st.scr1);
       C = 2 * vr * Bn;
-      orig = scr1;
+      orig = st.scr1;
     }
     int Knew = factor(orig, R, C, chi_lim, cut, is_move);
-    if (status == ST_CAPACITY) return;
+    if (st.status == ST_CAPACITY) return;
     const int lay = s.iscr[7];
     double* coef = (lay == 2) ? s.X : s.P2;                 // coefficients M' (Knew x C, ld LD)
     double* stage = (lay == 2) ? (s.X + CHI * LD) : s.X;    // staging area for the next site tensor
@@ -341,28 +327,31 @@ struct Engine {
       MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; coef[k * LD + c] *= inv; }
       MD_SYNC();
     }
-    store_u(jn - 1, K, Knew);
+    long long ts = MD_CLOCK();
+    store_u(jn - 1, st.K, Knew);
     if (iso) {
-      stage_site(jn, stage, Mr, Bn);
-      apply_site(coef, LD, Knew, vl, vr, Mr, Bn, stage, scr0);
+      stage_site(jn, stage, st.Mr, Bn);
+      MD_LEADER { s.cnt.cyc_io += (double)(MD_CLOCK() - ts); }
+      long long ta = MD_CLOCK();
+      apply_site(coef, LD, Knew, vl, vr, st.Mr, Bn, stage, st.scr0);
+      MD_LEADER { s.cnt.cyc_apply += (double)(MD_CLOCK() - ta); }
     } else {
-      MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; scr0[t] = coef[k * LD + c]; }
-      MD_LEADER { cnt.bytes_hbm += 8.0 * Knew * C; }
+      MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; st.scr0[t] = coef[k * LD + c]; }
+      MD_LEADER { s.cnt.bytes_hbm += 8.0 * Knew * C; }
       MD_SYNC();
     }
-    K = Knew; Wq = vr; Mr = Bn;
-    MD_LEADER { cnt.n_steps += 1.0; set_dim_right(jn - 1, Knew); }
+    MD_LEADER { st.K = Knew; st.Wq = vr; st.Mr = Bn; s.cnt.n_steps += 1.0; set_dim_right(jn - 1, Knew); }
     MD_SYNC();
   }
 
-  // ---- carried (K,2,1,Mr) -> site j, optionally divided by its Frobenius norm (optimiser/utils.py:340-345) ----
+  // ---- carried (st.K,2,1,st.Mr) -> site j, optionally divided by its Frobenius norm (optimiser/utils.py:340-345) ----
   MD_DEV void carried_to_site(int j, int renorm) {
-    const int n = K * 2 * Mr;
+    const int n = st.K * 2 * st.Mr;
     double scale = 1.0;
     if (renorm) {
       MD_PAR_FOR(ch, 256) {
         double acc = 0.0;
-        for (int t = ch; t < n; t += 256) { double v = scr0[t]; acc += v * v; }
+        for (int t = ch; t < n; t += 256) { double v = st.scr0[t]; acc += v * v; }
         s.part[ch] = acc;
       }
       MD_SYNC();
@@ -375,91 +364,96 @@ struct Engine {
       MD_SYNC();
       scale = s.dscr[4];
     }
-    double* dst = sites + (size_t)phys(j) * SITE_STRIDE;
-    const int A = K, B = Mr;
-    if (!mirrored) { MD_PAR_FOR(g, n) dst[g] = scr0[g] * scale; }
+    double* dst = st.sites + (size_t)phys(j) * SITE_STRIDE;
+    const int A = st.K, B = st.Mr;
+    if (!st.mirrored) { MD_PAR_FOR(g, n) dst[g] = st.scr0[g] * scale; }
     else {
       MD_PAR_FOR(g, n) {  // phys dims (B, 2, A)
         int a = g % A; int r = g / A; int p = r & 1; int b = r >> 1;
-        dst[g] = scr0[(a * 2 + p) * B + b] * scale;
+        dst[g] = st.scr0[(a * 2 + p) * B + b] * scale;
       }
     }
-    MD_LEADER { cnt.bytes_hbm += 16.0 * n; }
+    MD_LEADER { s.cnt.bytes_hbm += 16.0 * n; }
     MD_SYNC();
   }
 
-  // ---- sweep of an MPO over frame sites start..start+len-1 (tids == nullptr: identity MPO = move) ----
+  // ---- sweep of an MPO over frame st.sites start..start+len-1 (tids == nullptr: identity MPO = move) ----
   MD_DEV void sweep(int start, int len, const int* tids, int chi_lim, double cut, int renorm_after,
                     int is_move, int renorm_sv) {
     carried_from_site(start, tids ? tids[0] : -1);
     for (int t = 1; t < len; ++t) {
       step(start + t, tids ? tids[t] : -1, chi_lim, cut, is_move, renorm_sv);
-      if (status == ST_CAPACITY) return;
+      if (st.status == ST_CAPACITY) return;
     }
-    if (Wq != 1) { status = ST_CAPACITY; return; }
+    if (st.Wq != 1) { st.status = ST_CAPACITY; return; }
     carried_to_site(start + len - 1, renorm_after);
   }
 
   // ---- move the orthogonality centre (canonical.py:345-420) ----
+  MD_DEV void set_frame(int mir) { MD_SYNC(); MD_LEADER { st.mirrored = mir; } MD_SYNC(); }
+  MD_DEV void set_centre(int c) { MD_SYNC(); MD_LEADER { st.centre = c; } MD_SYNC(); }
+
   MD_DEV void move_centre(int target) {
-    if (target == centre) return;
+    const int from = st.centre;
+    if (target == from) return;
     const int chi_lim = CHI;
-    if (target > centre) {
-      mirrored = 0;
-      sweep(centre, target - centre + 1, nullptr, chi_lim, P.cut_move, 0, 1, 0);
+    if (target > from) {
+      set_frame(0);
+      sweep(from, target - from + 1, nullptr, chi_lim, st.P.cut_move, 0, 1, 0);
     } else {
-      mirrored = 1;
-      const int N = P.n_sites;
-      sweep(N - 1 - centre, centre - target + 1, nullptr, chi_lim, P.cut_move, 0, 1, 0);
-      mirrored = 0;
+      set_frame(1);
+      const int N = st.P.n_sites;
+      sweep(N - 1 - from, from - target + 1, nullptr, chi_lim, st.P.cut_move, 0, 1, 0);
+      set_frame(0);
     }
-    centre = target;
+    set_centre(target);
   }
 
   // ---- product state + bit-flip bias (mps/utils.py:439-512, decoding.py:140-190) ----
   MD_DEV void init_product(const uint8_t* sym) {
-    const int N = P.n_sites;
-    const double d = (P.bias_p >= 0.0) ? sqrt(1.0 - P.bias_p) : 1.0;
-    const double o = (P.bias_p >= 0.0) ? sqrt(P.bias_p) : 0.0;
-    const int kL = P.n_logical;
+    const int N = st.P.n_sites;
+    const double d = (st.P.bias_p >= 0.0) ? sqrt(1.0 - st.P.bias_p) : 1.0;
+    const double o = (st.P.bias_p >= 0.0) ? sqrt(st.P.bias_p) : 0.0;
+    const int kL = st.P.n_logical;
     MD_PAR_FOR(j, N) {
       double a0, a1;
       int c = sym[j];
       if (c == 0) { a0 = 1.0; a1 = 0.0; }
       else if (c == 1) { a0 = 0.0; a1 = 1.0; }
       else { a0 = 1.0 / sqrt(2.0); a1 = a0; }
-      if (j >= kL && P.bias_p >= 0.0) {
+      if (j >= kL && st.P.bias_p >= 0.0) {
         double b0 = a0 * d + a1 * o, b1 = a0 * o + a1 * d;
         a0 = b0; a1 = b1;
       }
-      sites[(size_t)j * SITE_STRIDE + 0] = a0;
-      sites[(size_t)j * SITE_STRIDE + 1] = a1;
+      st.sites[(size_t)j * SITE_STRIDE + 0] = a0;
+      st.sites[(size_t)j * SITE_STRIDE + 1] = a1;
     }
-    MD_PAR_FOR(j, N + 1) bd[j] = 1;
-    centre = 0; mirrored = 0; status = ST_OK; n_traced = 0;
+    MD_PAR_FOR(j, N + 1) st.bd[j] = 1;
+    MD_SYNC();
+    MD_LEADER { st.centre = 0; st.mirrored = 0; st.status = ST_OK; st.n_traced = 0; }
     MD_SYNC();
   }
 
-  // ---- marginal over sites kL..N-1, reverse, dense, |.|, L2 renorm, tolerant arg-max ----
+  // ---- marginal over st.sites kL..N-1, reverse, dense, |.|, L2 renorm, tolerant arg-max ----
   //   canonical.py:956-989, :150-161, :241-272; decoding.py:1362-1379
   MD_DEV void marginal_readout(double* out, int* success) {
-    const int N = P.n_sites, kL = P.n_logical, ren = P.renormalise;
+    const int N = st.P.n_sites, kL = st.P.n_logical, ren = st.P.renormalise;
     double* T = s.part;        // current last tensor (L x 2), L <= CHI
     double* w = s.wv;          // traced vector
-    int L = bd[N - 1];
-    MD_PAR_FOR(t, L * 2) T[t] = sites[(size_t)(N - 1) * SITE_STRIDE + t];  // (L, 2, 1)
+    int L = st.bd[N - 1];
+    MD_PAR_FOR(t, L * 2) T[t] = st.sites[(size_t)(N - 1) * SITE_STRIDE + t];  // (L, 2, 1)
     MD_SYNC();
     for (int site = N - 1; site >= kL; --site) {
       MD_PAR_FOR(l, L) w[l] = (T[l * 2] + T[l * 2 + 1]) * (1.0 / sqrt(2.0));
       MD_SYNC();
-      const int L2 = bd[site - 1];
-      const double* A = sites + (size_t)(site - 1) * SITE_STRIDE;  // (L2, 2, L)
+      const int L2 = st.bd[site - 1];
+      const double* A = st.sites + (size_t)(site - 1) * SITE_STRIDE;  // (L2, 2, L)
       MD_PAR_FOR(t, L2 * 2) {
         double acc = 0.0;
         for (int l = 0; l < L; ++l) acc += A[(size_t)t * L + l] * w[l];
         T[t] = acc;
       }
-      MD_LEADER { cnt.bytes_hbm += 8.0 * L2 * 2 * L; cnt.flops_apply += 2.0 * L2 * 2 * L; }
+      MD_LEADER { s.cnt.bytes_hbm += 8.0 * L2 * 2 * L; s.cnt.flops_apply += 2.0 * L2 * 2 * L; }
       MD_SYNC();
       if (ren) {
         MD_LEADER {
@@ -475,10 +469,10 @@ struct Engine {
       L = L2;
     }
     // the merged last logical tensor goes back into the MPS (what CanonicalMPS.marginal returns)
-    MD_PAR_FOR(t, L * 2) sites[(size_t)(kL - 1) * SITE_STRIDE + t] = T[t];
-    MD_LEADER { bd[kL] = 1; }
+    MD_PAR_FOR(t, L * 2) st.sites[(size_t)(kL - 1) * SITE_STRIDE + t] = T[t];
+    MD_LEADER { st.bd[kL] = 1; }
     MD_SYNC();
-    // dense over the kL logical sites: D_j[(p_j .. p_0), b]
+    // dense over the kL logical st.sites: D_j[(p_j .. p_0), b]
     double* D0 = s.X;
     double* D1 = s.X + (N2 * LD) / 2;
     int nb = 1, nidx = 1;
@@ -486,8 +480,8 @@ struct Engine {
     MD_SYNC();
     for (int j = 0; j < kL; ++j) {
       const int Bl = nb;
-      const int Br = (j == kL - 1) ? 1 : bd[j + 1];
-      const double* A = sites + (size_t)j * SITE_STRIDE;
+      const int Br = (j == kL - 1) ? 1 : st.bd[j + 1];
+      const double* A = st.sites + (size_t)j * SITE_STRIDE;
       const int last = (j == kL - 1);
       MD_PAR_FOR(t, nidx * 2 * Br) {
         int b2 = t % Br; int r = t / Br; int idx = r % nidx; int p = r / nidx;
@@ -514,7 +508,7 @@ struct Engine {
         if (v != v) nan_seen = 1;
         if (v > top) top = v;
       }
-      if (nan_seen) { *success = 0; if (status == ST_OK) status = ST_ZERO_NORM; }
+      if (nan_seen) { *success = 0; if (st.status == ST_OK) st.status = ST_ZERO_NORM; }
       else {
         double eps = fmax(1e-9 * top, 1e-12);
         *success = (out[0] >= top - eps) ? 1 : 0;
@@ -529,19 +523,19 @@ struct Engine {
     run_ops(prog, out, success);
   }
 
-  // ---- run a program on the MPS already present in sites / bd / centre ----
+  // ---- run a program on the MPS already present in st.sites / st.bd / st.centre ----
   MD_DEV void run_ops(const int* prog, double* out, int* success) {
+    const long long t_all = MD_CLOCK();
     int pc = 0;
-    while (pc < P.n_ops) {
+    while (pc < st.P.n_ops) {
       const int op = prog[pc];
       if (op == OP_END) break;
       if (op == OP_SWEEP) {
         const int start = prog[pc + 1], len = prog[pc + 2], ren = prog[pc + 3], rsv = prog[pc + 4];
         move_centre(start);
-        if (status != ST_CAPACITY) {
-          mirrored = 0;
-          sweep(start, len, prog + pc + 5, P.chi_max, P.cut_sweep, ren, 0, rsv);
-          centre = start + len - 1;
+        if (st.status != ST_CAPACITY) {
+          sweep(start, len, prog + pc + 5, st.P.chi_max, st.P.cut_sweep, ren, 0, rsv);
+          set_centre(start + len - 1);
         }
         pc += 5 + len;
       } else if (op == OP_MOVE) {
@@ -551,11 +545,12 @@ struct Engine {
         if (out != nullptr) marginal_readout(out, success);
         pc += 1;
       } else {
-        status = ST_CAPACITY;
+        st.status = ST_CAPACITY;
         break;
       }
-      if (status == ST_CAPACITY) break;
+      if (st.status == ST_CAPACITY) break;
     }
+    MD_LEADER { s.cnt.cyc_total += (double)(MD_CLOCK() - t_all); }
   }
 };
 

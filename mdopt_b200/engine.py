@@ -60,7 +60,7 @@ class DecodeEngine:
                 raise _lib.MdoptCudaError("decode kernel cannot be made resident on this device")
             self.ws_bytes = int(self.lib.mdopt_decode_workspace_bytes(self.cap, self.n_sites, self.n_ctas))
             self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
-            self.counters = torch.zeros(8, dtype=torch.float64, device=self.device)
+            self.counters = torch.zeros(16, dtype=torch.float64, device=self.device)
         self.max_batch = 0
         self._alloc(max_batch)
         self._programs: Dict[int, DeviceProgram] = {}
@@ -143,7 +143,8 @@ class DecodeEngine:
 
     def read_counters(self) -> Dict[str, float]:
         c = self.counters.cpu().numpy()
-        keys = ["flops_qr", "flops_jacobi", "flops_apply", "bytes", "steps", "truncating_steps", "jacobi_sweeps"]
+        keys = ["flops_qr", "flops_jacobi", "flops_apply", "bytes", "steps", "truncating_steps", "jacobi_sweeps",
+                "qr_reflectors", "cyc_qr", "cyc_formq", "cyc_jacobi", "cyc_apply", "cyc_io", "cyc_coef", "cyc_total"]
         return {k: float(v) for k, v in zip(keys, c)}
 
 

@@ -22,29 +22,29 @@ int decode_impl(const mdopt_decode_desc* d, const int32_t* program, const double
   Smem<CHI>* sm = new Smem<CHI>();
   std::vector<double> ws(ws_doubles(CHI, d->n_sites));
   Engine<CHI> E(*sm);
-  E.sites = ws.data();
-  E.scr0 = E.sites + (size_t)d->n_sites * Engine<CHI>::SITE_STRIDE;
-  E.scr1 = E.scr0 + (size_t)(2 * CHI) * (2 * CHI);
-  E.bd = reinterpret_cast<int*>(E.scr1 + (size_t)(2 * CHI) * (2 * CHI));
-  E.wtab = wtab;
-  E.wdim = wdim;
+  E.st.sites = ws.data();
+  E.st.scr0 = E.st.sites + (size_t)d->n_sites * Engine<CHI>::SITE_STRIDE;
+  E.st.scr1 = E.st.scr0 + (size_t)(2 * CHI) * (2 * CHI);
+  E.st.bd = reinterpret_cast<int*>(E.st.scr1 + (size_t)(2 * CHI) * (2 * CHI));
+  E.st.wtab = wtab;
+  E.st.wdim = wdim;
   DecodeParams P;
   P.n_sites = d->n_sites; P.n_logical = d->n_logical; P.chi_max = d->chi_max; P.mode = d->mode;
   P.renormalise = d->renormalise; P.trace_stride = d->trace_stride; P.trace_max = d->trace_max;
   P.n_ops = d->n_ops; P.cut_sweep = d->cut_sweep; P.cut_move = d->cut_move; P.rank_tol = d->rank_tol;
   P.bias_p = d->bias_p;
-  E.P = P;
-  E.cnt = Counters{0, 0, 0, 0, 0, 0, 0, 0};
+  E.st.P = P;
+  sm->cnt = Counters{};
   const int ncls = 1 << d->n_logical;
   for (int b = 0; b < batch; ++b) {
-    E.trace = (trace && d->trace_stride > 0) ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
+    E.st.trace = (trace && d->trace_stride > 0) ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
     E.run(program, symbols + (size_t)b * d->n_sites, dist + (size_t)b * ncls, success + b);
-    status[b] = E.status;
+    status[b] = E.st.status;
   }
   if (counters) {
-    counters[0] = E.cnt.flops_qr; counters[1] = E.cnt.flops_jacobi; counters[2] = E.cnt.flops_apply;
-    counters[3] = E.cnt.bytes_hbm; counters[4] = E.cnt.n_steps; counters[5] = E.cnt.n_trunc;
-    counters[6] = E.cnt.n_jacobi_sweeps; counters[7] = 0;
+    counters[0] = sm->cnt.flops_qr; counters[1] = sm->cnt.flops_jacobi; counters[2] = sm->cnt.flops_apply;
+    counters[3] = sm->cnt.bytes_hbm; counters[4] = sm->cnt.n_steps; counters[5] = sm->cnt.n_trunc;
+    counters[6] = sm->cnt.n_jacobi_sweeps; counters[7] = 0;
   }
   delete sm;
   return 0;
@@ -55,9 +55,8 @@ int svd_impl(int m, int n, const double* a, int chi_max, double cut, double* u, 
   Smem<CHI>* sm = new Smem<CHI>();
   Smem<CHI>& s = *sm;
   constexpr int LD = Smem<CHI>::LD;
-  Counters cnt{0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = 0; i < m; ++i) for (int c = 0; c < n; ++c) s.X[i * LD + c] = a[i * n + c];
-  jacobi_columns<CHI>(s, m, n, cnt);
+  jacobi_columns<CHI>(s, m, n);
   const int kmax = m < n ? m : n;
   truncation_rule<CHI>(s, n, chi_max < kmax ? chi_max : kmax, cut);
   int k = s.iscr[0];
@@ -83,13 +82,12 @@ int qr_impl(int m, int n, const double* a, int kmax, double rel_tol, double* q, 
   Smem<CHI>* sm = new Smem<CHI>();
   Smem<CHI>& s = *sm;
   constexpr int LD = Smem<CHI>::LD;
-  Counters cnt{0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = 0; i < m; ++i) for (int c = 0; c < n; ++c) s.X[i * LD + c] = a[i * n + c];
-  qrcp<CHI>(s, m, n, kmax, rel_tol, cnt);
+  qrcp<CHI>(s, m, n, kmax, rel_tol);
   int K = s.iscr[0];
   *more = s.iscr[1];
   extract_coeff<CHI>(s, K, n);
-  form_q<CHI>(s, m, K, cnt);
+  form_q<CHI>(s, m, K);
   for (int i = 0; i < m; ++i) for (int k = 0; k < K; ++k) q[i * K + k] = s.X[i * LD + k];
   for (int k = 0; k < K; ++k) for (int c = 0; c < n; ++c) coeff[k * n + c] = s.P2[k * LD + c];
   delete sm;
@@ -103,20 +101,20 @@ int program_impl(const mdopt_decode_desc* d, const int32_t* program, const doubl
   Smem<CHI>* sm = new Smem<CHI>();
   std::vector<double> ws(2 * (size_t)(2 * CHI) * (2 * CHI));
   Engine<CHI> E(*sm);
-  E.sites = sites_io; E.bd = bonds_io;
-  E.scr0 = ws.data(); E.scr1 = E.scr0 + (size_t)(2 * CHI) * (2 * CHI);
-  E.wtab = wtab; E.wdim = wdim;
+  E.st.sites = sites_io; E.st.bd = bonds_io;
+  E.st.scr0 = ws.data(); E.st.scr1 = E.st.scr0 + (size_t)(2 * CHI) * (2 * CHI);
+  E.st.wtab = wtab; E.st.wdim = wdim;
   DecodeParams P;
   P.n_sites = d->n_sites; P.n_logical = d->n_logical; P.chi_max = d->chi_max; P.mode = d->mode;
   P.renormalise = d->renormalise; P.trace_stride = d->trace_stride; P.trace_max = d->trace_max;
   P.n_ops = d->n_ops; P.cut_sweep = d->cut_sweep; P.cut_move = d->cut_move; P.rank_tol = d->rank_tol;
   P.bias_p = d->bias_p;
-  E.P = P;
-  E.cnt = Counters{0, 0, 0, 0, 0, 0, 0, 0};
-  E.centre = *centre_io; E.mirrored = 0; E.status = ST_OK; E.n_traced = 0;
-  E.trace = (trace && d->trace_stride > 0) ? trace : nullptr;
+  E.st.P = P;
+  sm->cnt = Counters{};
+  E.st.centre = *centre_io; E.st.mirrored = 0; E.st.status = ST_OK; E.st.n_traced = 0;
+  E.st.trace = (trace && d->trace_stride > 0) ? trace : nullptr;
   E.run_ops(program, dist, success);
-  *status = E.status; *centre_io = E.centre;
+  *status = E.st.status; *centre_io = E.st.centre;
   delete sm;
   return 0;
 }
