@@ -510,6 +510,21 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
   const int col = tid >> 2, part = tid & 3, lane = tid & 31;
   const bool col_ok = col < C;
   double* Vall = s.P2;
+  constexpr int NWARP = (CHI * 8 < 64 ? 64 : CHI * 8) / 32;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(s.vn1);  // one key per warp
+  // key = norm bits with the low byte replaced by (255 - column): integer max == largest norm, ties (to
+  // ~1e-14 relative) towards the lowest column index; 0 = closed / padded column
+  auto norm_key = [](double nrm, int c) -> unsigned long long {
+    return ((unsigned long long)__double_as_longlong(nrm) & ~0xFFull) | (unsigned long long)(0xFF - c);
+  };
+  auto warp_key_publish = [&](unsigned long long k) {
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, off);
+      k = o > k ? o : k;
+    }
+    if (lane == 0) keys[tid >> 5] = k;
+  };
   double x[RPT];
 #pragma unroll
   for (int idx = 0; idx < RPT; ++idx) {
@@ -524,7 +539,7 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
     nn += __shfl_xor_sync(0xffffffffu, nn, 1);
     nn += __shfl_xor_sync(0xffffffffu, nn, 2);
     nrm_me = sqrt(nn);
-    if (part == 0) s.vn1[col] = col_ok ? nrm_me : -1.0;
+    warp_key_publish(col_ok ? norm_key(nrm_me, col) : 0ull);
   }
   __syncthreads();
   double thresh = 0.0;
@@ -532,19 +547,16 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
   int K = 0, more = 0;
   bool open = col_ok;
   for (int j = 0; j < jmax; ++j) {
-    // ---- pivot: arg-max of the remaining column norms, computed redundantly by every warp ----
-    double best = -1.0;
-    int bi = 0x7fffffff;
-    for (int c = lane; c < N2; c += 32) {
-      double v = s.vn1[c];
-      if (v > best || (v == best && c < bi)) { best = v; bi = c; }
-    }
+    // ---- pivot: max over the per-warp keys (norm bits | inverted column index), redundantly per warp ----
+    unsigned long long key = (lane < NWARP) ? keys[lane] : 0ull;
 #pragma unroll
-    for (int off = 16; off; off >>= 1) {
-      double ov = __shfl_xor_sync(0xffffffffu, best, off);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    for (int off = NWARP / 2; off; off >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, off);
+      key = o > key ? o : key;
     }
+    key = __shfl_sync(0xffffffffu, key, 0);
+    const double best = key ? __longlong_as_double((long long)(key & ~0xFFull)) : -1.0;
+    const int bi = 0xFF - (int)(key & 0xFFull);
     if (j == 0) thresh = best * rel_tol;
     if (!(best > thresh)) break;
     if (j >= kmax) { more = 1; break; }
@@ -629,9 +641,10 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
       nn += __shfl_xor_sync(0xffffffffu, nn, 1);
       nn += __shfl_xor_sync(0xffffffffu, nn, 2);
       nrm_me = sqrt(nn);
-      if (part == 0 && open) s.vn1[col] = nrm_me;
     }
-    if (owner && part == 0) s.vn1[col] = -1.0;  // closed; written after the barrier so no warp's arg-max races it
+    // per-warp maximum of the open columns' keys; written after the first barrier of the iteration, so no
+    // warp's pivot search can race it
+    warp_key_publish(open ? norm_key(nrm_me, col) : 0ull);
     __syncthreads();
     K = j + 1;
   }

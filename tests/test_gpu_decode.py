@@ -62,7 +62,7 @@ def test_gating_by_literal_character(api):
         np.testing.assert_allclose(dist[b], r["dist"], rtol=5e-2 if both else 1e-10, atol=1e-13)
 
 
-@pytest.mark.parametrize("name,min_agree", [("d3_chi8_bitflip", 1.0), ("d5_chi16_bitflip", 0.9),
+@pytest.mark.parametrize("name,min_agree", [("d3_chi8_bitflip", 0.95), ("d5_chi16_bitflip", 0.9),
                                             ("d5_chi64_bitflip", 0.95)])
 def test_truncating_configs_success_agreement(api, name, min_agree):
     """Truncating configs cut exactly-degenerate singular-value multiplets, so marginals are only defined up
