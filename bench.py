@@ -43,8 +43,19 @@ def seeded_errors(n_qubits, rate, count, seed, offset=0):
 # CPU arm: the oracle port of the reference algorithm on the host cores (the reference itself is Python and
 # does not travel to the GPU box; oracle/mps_oracle.py is pinned bit-for-bit against it).
 # ------------------------------------------------------------------------------------------------------
-def _cpu_worker(err):
+def _cpu_init():
+    """One BLAS thread per worker (the reference's cluster convention, quantum_surface_cc.sh:58).  The env
+    var alone is not enough: the parent has usually initialised its BLAS pool before the fork."""
     os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+
+        _cpu_init.limit = threadpool_limits(limits=1)
+    except Exception:  # noqa: BLE001
+        pass
+
+
+def _cpu_worker(err):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import mps_oracle as O
 
@@ -60,7 +71,7 @@ def cpu_rate(errors, cores):
 
     os.environ["OMP_NUM_THREADS"] = "1"  # the reference's own cluster convention (quantum_surface_cc.sh:58)
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
+    with ctx.Pool(cores, initializer=_cpu_init) as pool:
         pool.map(_cpu_worker, errors[:cores])  # warm the workers (imports, BLAS init)
         t0 = time.perf_counter()
         oks = pool.map(_cpu_worker, errors, chunksize=1)

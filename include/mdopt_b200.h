@@ -47,6 +47,8 @@ extern "C" {
 #define MDOPT_OP_SWEEP 1    /* [1, start, len, renorm_centre_after, renorm_spectrum, tensor_id x len] */
 #define MDOPT_OP_MOVE 2     /* [2, target_site] */
 #define MDOPT_OP_MARGINAL 3 /* [3] marginalise sites n_logical..N-1 and read out */
+#define MDOPT_OP_GATE2 4    /* [4, site, gate_id, renormalise] two-site gate G[j][l][n][o] (16 doubles in wtab) on
+                               (site, site+1), then split with chi=capacity / cut_move (depolarising bias) */
 
 typedef struct mdopt_decode_desc {
   int32_t n_sites;      /* MPS length N = 2n + k */

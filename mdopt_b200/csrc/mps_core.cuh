@@ -409,6 +409,62 @@ struct Engine {
     set_centre(target);
   }
 
+  // ---- two-site gate on (site, site+1) with the centre at `site`, then split (depolarising bias:
+  //      decoding.py:254-274 -- theta = "ijk,klm,jlno->inom", split with chi=1e4 / cut=1e-12, spectrum and
+  //      centre renormalised).  The gate sits in the tensor table as 16 doubles G[j][l][n][o]. ----
+  MD_DEV void gate2(int site, int gid, int renorm) {
+    const int L = st.bd[site], M = st.bd[site + 1], Rr = st.bd[site + 2];
+    const int R = 2 * L, C = 2 * Rr;
+    if (R > N2 || C > N2 || M > CHI) { st.status = ST_CAPACITY; return; }
+    load_w(gid);
+    const double* A = st.sites + (size_t)site * SITE_STRIDE;
+    const double* B = st.sites + (size_t)(site + 1) * SITE_STRIDE;
+    double* theta = st.scr1;
+    MD_PAR_FOR(t, R * C) {
+      int m = t % Rr; int r = t / Rr;
+      int o = r & 1; r >>= 1;
+      int n = r & 1; int i = r >> 1;
+      double acc = 0.0;
+      for (int j = 0; j < 2; ++j)
+        for (int l = 0; l < 2; ++l) {
+          double g = s.W[((j * 2 + l) * 2 + n) * 2 + o];
+          if (g == 0.0) continue;
+          double inner = 0.0;
+          for (int k = 0; k < M; ++k) inner += A[(i * 2 + j) * M + k] * B[((size_t)k * 2 + l) * Rr + m];
+          acc += g * inner;
+        }
+      theta[t] = acc;
+    }
+    MD_LEADER { s.cnt.flops_apply += 8.0 * R * C * M; s.cnt.bytes_hbm += 8.0 * (L * 2 * M + M * 2 * Rr + R * C); }
+    MD_SYNC();
+    const int Knew = factor(theta, R, C, CHI, st.P.cut_move, 1);
+    if (st.status == ST_CAPACITY) return;
+    const int lay = s.iscr[7];
+    const double* coef = (lay == 2) ? s.X : s.P2;
+    double scale = 1.0;
+    if (renorm) {
+      MD_PAR_FOR(ch, 256) {
+        double acc = 0.0;
+        for (int t = ch; t < Knew * C; t += 256) { int k = t / C, c = t - k * C; double v = coef[k * LD + c]; acc += v * v; }
+        s.part[ch] = acc;
+      }
+      MD_SYNC();
+      MD_LEADER {
+        double acc = 0.0;
+        for (int ch = 0; ch < 256; ++ch) acc += s.part[ch];
+        s.dscr[4] = 1.0 / sqrt(acc);  // unguarded like the reference (0 -> inf -> NaN)
+      }
+      MD_SYNC();
+      scale = s.dscr[4];
+    }
+    store_u(site, L, Knew);
+    double* dst = st.sites + (size_t)(site + 1) * SITE_STRIDE;
+    MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; dst[t] = coef[k * LD + c] * scale; }
+    MD_SYNC();
+    MD_LEADER { st.bd[site + 1] = Knew; st.centre = site + 1; s.cnt.n_steps += 1.0; }
+    MD_SYNC();
+  }
+
   // ---- product state + bit-flip bias (mps/utils.py:439-512, decoding.py:140-190) ----
   MD_DEV void init_product(const uint8_t* sym) {
     const int N = st.P.n_sites;
@@ -541,6 +597,10 @@ struct Engine {
       } else if (op == OP_MOVE) {
         move_centre(prog[pc + 1]);
         pc += 2;
+      } else if (op == OP_GATE2) {
+        move_centre(prog[pc + 1]);
+        if (st.status != ST_CAPACITY) gate2(prog[pc + 1], prog[pc + 2], prog[pc + 3]);
+        pc += 4;
       } else if (op == OP_MARGINAL) {
         if (out != nullptr) marginal_readout(out, success);
         pc += 1;

@@ -50,11 +50,14 @@ def _code_key(code) -> Tuple:
     return (len(code),) + tuple(tuple(tuple(int(c) for c in row) for row in m.rows()) for m in mats)
 
 
-def _program_for(code, has_x, has_z, renormalise, strategy, orders) -> schedule.Program:
+def _program_for(code, has_x, has_z, renormalise, strategy, orders, bias_type="Bitflip", bias_prob=0.1):
+    depol = bias_type != "Bitflip"
     key = (_code_key(code), has_x, has_z, bool(renormalise), strategy,
-           None if not orders else tuple(sorted((k, tuple(v)) for k, v in orders.items())))
+           None if not orders else tuple(sorted((k, tuple(v)) for k, v in orders.items())),
+           depol, float(bias_prob) if depol else None)
     if key not in _PROGRAM_CACHE:
-        _PROGRAM_CACHE[key] = schedule.build_decode_program(code, has_x, has_z, renormalise, strategy, orders)
+        _PROGRAM_CACHE[key] = schedule.build_decode_program(code, has_x, has_z, renormalise, strategy, orders,
+                                                            "Depolarising" if depol else "Bitflip", bias_prob)
     return _PROGRAM_CACHE[key]
 
 
@@ -72,8 +75,7 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
     """
     from mdopt_b200 import engine
 
-    if bias_type != "Bitflip":
-        raise NotImplementedError("the GPU engine implements the Bitflip bias; the Depolarising bias is a next row")
+    depol = bias_type != "Bitflip"  # any other string takes the depolarising branch (decoding.py:1267-1283)
     if not 0 <= bias_prob <= 1:
         raise ValueError(f"The channel parameter should be a probability, given {bias_prob} at site 0.")
     k = code.num_x_logicals() + code.num_z_logicals()
@@ -100,9 +102,10 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
     chi = int(min(int(chi_max), 1 << 30))
     eng = engine.get_engine(n_sites, k, chi)
     for (has_x, has_z), idx in groups.items():
-        prog = _program_for(code, has_x, has_z, renormalise, contraction_strategy, orders)
+        prog = _program_for(code, has_x, has_z, renormalise, contraction_strategy, orders, bias_type, bias_prob)
         syms = schedule.symbols_from_errors([errors[b] for b in idx], k)
-        d, s, st = eng.decode_host(prog, syms, cut=cut, bias_p=bias_prob, renormalise=renormalise, mode=mode)
+        d, s, st = eng.decode_host(prog, syms, cut=cut, bias_p=(-1.0 if depol else bias_prob),
+                                   renormalise=renormalise, mode=mode)
         dist[idx], success[idx], status[idx] = d, s, st
         if not silent:
             logging.info("decoded %d syndromes with flags X=%s Z=%s", len(idx), has_x, has_z)

@@ -15,7 +15,7 @@ import numpy as np
 
 from mdopt_b200.optimiser.utils import (COPY_LEFT, SWAP, XOR_BULK, XOR_LEFT, XOR_RIGHT, ConstraintString, msro)
 
-OP_END, OP_SWEEP, OP_MOVE, OP_MARGINAL = 0, 1, 2, 3
+OP_END, OP_SWEEP, OP_MOVE, OP_MARGINAL, OP_GATE2 = 0, 1, 2, 3, 4
 MODE_FAST, MODE_SVD = 0, 1
 SYM_ZERO, SYM_ONE, SYM_PLUS = 0, 1, 2
 
@@ -49,6 +49,18 @@ class TensorTable:
             flat[: w.size] = w.ravel()
             self.data.append(flat)
             self.dims.append((w.shape[0], w.shape[1], int(self.is_isometric(w)), 0))
+        return self._ids[key]
+
+    def add_gate(self, gate: np.ndarray) -> int:
+        """Two-site gate with legs (pUL, pUR, pDL, pDR) = (j, l, n, o), stored as 16 doubles."""
+        g = np.ascontiguousarray(gate, dtype=np.float64)
+        if g.shape != (2, 2, 2, 2):
+            raise ValueError("a two-site gate must have shape (2, 2, 2, 2)")
+        key = b"gate" + g.tobytes()
+        if key not in self._ids:
+            self._ids[key] = len(self.data)
+            self.data.append(g.ravel().copy())
+            self.dims.append((2, 2, 0, 1))
         return self._ids[key]
 
     def arrays(self) -> Tuple[np.ndarray, np.ndarray]:
@@ -126,14 +138,33 @@ def append_strings(ops: List[int], table: TensorTable, strings, tensors, n_sites
         spans.append((start, span))
 
 
+def depolarising_bias(prob_bias: float) -> np.ndarray:
+    """Two-site bias operator (reference decoding.py:92-137; ``np.fill_diagonal`` on a 4-d array touches only
+    the four [i,i,i,i]... entries with equal indices, i.e. [0,0,0,0] and [1,1,1,1])."""
+    if not 0 <= prob_bias <= 1:
+        raise ValueError(f"The channel parameter `prob_bias` should be a probability, given {prob_bias}.")
+    op = np.full((2, 2, 2, 2), np.sqrt(prob_bias / 3))
+    np.fill_diagonal(op, np.sqrt(1 - prob_bias))
+    return op
+
+
 def build_decode_program(code, has_x: bool, has_z: bool, renormalise: bool = True, strategy: str = "Naive",
-                         orders: Optional[dict] = None) -> Program:
-    """Program for ``decode_css`` on errors with the given literal-character flags (decoding.py:1230-1339)."""
+                         orders: Optional[dict] = None, bias_type: str = "Bitflip",
+                         bias_prob: float = 0.1) -> Program:
+    """Program for ``decode_css`` on errors with the given literal-character flags (decoding.py:1230-1339).
+
+    ``bias_type="Bitflip"`` is applied by the kernel while it builds the product state; any other value takes
+    the reference's depolarising branch (decoding.py:1267-1283): centre to the first bias site, then one
+    two-site gate + split on every adjacent pair of error sites (decoding.py:252-274)."""
     k = code.num_x_logicals() + code.num_z_logicals()
     n_sites = 2 * len(code) + k
     checks, logicals = code_site_lists(code)
     orders = orders or {}
     table, ops, spans = TensorTable(), [], []
+    if bias_type != "Bitflip":
+        gid = table.add_gate(depolarising_bias(bias_prob))
+        for site in range(k, n_sites - 1):
+            ops.extend([OP_GATE2, site, gid, int(bool(renormalise))])
     logical_t = [COPY_LEFT, XOR_BULK, SWAP, XOR_RIGHT]
     check_t = [XOR_LEFT, XOR_BULK, SWAP, XOR_RIGHT]
     plan = []

@@ -11,16 +11,18 @@ from mdopt_b200 import schedule
 from mdopt_b200.codes import surface_code
 
 
-def emu_decode(code, errors, chi, cut, bias, mode, strategy="Optimised", renormalise=True, trace_max=0):
+def emu_decode(code, errors, chi, cut, bias, mode, strategy="Optimised", renormalise=True, trace_max=0,
+               bias_type="Bitflip"):
     out = []
     for e in errors:
         triv, hx, hz = schedule.error_flags(e)
         if triv:
             out.append((np.array([1.0, 0, 0, 0]), 1, 0, None, None))
             continue
-        prog = schedule.build_decode_program(code, hx, hz, renormalise, strategy)
+        prog = schedule.build_decode_program(code, hx, hz, renormalise, strategy, None, bias_type, bias)
         sym = schedule.symbols_from_errors([e], prog.n_logical)
-        dist, succ, st, tr, cnt = H.decode(prog, sym, chi, cut, bias, renormalise, mode, trace_max=trace_max)
+        dist, succ, st, tr, cnt = H.decode(prog, sym, chi, cut, bias if bias_type == "Bitflip" else -1.0,
+                                           renormalise, mode, trace_max=trace_max)
         out.append((dist[0], int(succ[0]), int(st[0]), tr[0], cnt))
     return out
 
@@ -140,3 +142,16 @@ def test_naive_strategy_and_no_renormalise():
                                         renormalise=ren, contraction_strategy=strategy)
                 assert ok == rok
                 np.testing.assert_allclose(dist, ref, rtol=1e-10, atol=1e-14)
+
+
+@pytest.mark.parametrize("mode", [schedule.MODE_FAST, schedule.MODE_SVD])
+def test_depolarising_bias_matches_reference(mode):
+    """decoding.py:193-276 (two-site bias + split on every adjacent pair) through the OP_GATE2 path."""
+    g = load_golden("d3_chi64_depol")
+    kw = g["kwargs"]
+    rows = [r for r in g["results"] if not ("X" in r["error"] and "Z" in r["error"])][:20]  # X+Z truncates at chi=64
+    res = emu_decode(surface_code(3), [r["error"] for r in rows], kw["chi_max"], kw["cut"], kw["bias_prob"], mode,
+                     bias_type="Depolarising")
+    for r, (dist, ok, st, _, _) in zip(rows, res):
+        assert st == 0 and ok == r["success"], r["error"]
+        np.testing.assert_allclose(dist, r["dist"], rtol=1e-10, atol=1e-14)

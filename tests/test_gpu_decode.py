@@ -125,3 +125,19 @@ def test_full_size_batch_properties(api):
     assert trivial.any()
     for b in np.nonzero(trivial)[0]:
         assert list(dist[b]) == [1.0, 0.0, 0.0, 0.0] and success[b] == 1
+
+
+@pytest.mark.parametrize("mode", ["fast", "svd"])
+def test_depolarising_bias_and_errors(api, mode):
+    """SURVEY 8a row a4 / config-3 style: depolarising errors (X, Y, Z) with the two-site depolarising bias.
+    Syndromes with both a literal X and a literal Z truncate inside degenerate multiplets at chi=64."""
+    g = load_golden("d3_chi64_depol")
+    kw = dict(g["kwargs"])
+    errors = [r["error"] for r in g["results"]]
+    dist, success, status = api["decode_css_batch"](api["surface_code"](3), errors, contraction_strategy="Optimised",
+                                                    mode=mode, return_status=True, **kw)
+    assert (status == 0).all()
+    for b, r in enumerate(g["results"]):
+        assert int(success[b]) == r["success"], r["error"]
+        both = "X" in r["error"] and "Z" in r["error"]
+        np.testing.assert_allclose(dist[b], r["dist"], rtol=0.1 if both else 1e-10, atol=1e-13)

@@ -1,0 +1,150 @@
+"""CPU tier: host-side logic (schedule builder, constraint strings, sharding + the gloo reduction)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import mps_oracle as O
+from mdopt_b200 import distributed as D
+from mdopt_b200 import schedule
+from mdopt_b200.codes import surface_code
+from mdopt_b200.drivers import quantum_surface as drv
+from mdopt_b200.optimiser import utils as U
+
+
+def test_mpo_tensors_equal_reference_tables():
+    from conftest import load_golden
+
+    ref = load_golden("mpo_tensors")
+    for name, values in ref.items():
+        np.testing.assert_array_equal(getattr(U, name), np.asarray(values))
+
+
+def test_isometry_flags():
+    flags = {n: schedule.TensorTable.is_isometric(getattr(U, n))
+             for n in ["IDENTITY", "XOR_BULK", "SWAP", "XOR_LEFT", "XOR_RIGHT", "COPY_LEFT"]}
+    assert flags == {"IDENTITY": True, "XOR_BULK": True, "SWAP": True, "XOR_LEFT": True, "XOR_RIGHT": False,
+                     "COPY_LEFT": False}
+
+
+def test_site_lists_match_oracle_and_notebook():
+    code = surface_code(3)
+    checks, logicals = schedule.code_site_lists(code)
+    ochecks, ologicals = O.code_sites(O.surface_code(3))
+    assert checks == ochecks and logicals == ologicals
+    # printed in the reference's notebook (quantum_surface.ipynb cells 10/13/19)
+    assert checks[0][0] == [[2], [4], [3, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19], [20]]
+    assert logicals[0][0][0] == [0] and logicals[0][0][1] == [6, 12] and logicals[0][0][3] == [18]
+    assert logicals[1][0] == [[1], [3, 5], [2, 4, 6], [7]]
+
+
+def test_program_layout():
+    code = surface_code(3)
+    prog = schedule.build_decode_program(code, True, False, True, "Optimised")
+    assert prog.n_sites == 28 and prog.n_logical == 2 and prog.n_strings == 7
+    ops = prog.ops.tolist()
+    pc, spans = 0, []
+    while ops[pc] == schedule.OP_SWEEP:
+        start, span = ops[pc + 1], ops[pc + 2]
+        assert ops[pc + 3] == 1 and ops[pc + 4] == 0
+        ids = ops[pc + 5: pc + 5 + span]
+        assert all(0 <= i < prog.wtab.shape[0] for i in ids)
+        assert prog.wdim[ids[-1]][1] == 1 and prog.wdim[ids[0]][0] == 1  # MPO bond closes at both ends
+        spans.append((start, span))
+        pc += 5 + span
+    assert ops[pc:pc + 2] == [schedule.OP_MARGINAL, schedule.OP_END]
+    assert spans == prog.spans
+    assert spans[0] == (0, 19)  # the X logical first, then the checks ordered by (first, last) site
+    assert [s[0] for s in spans[1:]] == sorted(s[0] for s in spans[1:])
+    none = schedule.build_decode_program(code, False, False)
+    assert none.ops.tolist() == [schedule.OP_MARGINAL, schedule.OP_END]
+    depol = schedule.build_decode_program(code, False, False, True, "Naive", None, "Depolarising", 0.1)
+    ops = depol.ops.tolist()
+    assert ops[:4] == [schedule.OP_GATE2, 2, 0, 1] and ops[-6:-2] == [schedule.OP_GATE2, 26, 0, 1]
+    assert len(ops) == 4 * 25 + 2
+    np.testing.assert_allclose(depol.wtab[0].reshape(2, 2, 2, 2), O.depolarising_bias(0.1))
+
+
+def test_symbols_and_flags():
+    syms = schedule.symbols_from_errors(["IXZY"], 2)
+    assert syms.tolist() == [[2, 2, 0, 0, 1, 0, 0, 1, 1, 1]]
+    assert schedule.error_flags("IIII") == (True, False, False)
+    assert schedule.error_flags("IYII") == (False, False, False)
+    assert schedule.error_flags("XYZI") == (False, True, True)
+    with pytest.raises(ValueError):
+        schedule.symbols_from_errors(["IQ"], 1)
+    with pytest.raises(ValueError):
+        schedule.symbols_from_errors(["II", "I"], 1)
+
+
+def test_constraint_string_errors():
+    t = [U.XOR_LEFT, U.XOR_BULK, U.SWAP, U.XOR_RIGHT]
+    with pytest.raises(ValueError):
+        U.ConstraintString([], [[0]])
+    with pytest.raises(ValueError):
+        U.ConstraintString(t, [])
+    with pytest.raises(ValueError):
+        U.ConstraintString(t, [[0], [1]])
+    with pytest.raises(ValueError):
+        U.ConstraintString(t, [[0], [1], [1], [2]])
+    with pytest.raises(ValueError):
+        U.ConstraintString(t, [[0], [1], [], [3]])
+    cs = U.ConstraintString(t, [[3], [5], [4, 6], [7]])
+    assert cs.span() == 5 and cs.start() == 3 and cs.tensor_slots() == [0, 2, 1, 2, 3]
+    assert [m.shape for m in cs.mpo()] == [(1, 2, 2, 2), (2, 2, 2, 2), (2, 2, 2, 2), (2, 2, 2, 2), (2, 1, 2, 2)]
+
+
+def test_seeded_errors_match_reference_generator():
+    ours = drv.generate_errors(5, 0.05, 20, "Bitflip", 123)
+    assert ours == O.seeded_errors(41, 0.05, 20, 123, "Bitflip")
+    from conftest import load_golden
+
+    assert ours == [r["error"] for r in load_golden("d5_chi64_bitflip")["results"]][:20]
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 100, 100001):
+        for world in (1, 2, 3, 8):
+            parts = [D.shard_bounds(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        D.shard_bounds(10, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_items, out):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = D.shard_bounds(n_items, rank, world)
+    rng = np.random.default_rng(5)
+    success = (rng.random(n_items) < 0.8).astype(np.int32)
+    rows = rng.random((n_items, 4))
+    rows[3] = np.nan
+    total = D.reduce_counts(D.local_counts(rows[lo:hi], success[lo:hi]))
+    gathered = D.gather_rows(rows[lo:hi])
+    ok = (total.tolist() == [n_items, int(success.sum()), 1]) and np.array_equal(
+        np.nan_to_num(gathered, nan=-1.0), np.nan_to_num(rows, nan=-1.0))
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_count_reduction():
+    import torch.multiprocessing as mp
+
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, 37, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
