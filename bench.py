@@ -27,6 +27,9 @@ import numpy as np  # noqa: E402
 LATTICE, CHI_MAX, ERROR_RATE, BIAS, CUT, SEED = 5, 64, 0.05, 0.1, 1e-17, 123
 WORKLOAD = f"surface_d{LATTICE}_bitflip_p{ERROR_RATE}_bias{BIAS}_chi{CHI_MAX}_cut{CUT}_optimised"
 REF_FLOP_PER_NONTRIVIAL = 47.98e9 + 1.70e9  # LAPACK-count of the reference's call sequence
+# dram__bytes_read.sum + dram__bytes_write.sum of decode_kernel<64> from the `ncu --set full` capture summarised
+# in profiles/r01_decode_kernel_ncu_summary.md: 13.10 GB for a launch of 143 non-trivial syndromes
+DRAM_BYTES_PER_NONTRIVIAL = 13.10e9 / 143
 
 
 def seeded_errors(n_qubits, rate, count, seed, offset=0):
@@ -66,43 +69,80 @@ def _cpu_worker(err):
     return int(ok)
 
 
-def cpu_rate(errors, cores):
+def cpu_rate(errors, cores, budget_s=25.0):
+    """Decode `errors` on `cores` worker processes for at most ~budget_s seconds of measured time; returns
+    (syndromes/s, seconds, n_done, n_success).  Bounded so the default bench always ends within minutes."""
     import multiprocessing as mp
 
     os.environ["OMP_NUM_THREADS"] = "1"  # the reference's own cluster convention (quantum_surface_cc.sh:58)
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init) as pool:
-        pool.map(_cpu_worker, errors[:cores])  # warm the workers (imports, BLAS init)
+    pool = ctx.Pool(cores, initializer=_cpu_init)
+    try:
+        warm = pool.map_async(_cpu_worker, errors[:cores])  # imports, BLAS init, first decode
+        warm.get(timeout=180)
         t0 = time.perf_counter()
-        oks = pool.map(_cpu_worker, errors, chunksize=1)
+        done, oks = 0, 0
+        it = pool.imap_unordered(_cpu_worker, errors, chunksize=1)
+        while done < len(errors):
+            remaining = budget_s - (time.perf_counter() - t0)
+            try:
+                oks += it.next(timeout=max(remaining, 0.01))
+                done += 1
+            except mp.TimeoutError:
+                break
         dt = time.perf_counter() - t0
-    return len(errors) / dt, dt, int(sum(oks))
+    finally:
+        pool.terminate()
+        pool.join()
+    return done / dt, dt, done, oks
+
+
+def cpu_sample_main():
+    """`bench.py --cpu-sample`: the bounded CPU sample, in its own interpreter (no torch, no CUDA context, so
+    forking the worker pool is safe).  Prints one JSON object."""
+    cores = min(len(os.sched_getaffinity(0)), 64)
+    n = LATTICE * LATTICE + (LATTICE - 1) ** 2
+    sample = seeded_errors(n, ERROR_RATE, 2 * cores, SEED)
+    r, dt, done, _ = cpu_rate(sample, cores)
+    print(json.dumps({"value": r, "unit": "syndromes/s", "cores": cores, "kind": "port",
+                      "sample": f"{done} of the first {len(sample)} seeded syndromes of the workload in {dt:.1f}s, "
+                                f"oracle port of the reference algorithm, multiprocessing.Pool({cores}), "
+                                "one BLAS thread per worker"}), flush=True)
+
+
+def cpu_baseline_subprocess():
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-sample"], capture_output=True,
+                             text=True, timeout=300)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:  # noqa: BLE001
+        return {"value": None, "unit": "syndromes/s", "cores": 0, "kind": "port", "sample": f"failed: {exc!r}"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = len(os.sched_getaffinity(0))
+    cores = min(len(os.sched_getaffinity(0)), 64)
     n = LATTICE * LATTICE + (LATTICE - 1) ** 2
-    per_step = max(cores, min(2 * cores, 64))
+    per_step = 2 * cores
     errors = seeded_errors(n, ERROR_RATE, per_step * (args.steps + args.warmup), SEED)
     rates, times = [], []
     for step in range(args.warmup + args.steps):
         chunk = errors[step * per_step:(step + 1) * per_step]
-        r, dt, _ = cpu_rate(chunk, cores)
+        r, dt, done, _ = cpu_rate(chunk, cores)
         if step >= args.warmup:
-            rates.append(r)
+            rates.append(done)
             times.append(dt)
-    total = per_step * args.steps / sum(times)
+    total = sum(rates) / sum(times)
     line = {
         "impl": "reference", "metric": "decoded syndromes/sec", "value": total, "unit": "syndromes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": per_step, "seed": SEED},
+        "config": {"workload": WORKLOAD, "batch_per_step": per_step, "seed": SEED, "done_per_step": rates},
         "cpu_baseline": {"value": total, "unit": "syndromes/s", "cores": cores, "kind": "port",
-                         "sample": f"{per_step} seeded syndromes per step x {args.steps} steps, "
-                                   f"multiprocessing.Pool({cores}), OMP_NUM_THREADS=1"},
+                         "sample": f"up to {per_step} seeded syndromes per step x {args.steps} steps (25 s cap "
+                                   f"per step), multiprocessing.Pool({cores}), one BLAS thread per worker"},
         "e2e": {"value": total, "unit": "syndromes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -260,14 +300,9 @@ def run_ours(args):
         flops = counters["flops_qr"] + counters["flops_jacobi"] + counters["flops_apply"]
         kernel_s = (sum(step_ms) / args.steps) * 1e-3
         achieved = flops / kernel_s / 1e12
-        cores = len(os.sched_getaffinity(0))
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            sample = seeded_errors(n, ERROR_RATE, max(cores, min(2 * cores, 64)), SEED)
-            r, dt, _ = cpu_rate(sample, cores)
-            cpu = {"value": r, "unit": "syndromes/s", "cores": cores, "kind": "port",
-                   "sample": f"first {len(sample)} seeded syndromes of the workload, oracle port of the reference "
-                             f"algorithm, multiprocessing.Pool({cores}), OMP_NUM_THREADS=1, {dt:.1f}s"}
+            cpu = cpu_baseline_subprocess()
         line = {
             "metric": "decoded syndromes/sec", "value": value, "unit": "syndromes/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -279,7 +314,11 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(len(nontriv) * ((1 << k) * 8 + 8))},
             "gpu_launches": args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": achieved / fp64_peak if fp64_peak else None,
+                         "traffic": DRAM_BYTES_PER_NONTRIVIAL * len(nontriv),
+                         "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/ (91.6 MB per "
+                                         "non-trivial syndrome; algorithmic bytes are higher because L2 absorbs the "
+                                         "carried-matrix round trips)",
                          "kernel": "decode_kernel<64>", "note": "FP64 pipe (B200 DMMA peak = cuBLAS DGEMM 8192^3 "
                          "measured in this run); achieved = FLOPs the kernel's own counters report per launch / "
                          "CUDA-event duration", "flops_per_launch": flops,
@@ -310,8 +349,11 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="syndromes per GPU per step")
     ap.add_argument("--mode", default="fast", choices=["fast", "svd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.cpu_sample:
+        cpu_sample_main()
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -505,19 +505,15 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
   constexpr int RPT = N2 / 4;               // register rows per thread
   constexpr int CH = RPT < 8 ? RPT : 8;     // register rows per chunk
   constexpr int NCHK = RPT / CH;            // chunk c covers matrix rows [4*CH*c, 4*CH*(c+1))
-  constexpr int NWARP = (CHI * 8 < 64 ? 64 : CHI * 8) / 32;
-  // register slot idx = 2*i2 + e holds matrix row 8*i2 + 2*part + e (pairs of rows -> 16-byte LDS)
+  // register slot idx = 2*i2 + e holds matrix row 8*i2 + 2*part + e (pairs of rows -> 16-byte LDS of v)
   const int tid = threadIdx.x;
   const int col = tid >> 2, part = tid & 3, lane = tid & 31;
   const bool col_ok = col < C;
-  // Reflector j is kept as the RAW pivot column Vall[j][:] (rows <= j hold R entries and are masked by the
-  // readers) plus tau[j] and scal[j]: v_j = (0, .., 0, 1, scal_j * raw[j+1:]).  The owner therefore does no
-  // arithmetic on its column in the serial section.
   double* Vall = s.P2;
-  double* scal_arr = s.vn2;
+  constexpr int NWARP = (CHI * 8 < 64 ? 64 : CHI * 8) / 32;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(s.vn1);  // one key per warp
-  // key = norm bits with the low byte replaced by (255 - column): integer max == largest norm, ties (to
-  // ~1e-14 relative) towards the lowest column index; 0 = closed / padded column
+  // key = bits of the SQUARED norm with the low byte replaced by (255 - column): integer max == largest
+  // norm, ties (to ~1e-14 relative) towards the lowest column index; 0 = closed / padded column
   auto norm_key = [](double nrm, int c) -> unsigned long long {
     return ((unsigned long long)__double_as_longlong(nrm) & ~0xFFull) | (unsigned long long)(0xFF - c);
   };
@@ -535,17 +531,15 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
     int r = 8 * (idx >> 1) + 2 * part + (idx & 1);
     x[idx] = (col_ok && r < R) ? orig[(size_t)r * C + col] : 0.0;
   }
-  double nrm_me;   // norm of the not-yet-eliminated part of this thread group's column
-  double a_me;     // its entry in the next pivot row (valid in all 4 lanes of the group)
+  double nn_me;  // SQUARED norm of the not-yet-eliminated part of this thread group's column
   {
     double nn = 0.0;
 #pragma unroll
     for (int idx = 0; idx < RPT; ++idx) nn += x[idx] * x[idx];
     nn += __shfl_xor_sync(0xffffffffu, nn, 1);
     nn += __shfl_xor_sync(0xffffffffu, nn, 2);
-    nrm_me = sqrt(nn);
-    a_me = __shfl_sync(0xffffffffu, x[0], lane & ~3);
-    warp_key_publish(col_ok ? norm_key(nrm_me, col) : 0ull);
+    nn_me = nn;
+    warp_key_publish(col_ok ? norm_key(nn_me, col) : 0ull);
   }
   __syncthreads();
   double thresh = 0.0;
@@ -553,7 +547,7 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
   int K = 0, more = 0;
   bool open = col_ok;
   for (int j = 0; j < jmax; ++j) {
-    // ---- pivot: max over the per-warp keys, computed redundantly by every warp ----
+    // ---- pivot: max over the per-warp keys (norm bits | inverted column index), redundantly per warp ----
     unsigned long long key = (lane < NWARP) ? keys[lane] : 0ull;
 #pragma unroll
     for (int off = NWARP / 2; off; off >>= 1) {
@@ -563,65 +557,61 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
     key = __shfl_sync(0xffffffffu, key, 0);
     const double best = key ? __longlong_as_double((long long)(key & ~0xFFull)) : -1.0;
     const int bi = 0xFF - (int)(key & 0xFFull);
-    if (j == 0) thresh = best * rel_tol;
+    if (j == 0) thresh = best * rel_tol * rel_tol;  // keys carry squared norms
     if (!(best > thresh)) break;
     if (j >= kmax) { more = 1; break; }
     const bool owner = (col == bi);
-    if (owner) {  // serial section: three scalars and the raw column
-      const double a = a_me;
-      const double beta = -copysign(nrm_me, a);   // R[j, j]; ||x[j:]|| is already known
+    if (owner) {
+      // pivot row entry a = x[row j]; beta = -sign(a) * ||x[j:]||  (the norm is already known)
+      const int jslot = ((j >> 3) << 1) | (j & 1), jpart = (j >> 1) & 3;
+      double a = 0.0;
+#pragma unroll
+      for (int idx = 0; idx < RPT; ++idx)
+        if (idx == jslot) a = x[idx];
+      a = __shfl_sync(0xFu << (lane & ~3), a, (lane & ~3) | jpart);
+      const double beta = -copysign(sqrt(nn_me), a);
       const double d = a - beta;
       const double inv = 1.0 / (beta * d);
+      const double tau = -d * d * inv;   // (beta - a) / beta
+      const double scal = beta * inv;    // 1 / (a - beta)
 #pragma unroll
-      for (int i2 = 0; i2 < RPT / 2; ++i2)
-        *reinterpret_cast<double2*>(Vall + j * N2 + 8 * i2 + 2 * part) = make_double2(x[2 * i2], x[2 * i2 + 1]);
-      if (part == 0) {
-        s.tau[j] = -d * d * inv;     // (beta - a) / beta
-        scal_arr[j] = beta * inv;    // 1 / (a - beta)
-        s.dscr[10] = beta;
+      for (int i2 = 0; i2 < RPT / 2; ++i2) {
+        const int r0 = 8 * i2 + 2 * part;
+        double2 v;
+        v.x = (r0 > j) ? x[2 * i2] * scal : ((r0 == j) ? 1.0 : 0.0);
+        v.y = (r0 + 1 > j) ? x[2 * i2 + 1] * scal : ((r0 + 1 == j) ? 1.0 : 0.0);
+        *reinterpret_cast<double2*>(Vall + j * N2 + r0) = v;
+        if (r0 == j) x[2 * i2] = beta; else if (r0 > j) x[2 * i2] = 0.0;
+        if (r0 + 1 == j) x[2 * i2 + 1] = beta; else if (r0 + 1 > j) x[2 * i2 + 1] = 0.0;
       }
+      if (part == 0) s.tau[j] = tau;
+      open = false;
     }
     __syncthreads();
     if (__any_sync(0xffffffffu, open)) {
       // ---- apply H_j.  Closed columns are invariant (their entries below their own pivot row are exactly
-      //      zero); the pivot column itself is masked.  Row chunks entirely above the pivot row or below the
-      //      matrix are skipped (warp-uniform). ----
-      const double tau = s.tau[j], scal = scal_arr[j];
-      const int jslot = ((j >> 3) << 1) | (j & 1), jpart = (j >> 1) & 3;
-      const int nslot = (((j + 1) >> 3) << 1) | ((j + 1) & 1), npart = ((j + 1) >> 1) & 3;
-      const double2* rc = reinterpret_cast<const double2*>(Vall + j * N2 + 2 * part);
-      double w = 0.0, xj = 0.0;
+      //      zero, so v.x == 0); only the pivot column itself must be masked.  Row chunks entirely above
+      //      the pivot row or below the matrix are skipped (warp-uniform). ----
+      const double tau = s.tau[j];
+      const double2* vj = reinterpret_cast<const double2*>(Vall + j * N2 + 2 * part);
+      double w = 0.0;
 #pragma unroll
       for (int c = 0; c < NCHK; ++c) {
         if (4 * CH * (c + 1) > j && 4 * CH * c < R) {
           double w0 = 0.0, w1 = 0.0;
-          if (4 * CH * c > j) {
 #pragma unroll
-            for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
-              const double2 v = rc[4 * i2];
-              w0 += v.x * x[2 * i2];
-              w1 += v.y * x[2 * i2 + 1];
-            }
-          } else {
-#pragma unroll
-            for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
-              const int r0 = 8 * i2 + 2 * part;
-              const double2 v = rc[4 * i2];
-              if (r0 > j) w0 += v.x * x[2 * i2];
-              if (r0 + 1 > j) w1 += v.y * x[2 * i2 + 1];
-              if (2 * i2 == jslot) xj = x[2 * i2];
-              if (2 * i2 + 1 == jslot) xj = x[2 * i2 + 1];
-            }
+          for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
+            const double2 v = vj[4 * i2];
+            w0 += v.x * x[2 * i2];
+            w1 += v.y * x[2 * i2 + 1];
           }
           w += w0 + w1;
         }
       }
       w += __shfl_xor_sync(0xffffffffu, w, 1);
       w += __shfl_xor_sync(0xffffffffu, w, 2);
-      xj = __shfl_sync(0xffffffffu, xj, (lane & ~3) | jpart);
-      w = owner ? 0.0 : tau * (xj + scal * w);   // tau * v^T x
-      const double ws = w * scal;
-      double nn = 0.0, an = 0.0;
+      w = owner ? 0.0 : w * tau;
+      double nn = 0.0;
 #pragma unroll
       for (int c = 0; c < NCHK; ++c) {
         if (4 * CH * (c + 1) > j && 4 * CH * c < R) {
@@ -629,8 +619,8 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
           if (4 * CH * c > j) {  // every row of the chunk is below the pivot row
 #pragma unroll
             for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
-              const double2 v = rc[4 * i2];
-              const double xa = x[2 * i2] - ws * v.x, xb = x[2 * i2 + 1] - ws * v.y;
+              const double2 v = vj[4 * i2];
+              const double xa = x[2 * i2] - w * v.x, xb = x[2 * i2 + 1] - w * v.y;
               x[2 * i2] = xa; x[2 * i2 + 1] = xb;
               s0 += xa * xa; s1 += xb * xb;
             }
@@ -638,38 +628,23 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
 #pragma unroll
             for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
               const int r0 = 8 * i2 + 2 * part;
-              const double2 v = rc[4 * i2];
-              double xa = x[2 * i2], xb = x[2 * i2 + 1];
-              if (r0 > j) { xa -= ws * v.x; s0 += xa * xa; } else if (r0 == j) xa -= w;
-              if (r0 + 1 > j) { xb -= ws * v.y; s1 += xb * xb; } else if (r0 + 1 == j) xb -= w;
+              const double2 v = vj[4 * i2];
+              const double xa = x[2 * i2] - w * v.x, xb = x[2 * i2 + 1] - w * v.y;
               x[2 * i2] = xa; x[2 * i2 + 1] = xb;
+              if (r0 > j) s0 += xa * xa;
+              if (r0 + 1 > j) s1 += xb * xb;
             }
           }
           nn += s0 + s1;
         }
-        if (4 * CH * c <= j + 1 && j + 1 < 4 * CH * (c + 1)) {  // chunk holding the next pivot row
-#pragma unroll
-          for (int idx = c * CH; idx < (c + 1) * CH; ++idx)
-            if (idx == nslot) an = x[idx];
-        }
       }
       nn += __shfl_xor_sync(0xffffffffu, nn, 1);
       nn += __shfl_xor_sync(0xffffffffu, nn, 2);
-      nrm_me = sqrt(nn);
-      a_me = __shfl_sync(0xffffffffu, an, (lane & ~3) | npart);
-      if (owner) {  // keep R[0:j+1, j] in registers, zero below (what makes closed columns invariant)
-        const double beta = s.dscr[10];
-#pragma unroll
-        for (int idx = 0; idx < RPT; ++idx) {
-          const int r = 8 * (idx >> 1) + 2 * part + (idx & 1);
-          if (r == j) x[idx] = beta; else if (r > j) x[idx] = 0.0;
-        }
-        open = false;
-      }
+      nn_me = nn;
     }
     // per-warp maximum of the open columns' keys; written after the first barrier of the iteration, so no
     // warp's pivot search can race it
-    warp_key_publish(open ? norm_key(nrm_me, col) : 0ull);
+    warp_key_publish(open ? norm_key(nn_me, col) : 0ull);
     __syncthreads();
     K = j + 1;
   }
@@ -690,9 +665,8 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
   __syncthreads();
 }
 
-// Q = H_0 ... H_{K-1} [I_K; 0] in registers (8 threads per column, rows interleaved), written to s.P2 as a
-// flat R x K matrix (ld K) after every thread has finished reading the reflectors from it.  Reflectors are
-// read in the raw-column form qrcp_reg leaves (see there).
+// Q = H_0 ... H_{K-1} [I_K; 0] in registers (8 threads per column, rows interleaved mod 8), written to
+// s.P2 as a flat R x K matrix (ld K) after every thread has finished reading the reflectors from it.
 template <int CHI>
 __device__ __noinline__ void form_q_reg(Smem<CHI>& s, int R, int K) {
   constexpr int N2 = Smem<CHI>::N2;
@@ -700,42 +674,28 @@ __device__ __noinline__ void form_q_reg(Smem<CHI>& s, int R, int K) {
   constexpr int CH = RPT < 8 ? RPT : 8;
   constexpr int NCHK = RPT / CH;            // chunk c covers matrix rows [8*CH*c, 8*CH*(c+1))
   // register slot idx = 2*i2 + e holds matrix row 16*i2 + 2*part + e
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int col = tid >> 3, part = tid & 7;
   const int warp_col0 = (tid >> 5) * 4;     // first of the 4 columns this warp owns
   const double* Vall = s.P2;
-  const double* scal_arr = s.vn2;
   double q[RPT];
 #pragma unroll
   for (int idx = 0; idx < RPT; ++idx) q[idx] = (16 * (idx >> 1) + 2 * part + (idx & 1) == col) ? 1.0 : 0.0;
   // H_j leaves e_c untouched for j > c, so a warp starts at its largest column index
   const int jstart = (warp_col0 < K) ? min(K - 1, warp_col0 + 3) : -1;
   for (int j = jstart; j >= 0; --j) {
-    const double tau = s.tau[j], scal = scal_arr[j];
-    const int jslot = ((j >> 4) << 1) | (j & 1), jpart = (j >> 1) & 7;
-    const double2* rc = reinterpret_cast<const double2*>(Vall + j * N2 + 2 * part);
-    double w = 0.0, qj = 0.0;
+    const double tau = s.tau[j];
+    const double2* vj = reinterpret_cast<const double2*>(Vall + j * N2 + 2 * part);
+    double w = 0.0;
 #pragma unroll
     for (int c = 0; c < NCHK; ++c) {
       if (8 * CH * (c + 1) > j && 8 * CH * c < R) {
         double w0 = 0.0, w1 = 0.0;
-        if (8 * CH * c > j) {
 #pragma unroll
-          for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
-            const double2 v = rc[8 * i2];
-            w0 += v.x * q[2 * i2];
-            w1 += v.y * q[2 * i2 + 1];
-          }
-        } else {
-#pragma unroll
-          for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
-            const int r0 = 16 * i2 + 2 * part;
-            const double2 v = rc[8 * i2];
-            if (r0 > j) w0 += v.x * q[2 * i2];
-            if (r0 + 1 > j) w1 += v.y * q[2 * i2 + 1];
-            if (2 * i2 == jslot) qj = q[2 * i2];
-            if (2 * i2 + 1 == jslot) qj = q[2 * i2 + 1];
-          }
+        for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
+          const double2 v = vj[8 * i2];
+          w0 += v.x * q[2 * i2];
+          w1 += v.y * q[2 * i2 + 1];
         }
         w += w0 + w1;
       }
@@ -743,27 +703,15 @@ __device__ __noinline__ void form_q_reg(Smem<CHI>& s, int R, int K) {
     w += __shfl_xor_sync(0xffffffffu, w, 1);
     w += __shfl_xor_sync(0xffffffffu, w, 2);
     w += __shfl_xor_sync(0xffffffffu, w, 4);
-    qj = __shfl_sync(0xffffffffu, qj, (lane & ~7) | jpart);
-    w = tau * (qj + scal * w);
-    const double ws = w * scal;
+    w *= tau;
 #pragma unroll
     for (int c = 0; c < NCHK; ++c) {
       if (8 * CH * (c + 1) > j && 8 * CH * c < R) {
-        if (8 * CH * c > j) {
 #pragma unroll
-          for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
-            const double2 v = rc[8 * i2];
-            q[2 * i2] -= ws * v.x;
-            q[2 * i2 + 1] -= ws * v.y;
-          }
-        } else {
-#pragma unroll
-          for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
-            const int r0 = 16 * i2 + 2 * part;
-            const double2 v = rc[8 * i2];
-            if (r0 > j) q[2 * i2] -= ws * v.x; else if (r0 == j) q[2 * i2] -= w;
-            if (r0 + 1 > j) q[2 * i2 + 1] -= ws * v.y; else if (r0 + 1 == j) q[2 * i2 + 1] -= w;
-          }
+        for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
+          const double2 v = vj[8 * i2];
+          q[2 * i2] -= w * v.x;
+          q[2 * i2 + 1] -= w * v.y;
         }
       }
     }

@@ -86,6 +86,7 @@ decode_kernel(DecodeParams P, const int* __restrict__ prog, const double* __rest
     atomicAdd(counters + 12, s.cnt.cyc_io);
     atomicAdd(counters + 13, s.cnt.cyc_coef);
     atomicAdd(counters + 14, s.cnt.cyc_total);
+    atomicAdd(counters + 15, s.cnt.cyc_pad);
   }
 }
 

@@ -144,7 +144,7 @@ class DecodeEngine:
     def read_counters(self) -> Dict[str, float]:
         c = self.counters.cpu().numpy()
         keys = ["flops_qr", "flops_jacobi", "flops_apply", "bytes", "steps", "truncating_steps", "jacobi_sweeps",
-                "qr_reflectors", "cyc_qr", "cyc_formq", "cyc_jacobi", "cyc_apply", "cyc_io", "cyc_coef", "cyc_total"]
+                "qr_reflectors", "cyc_qr", "cyc_formq", "cyc_jacobi", "cyc_apply", "cyc_io", "cyc_coef", "cyc_total", "cyc_pad"]
         return {k: float(v) for k, v in zip(keys, c)}
 
 

@@ -43,6 +43,7 @@ SWAP = _tensor((2, 2, 2, 2), lambda a, b, u, d: (a == b) and (u == d))
 # svd / split.  Reference: mdopt/utils/utils.py:29-138 and :290-383.
 # --------------------------------------------------------------------------------------------------
 
+TRUNC_LOG = None  # tests may set this to a list; every svd() appends (discarded weight, largest s)
 SVD_HOOK = None  # tests may inject ``f(mat) -> (u, s, vh)`` the way the reference's xp.linalg.svd hook allows
 
 
@@ -78,6 +79,8 @@ def svd(mat, cut=1e-12, chi_max=int(1e4), renormalise=False):
     s = np.asarray(s, dtype=float)
     keep = min(int(chi_max), int(np.count_nonzero(s > cut)))  # utils.py:119
     trunc_err = float(np.sum(s[keep:] ** 2))  # utils.py:120-121
+    if TRUNC_LOG is not None:
+        TRUNC_LOG.append((trunc_err, float(s[0]) if s.size else 0.0))
     u, s, vh = u[:, :keep], s[:keep], vh[:keep, :]
     if renormalise and s.size:
         nrm = float(np.linalg.norm(s))
@@ -588,6 +591,18 @@ def surface_code(L):
     zs = [sorted([i * n + j for i in h[r]] + [n * n + r * m + c for c in range(m) if j in h[c]])
           for r in range(m) for j in range(n)]
     return CssCode(n * n + m * m, xs, zs, [[n - 1 + i * n for i in range(n)]], [list(range(n))])
+
+
+def decode_truncates(code, error, rel=1e-22, **kw):
+    """True when the reference algorithm discards weight above rel * s0^2 in any split of this decode, i.e.
+    when the result depends on how LAPACK resolves (possibly degenerate) truncations."""
+    global TRUNC_LOG
+    TRUNC_LOG = []
+    try:
+        decode_css(code, error, **kw)
+        return any(err > rel * s0 * s0 for err, s0 in TRUNC_LOG)
+    finally:
+        TRUNC_LOG = None
 
 
 def seeded_errors(num_qubits, rate, count, seed, model="Bitflip"):

@@ -130,14 +130,20 @@ def test_full_size_batch_properties(api):
 @pytest.mark.parametrize("mode", ["fast", "svd"])
 def test_depolarising_bias_and_errors(api, mode):
     """SURVEY 8a row a4 / config-3 style: depolarising errors (X, Y, Z) with the two-site depolarising bias.
-    Syndromes with both a literal X and a literal Z truncate inside degenerate multiplets at chi=64."""
+    The depolarising bias roughly squares the bond dimension, so many d=3 syndromes truncate at chi=64; the
+    oracle tells which (decode_truncates) and only those get the loose, ill-posed-truncation tolerance."""
     g = load_golden("d3_chi64_depol")
     kw = dict(g["kwargs"])
     errors = [r["error"] for r in g["results"]]
     dist, success, status = api["decode_css_batch"](api["surface_code"](3), errors, contraction_strategy="Optimised",
                                                     mode=mode, return_status=True, **kw)
     assert (status == 0).all()
+    ocode = O.surface_code(3)
+    exact = 0
     for b, r in enumerate(g["results"]):
         assert int(success[b]) == r["success"], r["error"]
-        both = "X" in r["error"] and "Z" in r["error"]
-        np.testing.assert_allclose(dist[b], r["dist"], rtol=0.1 if both else 1e-10, atol=1e-13)
+        trivial = set(r["error"]) == {"I"}
+        truncating = (not trivial) and O.decode_truncates(ocode, r["error"], contraction_strategy="Optimised", **kw)
+        np.testing.assert_allclose(dist[b], r["dist"], rtol=0.1 if truncating else 1e-10, atol=1e-13)
+        exact += not truncating
+    assert exact >= 10
