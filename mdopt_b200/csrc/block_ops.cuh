@@ -498,16 +498,16 @@ MD_DEV void truncation_rule(Smem<CHI>& s, int C, int chi_lim, double cut) {
 // Pivot rule and stop rule are identical to qrcp<> above (largest remaining column norm, ties to the
 // lowest column index; stop at rel_tol * largest initial norm or at kmax).
 // =================================================================================================
-template <int CHI>
+template <int CHI, int TPC>
 __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, int C, int kmax, double rel_tol) {
   constexpr int LD = Smem<CHI>::LD;
   constexpr int N2 = Smem<CHI>::N2;
-  constexpr int RPT = N2 / 4;               // register rows per thread
+  constexpr int RPT = N2 / TPC;             // register rows per thread (TPC threads per column)
   constexpr int CH = RPT < 8 ? RPT : 8;     // register rows per chunk
-  constexpr int NCHK = RPT / CH;            // chunk c covers matrix rows [4*CH*c, 4*CH*(c+1))
-  // register slot idx = 2*i2 + e holds matrix row 8*i2 + 2*part + e (pairs of rows -> 16-byte LDS of v)
+  constexpr int NCHK = RPT / CH;            // chunk c covers matrix rows [TPC*CH*c, TPC*CH*(c+1))
+  // register slot idx = 2*i2 + e holds matrix row 2*TPC*i2 + 2*part + e (pairs of rows -> 16-byte LDS of v)
   const int tid = threadIdx.x;
-  const int col = tid >> 2, part = tid & 3, lane = tid & 31;
+  const int col = tid / TPC, part = tid % TPC, lane = tid & 31;
   const bool col_ok = col < C;
   double* Vall = s.P2;
   constexpr int NWARP = (CHI * 8 < 64 ? 64 : CHI * 8) / 32;
@@ -519,7 +519,7 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
   };
   auto warp_key_publish = [&](unsigned long long k) {
 #pragma unroll
-    for (int off = 4; off < 32; off <<= 1) {
+    for (int off = TPC; off < 32; off <<= 1) {
       const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, off);
       k = o > k ? o : k;
     }
@@ -528,7 +528,7 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
   double x[RPT];
 #pragma unroll
   for (int idx = 0; idx < RPT; ++idx) {
-    int r = 8 * (idx >> 1) + 2 * part + (idx & 1);
+    int r = 2 * TPC * (idx >> 1) + 2 * part + (idx & 1);
     x[idx] = (col_ok && r < R) ? orig[(size_t)r * C + col] : 0.0;
   }
   double nn_me;  // SQUARED norm of the not-yet-eliminated part of this thread group's column
@@ -536,8 +536,8 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
     double nn = 0.0;
 #pragma unroll
     for (int idx = 0; idx < RPT; ++idx) nn += x[idx] * x[idx];
-    nn += __shfl_xor_sync(0xffffffffu, nn, 1);
-    nn += __shfl_xor_sync(0xffffffffu, nn, 2);
+#pragma unroll
+    for (int off = 1; off < TPC; off <<= 1) nn += __shfl_xor_sync(0xffffffffu, nn, off);
     nn_me = nn;
     warp_key_publish(col_ok ? norm_key(nn_me, col) : 0ull);
   }
@@ -563,12 +563,12 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
     const bool owner = (col == bi);
     if (owner) {
       // pivot row entry a = x[row j]; beta = -sign(a) * ||x[j:]||  (the norm is already known)
-      const int jslot = ((j >> 3) << 1) | (j & 1), jpart = (j >> 1) & 3;
+      const int jslot = ((j / (2 * TPC)) << 1) | (j & 1), jpart = (j >> 1) % TPC;
       double a = 0.0;
 #pragma unroll
       for (int idx = 0; idx < RPT; ++idx)
         if (idx == jslot) a = x[idx];
-      a = __shfl_sync(0xFu << (lane & ~3), a, (lane & ~3) | jpart);
+      a = __shfl_sync(((1u << TPC) - 1u) << (lane & ~(TPC - 1)), a, (lane & ~(TPC - 1)) | jpart);
       const double beta = -copysign(sqrt(nn_me), a);
       const double d = a - beta;
       const double inv = 1.0 / (beta * d);
@@ -576,7 +576,7 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
       const double scal = beta * inv;    // 1 / (a - beta)
 #pragma unroll
       for (int i2 = 0; i2 < RPT / 2; ++i2) {
-        const int r0 = 8 * i2 + 2 * part;
+        const int r0 = 2 * TPC * i2 + 2 * part;
         double2 v;
         v.x = (r0 > j) ? x[2 * i2] * scal : ((r0 == j) ? 1.0 : 0.0);
         v.y = (r0 + 1 > j) ? x[2 * i2 + 1] * scal : ((r0 + 1 == j) ? 1.0 : 0.0);
@@ -597,29 +597,29 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
       double w = 0.0;
 #pragma unroll
       for (int c = 0; c < NCHK; ++c) {
-        if (4 * CH * (c + 1) > j && 4 * CH * c < R) {
+        if (TPC * CH * (c + 1) > j && TPC * CH * c < R) {
           double w0 = 0.0, w1 = 0.0;
 #pragma unroll
           for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
-            const double2 v = vj[4 * i2];
+            const double2 v = vj[TPC * i2];
             w0 += v.x * x[2 * i2];
             w1 += v.y * x[2 * i2 + 1];
           }
           w += w0 + w1;
         }
       }
-      w += __shfl_xor_sync(0xffffffffu, w, 1);
-      w += __shfl_xor_sync(0xffffffffu, w, 2);
+#pragma unroll
+      for (int off = 1; off < TPC; off <<= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
       w = owner ? 0.0 : w * tau;
       double nn = 0.0;
 #pragma unroll
       for (int c = 0; c < NCHK; ++c) {
-        if (4 * CH * (c + 1) > j && 4 * CH * c < R) {
+        if (TPC * CH * (c + 1) > j && TPC * CH * c < R) {
           double s0 = 0.0, s1 = 0.0;
-          if (4 * CH * c > j) {  // every row of the chunk is below the pivot row
+          if (TPC * CH * c > j) {  // every row of the chunk is below the pivot row
 #pragma unroll
             for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
-              const double2 v = vj[4 * i2];
+              const double2 v = vj[TPC * i2];
               const double xa = x[2 * i2] - w * v.x, xb = x[2 * i2 + 1] - w * v.y;
               x[2 * i2] = xa; x[2 * i2 + 1] = xb;
               s0 += xa * xa; s1 += xb * xb;
@@ -627,8 +627,8 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
           } else {
 #pragma unroll
             for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
-              const int r0 = 8 * i2 + 2 * part;
-              const double2 v = vj[4 * i2];
+              const int r0 = 2 * TPC * i2 + 2 * part;
+              const double2 v = vj[TPC * i2];
               const double xa = x[2 * i2] - w * v.x, xb = x[2 * i2 + 1] - w * v.y;
               x[2 * i2] = xa; x[2 * i2 + 1] = xb;
               if (r0 > j) s0 += xa * xa;
@@ -638,8 +638,8 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
           nn += s0 + s1;
         }
       }
-      nn += __shfl_xor_sync(0xffffffffu, nn, 1);
-      nn += __shfl_xor_sync(0xffffffffu, nn, 2);
+#pragma unroll
+      for (int off = 1; off < TPC; off <<= 1) nn += __shfl_xor_sync(0xffffffffu, nn, off);
       nn_me = nn;
     }
     // per-warp maximum of the open columns' keys; written after the first barrier of the iteration, so no
@@ -651,7 +651,7 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
   if (!more) {
 #pragma unroll
     for (int idx = 0; idx < RPT; ++idx) {
-      int r = 8 * (idx >> 1) + 2 * part + (idx & 1);
+      int r = 2 * TPC * (idx >> 1) + 2 * part + (idx & 1);
       if (col_ok && r < K) s.X[r * LD + col] = x[idx];
     }
   }
