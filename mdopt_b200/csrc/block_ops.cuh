@@ -498,24 +498,27 @@ MD_DEV void truncation_rule(Smem<CHI>& s, int C, int chi_lim, double cut) {
 // Pivot rule and stop rule are identical to qrcp<> above (largest remaining column norm, ties to the
 // lowest column index; stop at rel_tol * largest initial norm or at kmax).
 // =================================================================================================
-template <int CHI, int TPC>
+template <int CHI, int TPC, int CPT>
 __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, int C, int kmax, double rel_tol) {
+  // TPC threads share a column (rows interleaved in pairs), each thread group owns CPT columns
+  // (col, col + NCOL, ...).  <8,1> covers C <= CHI (every centre move), <8,2> covers C <= 2*CHI.
   constexpr int LD = Smem<CHI>::LD;
   constexpr int N2 = Smem<CHI>::N2;
-  constexpr int RPT = N2 / TPC;             // register rows per thread (TPC threads per column)
+  constexpr int NT = (CHI * 8 < 64) ? 64 : CHI * 8;
+  constexpr int NCOL = NT / TPC;            // columns covered by one pass of the thread groups
+  constexpr int RPT = N2 / TPC;             // register rows per thread and column
   constexpr int CH = RPT < 8 ? RPT : 8;     // register rows per chunk
   constexpr int NCHK = RPT / CH;            // chunk c covers matrix rows [TPC*CH*c, TPC*CH*(c+1))
+  constexpr int NWARP = NT / 32;
   // register slot idx = 2*i2 + e holds matrix row 2*TPC*i2 + 2*part + e (pairs of rows -> 16-byte LDS of v)
   const int tid = threadIdx.x;
-  const int col = tid / TPC, part = tid % TPC, lane = tid & 31;
-  const bool col_ok = col < C;
+  const int col0 = tid / TPC, part = tid % TPC, lane = tid & 31;
   double* Vall = s.P2;
-  constexpr int NWARP = (CHI * 8 < 64 ? 64 : CHI * 8) / 32;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(s.vn1);  // one key per warp
   // key = bits of the SQUARED norm with the low byte replaced by (255 - column): integer max == largest
   // norm, ties (to ~1e-14 relative) towards the lowest column index; 0 = closed / padded column
-  auto norm_key = [](double nrm, int c) -> unsigned long long {
-    return ((unsigned long long)__double_as_longlong(nrm) & ~0xFFull) | (unsigned long long)(0xFF - c);
+  auto norm_key = [](double nn, int c) -> unsigned long long {
+    return ((unsigned long long)__double_as_longlong(nn) & ~0xFFull) | (unsigned long long)(0xFF - c);
   };
   auto warp_key_publish = [&](unsigned long long k) {
 #pragma unroll
@@ -525,27 +528,38 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
     }
     if (lane == 0) keys[tid >> 5] = k;
   };
-  double x[RPT];
+  double x[CPT][RPT];
+  double nn_me[CPT];   // SQUARED norm of the not-yet-eliminated part of each owned column
+  bool open[CPT];
 #pragma unroll
-  for (int idx = 0; idx < RPT; ++idx) {
-    int r = 2 * TPC * (idx >> 1) + 2 * part + (idx & 1);
-    x[idx] = (col_ok && r < R) ? orig[(size_t)r * C + col] : 0.0;
+  for (int k = 0; k < CPT; ++k) {
+    const int col = col0 + k * NCOL;
+    open[k] = col < C;
+#pragma unroll
+    for (int idx = 0; idx < RPT; ++idx) {
+      int r = 2 * TPC * (idx >> 1) + 2 * part + (idx & 1);
+      x[k][idx] = (open[k] && r < R) ? orig[(size_t)r * C + col] : 0.0;
+    }
   }
-  double nn_me;  // SQUARED norm of the not-yet-eliminated part of this thread group's column
   {
-    double nn = 0.0;
+    unsigned long long kmax_key = 0ull;
 #pragma unroll
-    for (int idx = 0; idx < RPT; ++idx) nn += x[idx] * x[idx];
+    for (int k = 0; k < CPT; ++k) {
+      double nn = 0.0;
 #pragma unroll
-    for (int off = 1; off < TPC; off <<= 1) nn += __shfl_xor_sync(0xffffffffu, nn, off);
-    nn_me = nn;
-    warp_key_publish(col_ok ? norm_key(nn_me, col) : 0ull);
+      for (int idx = 0; idx < RPT; ++idx) nn += x[k][idx] * x[k][idx];
+#pragma unroll
+      for (int off = 1; off < TPC; off <<= 1) nn += __shfl_xor_sync(0xffffffffu, nn, off);
+      nn_me[k] = nn;
+      const unsigned long long kk = open[k] ? norm_key(nn, col0 + k * NCOL) : 0ull;
+      kmax_key = kk > kmax_key ? kk : kmax_key;
+    }
+    warp_key_publish(kmax_key);
   }
   __syncthreads();
   double thresh = 0.0;
   const int jmax = min(R, C);
   int K = 0, more = 0;
-  bool open = col_ok;
   for (int j = 0; j < jmax; ++j) {
     // ---- pivot: max over the per-warp keys (norm bits | inverted column index), redundantly per warp ----
     unsigned long long key = (lane < NWARP) ? keys[lane] : 0ull;
@@ -560,99 +574,148 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
     if (j == 0) thresh = best * rel_tol * rel_tol;  // keys carry squared norms
     if (!(best > thresh)) break;
     if (j >= kmax) { more = 1; break; }
-    const bool owner = (col == bi);
+    const int ko = (bi >= NCOL) ? bi / NCOL : 0;      // which of my columns could be the pivot
+    const bool owner = (col0 + ko * NCOL == bi);
     if (owner) {
       // pivot row entry a = x[row j]; beta = -sign(a) * ||x[j:]||  (the norm is already known)
       const int jslot = ((j / (2 * TPC)) << 1) | (j & 1), jpart = (j >> 1) % TPC;
-      double a = 0.0;
 #pragma unroll
-      for (int idx = 0; idx < RPT; ++idx)
-        if (idx == jslot) a = x[idx];
-      a = __shfl_sync(((1u << TPC) - 1u) << (lane & ~(TPC - 1)), a, (lane & ~(TPC - 1)) | jpart);
-      const double beta = -copysign(sqrt(nn_me), a);
-      const double d = a - beta;
-      const double inv = 1.0 / (beta * d);
-      const double tau = -d * d * inv;   // (beta - a) / beta
-      const double scal = beta * inv;    // 1 / (a - beta)
+      for (int k = 0; k < CPT; ++k) {
+        if (k == ko) {
+          double a = 0.0;
 #pragma unroll
-      for (int i2 = 0; i2 < RPT / 2; ++i2) {
-        const int r0 = 2 * TPC * i2 + 2 * part;
-        double2 v;
-        v.x = (r0 > j) ? x[2 * i2] * scal : ((r0 == j) ? 1.0 : 0.0);
-        v.y = (r0 + 1 > j) ? x[2 * i2 + 1] * scal : ((r0 + 1 == j) ? 1.0 : 0.0);
-        *reinterpret_cast<double2*>(Vall + j * N2 + r0) = v;
-        if (r0 == j) x[2 * i2] = beta; else if (r0 > j) x[2 * i2] = 0.0;
-        if (r0 + 1 == j) x[2 * i2 + 1] = beta; else if (r0 + 1 > j) x[2 * i2 + 1] = 0.0;
+          for (int idx = 0; idx < RPT; ++idx)
+            if (idx == jslot) a = x[k][idx];
+          a = __shfl_sync(((1u << TPC) - 1u) << (lane & ~(TPC - 1)), a, (lane & ~(TPC - 1)) | jpart);
+          const double beta = -copysign(sqrt(nn_me[k]), a);
+          const double d = a - beta;
+          const double inv = 1.0 / (beta * d);
+          const double tau = -d * d * inv;   // (beta - a) / beta
+          const double scal = beta * inv;    // 1 / (a - beta)
+#pragma unroll
+          for (int i2 = 0; i2 < RPT / 2; ++i2) {
+            const int r0 = 2 * TPC * i2 + 2 * part;
+            double2 v;
+            v.x = (r0 > j) ? x[k][2 * i2] * scal : ((r0 == j) ? 1.0 : 0.0);
+            v.y = (r0 + 1 > j) ? x[k][2 * i2 + 1] * scal : ((r0 + 1 == j) ? 1.0 : 0.0);
+            *reinterpret_cast<double2*>(Vall + j * N2 + r0) = v;
+            if (r0 == j) x[k][2 * i2] = beta; else if (r0 > j) x[k][2 * i2] = 0.0;
+            if (r0 + 1 == j) x[k][2 * i2 + 1] = beta; else if (r0 + 1 > j) x[k][2 * i2 + 1] = 0.0;
+          }
+          open[k] = false;
+          if (part == 0) s.tau[j] = tau;
+        }
       }
-      if (part == 0) s.tau[j] = tau;
-      open = false;
     }
     __syncthreads();
-    if (__any_sync(0xffffffffu, open)) {
+    bool any_open = false;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) any_open |= open[k];
+    if (__any_sync(0xffffffffu, any_open)) {
       // ---- apply H_j.  Closed columns are invariant (their entries below their own pivot row are exactly
       //      zero, so v.x == 0); only the pivot column itself must be masked.  Row chunks entirely above
-      //      the pivot row or below the matrix are skipped (warp-uniform). ----
+      //      the pivot row or below the matrix are skipped (warp-uniform).  v is loaded once per chunk and
+      //      used for all CPT columns of the thread group. ----
       const double tau = s.tau[j];
       const double2* vj = reinterpret_cast<const double2*>(Vall + j * N2 + 2 * part);
-      double w = 0.0;
+      double w[CPT];
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) w[k] = 0.0;
 #pragma unroll
       for (int c = 0; c < NCHK; ++c) {
         if (TPC * CH * (c + 1) > j && TPC * CH * c < R) {
-          double w0 = 0.0, w1 = 0.0;
+          double w0[CPT], w1[CPT];
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) { w0[k] = 0.0; w1[k] = 0.0; }
 #pragma unroll
           for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
             const double2 v = vj[TPC * i2];
-            w0 += v.x * x[2 * i2];
-            w1 += v.y * x[2 * i2 + 1];
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+              w0[k] += v.x * x[k][2 * i2];
+              w1[k] += v.y * x[k][2 * i2 + 1];
+            }
           }
-          w += w0 + w1;
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) w[k] += w0[k] + w1[k];
         }
       }
 #pragma unroll
-      for (int off = 1; off < TPC; off <<= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
-      w = owner ? 0.0 : w * tau;
-      double nn = 0.0;
+      for (int off = 1; off < TPC; off <<= 1) {
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) w[k] += __shfl_xor_sync(0xffffffffu, w[k], off);
+      }
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) w[k] = (owner && k == ko) ? 0.0 : w[k] * tau;
+      double nn[CPT];
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) nn[k] = 0.0;
 #pragma unroll
       for (int c = 0; c < NCHK; ++c) {
         if (TPC * CH * (c + 1) > j && TPC * CH * c < R) {
-          double s0 = 0.0, s1 = 0.0;
+          double s0[CPT], s1[CPT];
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) { s0[k] = 0.0; s1[k] = 0.0; }
           if (TPC * CH * c > j) {  // every row of the chunk is below the pivot row
 #pragma unroll
             for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
               const double2 v = vj[TPC * i2];
-              const double xa = x[2 * i2] - w * v.x, xb = x[2 * i2 + 1] - w * v.y;
-              x[2 * i2] = xa; x[2 * i2 + 1] = xb;
-              s0 += xa * xa; s1 += xb * xb;
+#pragma unroll
+              for (int k = 0; k < CPT; ++k) {
+                const double xa = x[k][2 * i2] - w[k] * v.x, xb = x[k][2 * i2 + 1] - w[k] * v.y;
+                x[k][2 * i2] = xa; x[k][2 * i2 + 1] = xb;
+                s0[k] += xa * xa; s1[k] += xb * xb;
+              }
             }
           } else {
 #pragma unroll
             for (int i2 = c * CH / 2; i2 < (c + 1) * CH / 2; ++i2) {
               const int r0 = 2 * TPC * i2 + 2 * part;
               const double2 v = vj[TPC * i2];
-              const double xa = x[2 * i2] - w * v.x, xb = x[2 * i2 + 1] - w * v.y;
-              x[2 * i2] = xa; x[2 * i2 + 1] = xb;
-              if (r0 > j) s0 += xa * xa;
-              if (r0 + 1 > j) s1 += xb * xb;
+#pragma unroll
+              for (int k = 0; k < CPT; ++k) {
+                const double xa = x[k][2 * i2] - w[k] * v.x, xb = x[k][2 * i2 + 1] - w[k] * v.y;
+                x[k][2 * i2] = xa; x[k][2 * i2 + 1] = xb;
+                if (r0 > j) s0[k] += xa * xa;
+                if (r0 + 1 > j) s1[k] += xb * xb;
+              }
             }
           }
-          nn += s0 + s1;
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) nn[k] += s0[k] + s1[k];
         }
       }
 #pragma unroll
-      for (int off = 1; off < TPC; off <<= 1) nn += __shfl_xor_sync(0xffffffffu, nn, off);
-      nn_me = nn;
+      for (int off = 1; off < TPC; off <<= 1) {
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) nn[k] += __shfl_xor_sync(0xffffffffu, nn[k], off);
+      }
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) nn_me[k] = nn[k];
     }
     // per-warp maximum of the open columns' keys; written after the first barrier of the iteration, so no
     // warp's pivot search can race it
-    warp_key_publish(open ? norm_key(nn_me, col) : 0ull);
+    {
+      unsigned long long kmax_key = 0ull;
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) {
+        const unsigned long long kk = open[k] ? norm_key(nn_me[k], col0 + k * NCOL) : 0ull;
+        kmax_key = kk > kmax_key ? kk : kmax_key;
+      }
+      warp_key_publish(kmax_key);
+    }
     __syncthreads();
     K = j + 1;
   }
   if (!more) {
 #pragma unroll
-    for (int idx = 0; idx < RPT; ++idx) {
-      int r = 2 * TPC * (idx >> 1) + 2 * part + (idx & 1);
-      if (col_ok && r < K) s.X[r * LD + col] = x[idx];
+    for (int k = 0; k < CPT; ++k) {
+      const int col = col0 + k * NCOL;
+#pragma unroll
+      for (int idx = 0; idx < RPT; ++idx) {
+        int r = 2 * TPC * (idx >> 1) + 2 * part + (idx & 1);
+        if (col < C && r < K) s.X[r * LD + col] = x[k][idx];
+      }
     }
   }
   if (tid == 0) {

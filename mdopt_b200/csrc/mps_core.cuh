@@ -165,9 +165,10 @@ struct Engine {
     if (!use_svd) {
 #ifndef MDOPT_EMU
       long long t0 = MD_CLOCK();
-      // narrow matrices (every centre move has C <= CHI) spread each column over 8 lanes so all warps work
-      if (C <= CHI) qrcp_reg<CHI, 8>(s, orig, R, C, kmax, st.P.rank_tol);
-      else qrcp_reg<CHI, 4>(s, orig, R, C, kmax, st.P.rank_tol);
+      // 8 lanes per column; a thread group owns one column for C <= CHI (every centre move) and two
+      // (c, c + CHI) for wider matrices
+      if (C <= CHI) qrcp_reg<CHI, 8, 1>(s, orig, R, C, kmax, st.P.rank_tol);
+      else qrcp_reg<CHI, 8, 2>(s, orig, R, C, kmax, st.P.rank_tol);
       MD_LEADER { s.cnt.cyc_qr += (double)(MD_CLOCK() - t0); }
 #else
       load_x(orig, R, C);
