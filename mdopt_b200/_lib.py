@@ -22,11 +22,29 @@ def lib_path() -> str:
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
+def _try_build() -> None:
+    """Build the library in-tree when it is missing and nvcc is available (still no CPU fallback)."""
+    import importlib.util
+    import shutil
+
+    if shutil.which(os.environ.get("NVCC", "nvcc")) is None:
+        return
+    entry = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "__graft_entry__.py")
+    if not os.path.exists(entry):
+        return
+    spec = importlib.util.spec_from_file_location("_mdopt_graft_entry", entry)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build_library()
+
+
 def load() -> C.CDLL:
     """Load and bind the shared library (no GPU needed for this step)."""
     global _lib
     if _lib is None:
         path = lib_path()
+        if not os.path.exists(path):
+            _try_build()
         if not os.path.exists(path):
             raise ImportError(
                 f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
