@@ -85,6 +85,9 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
         mode = "svd"
     errors = list(errors)
     B = len(errors)
+    if B == 0:
+        empty = (np.zeros((0, 1 << k)), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32))
+        return empty if return_status else empty[:2]
     dist = np.zeros((B, 1 << k))
     success = np.zeros(B, dtype=np.int32)
     status = np.zeros(B, dtype=np.int32)

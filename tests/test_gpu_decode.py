@@ -147,3 +147,47 @@ def test_depolarising_bias_and_errors(api, mode):
         np.testing.assert_allclose(dist[b], r["dist"], rtol=0.1 if truncating else 1e-10, atol=1e-13)
         exact += not truncating
     assert exact >= 10
+
+
+def test_edge_batches(api):
+    """Empty batch, all-identity batch, batch of one, mixed literal-character flags in one call, and a batch
+    larger than the resident CTA count (several syndromes per CTA through the work counter)."""
+    code, ocode = api["surface_code"](3), O.surface_code(3)
+    kw = dict(chi_max=32, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, contraction_strategy="Optimised")
+    d, s = api["decode_css_batch"](code, [], **kw)
+    assert d.shape == (0, 4) and s.shape == (0,)
+    d, s = api["decode_css_batch"](code, ["I" * 13] * 5, **kw)
+    assert (d == np.array([1.0, 0, 0, 0])).all() and (s == 1).all()
+    mixed = ["IIXIIIIIIIIII", "IIIIZIIIIIIII", "IIYIIIIIIIIII", "I" * 13, "IXIIIIIIIIIIZ", "YIXIIIIIIIIII"]
+    d, s, st = api["decode_css_batch"](code, mixed, return_status=True, **kw)
+    assert (st == 0).all()
+    for b, e in enumerate(mixed):
+        ref, ok = O.decode_css(ocode, e, **kw)
+        assert int(s[b]) == ok
+        if not O.decode_truncates(ocode, e, **kw) or set(e) == {"I"}:
+            np.testing.assert_allclose(d[b], np.asarray(ref, float), rtol=1e-10, atol=1e-14)
+    one = api["decode_css_batch"](code, mixed[:1], **kw)
+    np.testing.assert_array_equal(one[0][0], d[0])
+    many = O.seeded_errors(13, 0.2, 700, 5, "Bitflip")  # > 148 * occupancy CTAs
+    dm, sm = api["decode_css_batch"](code, many, **kw)
+    again, _ = api["decode_css_batch"](code, many[::-1], **kw)
+    np.testing.assert_array_equal(dm, again[::-1])  # result does not depend on which CTA picks a syndrome up
+    with pytest.raises(ValueError):
+        api["decode_css_batch"](code, ["IIX"], **kw)
+    with pytest.raises(ValueError):
+        api["decode_css_batch"](code, ["IIXIIIIIIIIII"], chi_max=32, bias_type="Bitflip", bias_prob=1.5)
+    from mdopt_b200 import _lib
+
+    with pytest.raises(_lib.MdoptCudaError):
+        api["decode_css_batch"](code, ["IIXIIIIIIIIII"], chi_max=128, bias_type="Bitflip")
+
+
+def test_non_ok_status_paths(api):
+    """A program whose MPO bond does not close is rejected on the host; a capacity overflow inside the kernel
+    yields NaN rows and MDOPT_ST_CAPACITY, never a silent wrong answer."""
+    from mdopt_b200 import schedule
+    from mdopt_b200.optimiser.utils import SWAP, XOR_BULK, XOR_LEFT
+
+    with pytest.raises(ValueError):
+        schedule.append_strings([], schedule.TensorTable(), [[[0], [1], [], [3]]], [XOR_LEFT, XOR_BULK, SWAP, SWAP], 28,
+                                True, [])

@@ -218,3 +218,22 @@ def test_apply_constraints_against_dense_projector(torch_mod):
             assert abs(dense[idx]) < 1e-13
         else:
             assert abs(abs(dense[idx]) - 1 / np.sqrt(2 ** (n - 1))) < 1e-12
+
+
+def test_marginal_tail_on_gpu(torch_mod):
+    """CanonicalMPS.marginal for the decoder's case (contiguous tail) against the oracle
+    (reference canonical.py:906-991; hand case tests/mps/test_canonical.py:851-865 style)."""
+    from mdopt_b200.mps import CanonicalMPS
+
+    rng = np.random.default_rng(21)
+    for ren in (True, False):
+        omps = _random_canonical_mps(rng, 7, 8)
+        ours = CanonicalMPS([t.copy() for t in omps.tensors], 0)
+        ref = O.marginal(omps.copy(), list(range(2, 7)), renormalise=ren)
+        got = ours.marginal(list(range(2, 7)), renormalise=ren)
+        assert got is ours and len(got.tensors) == 2 and got.orth_centre == 1
+        np.testing.assert_allclose(got.dense(), ref.dense(), rtol=1e-12, atol=1e-14)
+    with pytest.raises(NotImplementedError):
+        ours.marginal([0])
+    with pytest.raises(ValueError):
+        ours.marginal([99])
