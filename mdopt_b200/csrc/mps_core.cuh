@@ -113,21 +113,45 @@ struct Engine {
         for (int b = 0; b < TM; ++b) acc[a][b] = 0.0;
       for (int q = 0; q < vl; ++q) {
         for (int pu = 0; pu < 2; ++pu) {
-          double w = w_at(vr, q, wo, pu, pd);
+          const double w = w_at(vr, q, wo, pu, pd);
           if (w == 0.0) continue;
+          // unscaled partial product of this (q, pU) term; the MPO entry multiplies it once at the end
+          double part[TR][TM];
+#pragma unroll
+          for (int a = 0; a < TR; ++a)
+#pragma unroll
+            for (int b = 0; b < TM; ++b) part[a][b] = 0.0;
           const double* mrow = Min + row0 * ld + q * mr;
           const double* arow = As + pu * Bn + m0;
-          for (int m = 0; m < mr; ++m) {
-            double av[TM];
+          if (row0 + TR <= rows && m0 + TM <= Bn) {  // interior tile: no bounds checks in the inner loop
+            for (int m = 0; m < mr; ++m) {
+              double av[TM];
 #pragma unroll
-            for (int b = 0; b < TM; ++b) av[b] = (m0 + b < Bn) ? arow[(size_t)m * 2 * Bn + b] : 0.0;
+              for (int b = 0; b < TM; ++b) av[b] = arow[(size_t)m * 2 * Bn + b];
 #pragma unroll
-            for (int a = 0; a < TR; ++a) {
-              double x = (row0 + a < rows) ? w * mrow[a * ld + m] : 0.0;
+              for (int a = 0; a < TR; ++a) {
+                const double x = mrow[a * ld + m];
 #pragma unroll
-              for (int b = 0; b < TM; ++b) acc[a][b] += x * av[b];
+                for (int b = 0; b < TM; ++b) part[a][b] += x * av[b];
+              }
+            }
+          } else {
+            for (int m = 0; m < mr; ++m) {
+              double av[TM];
+#pragma unroll
+              for (int b = 0; b < TM; ++b) av[b] = (m0 + b < Bn) ? arow[(size_t)m * 2 * Bn + b] : 0.0;
+#pragma unroll
+              for (int a = 0; a < TR; ++a) {
+                const double x = (row0 + a < rows) ? mrow[a * ld + m] : 0.0;
+#pragma unroll
+                for (int b = 0; b < TM; ++b) part[a][b] += x * av[b];
+              }
             }
           }
+#pragma unroll
+          for (int a = 0; a < TR; ++a)
+#pragma unroll
+            for (int b = 0; b < TM; ++b) acc[a][b] += w * part[a][b];
         }
       }
 #pragma unroll
