@@ -237,3 +237,28 @@ def test_marginal_tail_on_gpu(torch_mod):
         ours.marginal([0])
     with pytest.raises(ValueError):
         ours.marginal([99])
+
+
+def test_shor_notebook_known_answer_on_gpu(torch_mod):
+    """examples/decoding/shor.ipynb cells 4-25 through the drop-in API: product state, bias, apply_constraints
+    (GPU) for checks and logicals, marginal (GPU), L1-normalised dense = the notebook's printed vector."""
+    from mdopt_b200.codes import CssCode
+    from mdopt_b200.decoding.decoding import bitflip_bias, css_code_constraint_sites, css_code_logicals_sites
+    from mdopt_b200.contractor import apply_one_site_operator
+    from mdopt_b200.mps.utils import create_custom_product_state
+    from mdopt_b200.optimiser.utils import COPY_LEFT, SWAP, XOR_BULK, XOR_LEFT, XOR_RIGHT, apply_constraints
+
+    code = CssCode(9, [[0, 1, 2, 3, 4, 5], [3, 4, 5, 6, 7, 8]], [[0, 1], [1, 2], [3, 4], [4, 5], [6, 7], [7, 8]],
+                   [[0, 1, 2]], [[0, 3, 6]])
+    mps = create_custom_product_state("++" + "0" * 18)
+    for site in range(2, 20):
+        mps.tensors[site] = apply_one_site_operator(mps.tensors[site], bitflip_bias(0.1))
+    checks, logicals = css_code_constraint_sites(code), css_code_logicals_sites(code)
+    for i in (0, 1):
+        mps = apply_constraints(mps, checks[i], [XOR_LEFT, XOR_BULK, SWAP, XOR_RIGHT], renormalise=True,
+                                strategy="Optimised", silent=True)
+    for i in (0, 1):
+        mps = apply_constraints(mps, logicals[i], [COPY_LEFT, XOR_BULK, SWAP, XOR_RIGHT], renormalise=True,
+                                strategy="Optimised", silent=True)
+    out = mps.marginal(list(range(2, 20))).dense(flatten=True, renormalise=True, norm=1)
+    np.testing.assert_allclose(np.abs(out), [0.61225663, 0.06778069, 0.28807136, 0.03189132], atol=5e-9)

@@ -90,3 +90,28 @@ def test_error_paths():
         O.constraint_mpo([O.XOR_LEFT, O.XOR_RIGHT], [[0], [2]])
     with pytest.raises(ValueError):
         O.svd(np.zeros((2, 2, 2)))
+
+
+SHOR = dict(n=9, x_stabs=[[0, 1, 2, 3, 4, 5], [3, 4, 5, 6, 7, 8]],
+            z_stabs=[[0, 1], [1, 2], [3, 4], [4, 5], [6, 7], [7, 8]], x_logicals=[[0, 1, 2]], z_logicals=[[0, 3, 6]])
+SHOR_KNOWN = [0.61225663, 0.06778069, 0.28807136, 0.03189132]  # examples/decoding/shor.ipynb cell 25 output
+
+
+def test_shor_notebook_known_answer():
+    """The Shor-code walk-through of the reference (examples/decoding/shor.ipynb cells 4-25): |++0...0>,
+    bit-flip bias 0.1, X and Z checks then X and Z logicals ("Optimised"), marginal, L1-normalised dense."""
+    code = O.CssCode(SHOR["n"], SHOR["x_stabs"], SHOR["z_stabs"], SHOR["x_logicals"], SHOR["z_logicals"])
+    checks, logicals = O.code_sites(code)
+    assert checks[0] == [[[2], [4, 6, 8, 10], [3, 5, 7, 9, 11], [12]], [[8], [10, 12, 14, 16], [9, 11, 13, 15, 17], [18]]]
+    assert checks[1][0] == [[3], [], [4], [5]]
+    assert logicals[1] == [[[1], [3, 9], [2, 4, 5, 6, 7, 8, 10, 11, 12, 13, 14], [15]]]
+    mps = O.product_state("++" + "0" * 18)
+    mps = O.apply_bitflip_bias(mps, range(2, 20), 0.1)
+    for i in (0, 1):
+        mps = O.apply_constraints(mps, checks[i], [O.XOR_LEFT, O.XOR_BULK, O.SWAP, O.XOR_RIGHT], renormalise=True,
+                                  strategy="Optimised")
+    for i in (0, 1):
+        mps = O.apply_constraints(mps, logicals[i], [O.COPY_LEFT, O.XOR_BULK, O.SWAP, O.XOR_RIGHT], renormalise=True,
+                                  strategy="Optimised")
+    out = O.marginal(mps, list(range(2, 20))).dense(flatten=True, renormalise=True, norm=1)
+    np.testing.assert_allclose(out, SHOR_KNOWN, atol=5e-9)
