@@ -63,6 +63,11 @@ typedef struct mdopt_decode_desc {
   double cut_move;      /* 1e-12, mdopt/utils/utils.py:293 default used by move_orth_centre */
   double rank_tol;      /* MDOPT_MODE_FAST: relative rank threshold (default 1e-14) */
   double bias_p;        /* bit-flip bias probability, < 0: none */
+  int32_t n_head;       /* read-out: sites 0..n_head-1 form the dense stage (0: use n_logical) */
+  uint32_t kept_mask;   /* read-out: bit j set = site j (< n_head) is kept, clear = traced out; exactly
+                           n_logical bits set, bit n_head-1 set.  0: the first n_logical sites.  Only erasures of
+                           qubits with index < n_logical change it (decoding.py:1341-1347 passes qubit indices to
+                           marginal() as site indices) */
 } mdopt_decode_desc;
 
 int mdopt_b200_abi_version(void);

@@ -9,6 +9,7 @@ class DecodeDesc(C.Structure):
         ("n_sites", C.c_int32), ("n_logical", C.c_int32), ("chi_max", C.c_int32), ("mode", C.c_int32),
         ("renormalise", C.c_int32), ("trace_stride", C.c_int32), ("trace_max", C.c_int32), ("n_ops", C.c_int32),
         ("cut_sweep", C.c_double), ("cut_move", C.c_double), ("rank_tol", C.c_double), ("bias_p", C.c_double),
+        ("n_head", C.c_int32), ("kept_mask", C.c_uint32),
     ]
 
 
@@ -51,10 +52,12 @@ def bind(lib: C.CDLL) -> C.CDLL:
 
 
 def make_desc(n_sites, n_logical, chi_max, mode, renormalise, n_ops, cut_sweep, bias_p, trace_stride=0,
-              trace_max=0, cut_move=CUT_MOVE, rank_tol=DEFAULT_RANK_TOL) -> DecodeDesc:
+              trace_max=0, cut_move=CUT_MOVE, rank_tol=DEFAULT_RANK_TOL, kept_mask=0) -> DecodeDesc:
+    kept_mask = int(kept_mask)
+    n_head = kept_mask.bit_length() if kept_mask else 0
     return DecodeDesc(int(n_sites), int(n_logical), int(chi_max), int(mode), int(bool(renormalise)),
                       int(trace_stride), int(trace_max), int(n_ops), float(cut_sweep), float(cut_move),
-                      float(rank_tol), float(bias_p))
+                      float(rank_tol), float(bias_p), n_head, kept_mask)
 
 
 def chi_capacity(chi: int) -> int:

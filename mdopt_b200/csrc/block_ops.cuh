@@ -70,6 +70,8 @@ struct DecodeParams {
   double cut_move;    // 1e-12 (reference default of split_two_site_tensor inside move_orth_centre)
   double rank_tol;    // MODE_FAST relative rank threshold
   double bias_p;      // bit-flip bias probability; < 0 disables the bias
+  int n_head;         // read-out: number of leading sites in the dense stage (>= n_logical)
+  unsigned kept_mask; // read-out: which of them are kept (the others are traced out)
 };
 
 // Persistent per-CTA engine state (shared memory; see Engine in mps_core.cuh).

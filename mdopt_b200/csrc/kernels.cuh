@@ -229,6 +229,8 @@ int launch_decode(const mdopt_decode_desc* d, int n_ctas, const int32_t* program
   P.renormalise = d->renormalise; P.trace_stride = d->trace_stride; P.trace_max = d->trace_max;
   P.n_ops = d->n_ops; P.cut_sweep = d->cut_sweep; P.cut_move = d->cut_move; P.rank_tol = d->rank_tol;
   P.bias_p = d->bias_p;
+  P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
+  P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
   // the work counter lives in the last 256 bytes of the workspace
   int* work_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + per * (size_t)n_ctas);
   e = cudaMemsetAsync(work_counter, 0, 256, st);
@@ -286,6 +288,8 @@ int launch_mps_program(const mdopt_decode_desc* d, const int32_t* program, const
   P.renormalise = d->renormalise; P.trace_stride = d->trace_stride; P.trace_max = d->trace_max;
   P.n_ops = d->n_ops; P.cut_sweep = d->cut_sweep; P.cut_move = d->cut_move; P.rank_tol = d->rank_tol;
   P.bias_p = d->bias_p;
+  P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
+  P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
   mps_program_kernel<C_><<<batch, Cfg<C_>::NT, sizeof(Smem<C_>), st>>>(
       P, program, wtab, wdim, batch, sites_io, bonds_io, centre_io, dist, success, status,
       d->trace_stride > 0 ? trace : nullptr, reinterpret_cast<double*>(workspace));

@@ -520,7 +520,10 @@ struct Engine {
   // ---- marginal over st.sites kL..N-1, reverse, dense, |.|, L2 renorm, tolerant arg-max ----
   //   canonical.py:956-989, :150-161, :241-272; decoding.py:1362-1379
   MD_DEV void marginal_readout(double* out, int* success) {
-    const int N = st.P.n_sites, kL = st.P.n_logical, ren = st.P.renormalise;
+    // kL = number of leading sites handled by the dense stage; those with their bit in kept_mask set are kept
+    // (n_logical of them), the others are traced out like the tail (erasures of qubits < n_logical only)
+    const int N = st.P.n_sites, kL = st.P.n_head, ren = st.P.renormalise;
+    const unsigned kept = st.P.kept_mask;
     double* T = s.part;        // current last tensor (L x 2), L <= CHI
     double* w = s.wv;          // traced vector
     int L = st.bd[N - 1];
@@ -555,7 +558,7 @@ struct Engine {
     MD_PAR_FOR(t, L * 2) st.sites[(size_t)(kL - 1) * SITE_STRIDE + t] = T[t];
     MD_LEADER { st.bd[kL] = 1; }
     MD_SYNC();
-    // dense over the kL logical st.sites: D_j[(p_j .. p_0), b]
+    // dense stage over the kL leading sites: D_j[(kept physical indices, most recent first), b]
     double* D0 = s.X;
     double* D1 = s.X + (N2 * LD) / 2;
     int nb = 1, nidx = 1;
@@ -566,18 +569,32 @@ struct Engine {
       const int Br = (j == kL - 1) ? 1 : st.bd[j + 1];
       const double* A = st.sites + (size_t)j * SITE_STRIDE;
       const int last = (j == kL - 1);
-      MD_PAR_FOR(t, nidx * 2 * Br) {
-        int b2 = t % Br; int r = t / Br; int idx = r % nidx; int p = r / nidx;
-        double acc = 0.0;
-        for (int b = 0; b < Bl; ++b) {
-          double a = last ? T[b * 2 + p] : A[((size_t)b * 2 + p) * Br + b2];
-          acc += D0[idx * Bl + b] * a;
+      const int keep = (kept >> j) & 1u;
+      if (keep) {
+        MD_PAR_FOR(t, nidx * 2 * Br) {
+          int b2 = t % Br; int r = t / Br; int idx = r % nidx; int p = r / nidx;
+          double acc = 0.0;
+          for (int b = 0; b < Bl; ++b) {
+            double a = last ? T[b * 2 + p] : A[((size_t)b * 2 + p) * Br + b2];
+            acc += D0[idx * Bl + b] * a;
+          }
+          D1[(p * nidx + idx) * Br + b2] = acc;
         }
-        D1[(p * nidx + idx) * Br + b2] = acc;
+      } else {  // traced head site: contract its physical leg with (1, 1)/sqrt(2)
+        MD_PAR_FOR(t, nidx * Br) {
+          int b2 = t % Br; int idx = t / Br;
+          double acc = 0.0;
+          for (int b = 0; b < Bl; ++b) {
+            double a = last ? (T[b * 2] + T[b * 2 + 1]) : (A[((size_t)b * 2) * Br + b2] + A[((size_t)b * 2 + 1) * Br + b2]);
+            acc += D0[idx * Bl + b] * a;
+          }
+          D1[idx * Br + b2] = acc * (1.0 / sqrt(2.0));
+        }
       }
       MD_SYNC();
       double* tmp = D0; D0 = D1; D1 = tmp;
-      nidx *= 2; nb = Br;
+      if (keep) nidx *= 2;
+      nb = Br;
     }
     MD_LEADER {
       double nrm = 0.0, top = 0.0;

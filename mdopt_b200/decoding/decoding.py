@@ -91,7 +91,8 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
     dist = np.zeros((B, 1 << k))
     success = np.zeros(B, dtype=np.int32)
     status = np.zeros(B, dtype=np.int32)
-    groups: Dict[Tuple[bool, bool], List[int]] = {}
+    groups: Dict[Tuple[bool, bool, int], List[int]] = {}
+    default_mask = (1 << k) - 1
     for b, err in enumerate(errors):
         if len(err) != n:
             raise ValueError(f"The error length is {2 * len(err)}, expected {2 * n}.")
@@ -99,16 +100,18 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
         if trivial:
             dist[b, 0], success[b] = 1.0, 1
         else:
-            groups.setdefault((has_x, has_z), []).append(b)
+            mask = schedule.readout_kept_mask(err, k) if "E" in err else default_mask
+            groups.setdefault((has_x, has_z, mask), []).append(b)
     if not groups:
         return (dist, success, status) if return_status else (dist, success)
     chi = int(min(int(chi_max), 1 << 30))
     eng = engine.get_engine(n_sites, k, chi)
-    for (has_x, has_z), idx in groups.items():
+    for (has_x, has_z, mask), idx in groups.items():
         prog = _program_for(code, has_x, has_z, renormalise, contraction_strategy, orders, bias_type, bias_prob)
         syms = schedule.symbols_from_errors([errors[b] for b in idx], k)
         d, s, st = eng.decode_host(prog, syms, cut=cut, bias_p=(-1.0 if depol else bias_prob),
-                                   renormalise=renormalise, mode=mode)
+                                   renormalise=renormalise, mode=mode,
+                                   kept_mask=(0 if mask == default_mask else mask))
         dist[idx], success[idx], status[idx] = d, s, st
         if not silent:
             logging.info("decoded %d syndromes with flags X=%s Z=%s", len(idx), has_x, has_z)

@@ -19,7 +19,8 @@ OP_END, OP_SWEEP, OP_MOVE, OP_MARGINAL, OP_GATE2 = 0, 1, 2, 3, 4
 MODE_FAST, MODE_SVD = 0, 1
 SYM_ZERO, SYM_ONE, SYM_PLUS = 0, 1, 2
 
-_PAULI_BITS = {"I": (0, 0), "X": (1, 0), "Z": (0, 1), "Y": (1, 1)}  # decoding.py:283-320
+# decoding.py:283-320; "E" (erasure) becomes "++"
+_PAULI_BITS = {"I": (0, 0), "X": (1, 0), "Z": (0, 1), "Y": (1, 1), "E": (2, 2)}
 
 
 class TensorTable:
@@ -191,6 +192,25 @@ def error_flags(error: str) -> Tuple[bool, bool, bool]:
     return error == "I" * len(error), "X" in error, "Z" in error
 
 
+def readout_kept_mask(error: str, n_logical: int) -> int:
+    """Which leading sites survive the read-out of this error (bit j = site j is kept).
+
+    Without erasures these are the ``n_logical`` logical sites.  The reference first marginalises the erased
+    *qubit* indices as if they were *site* indices (decoding.py:1341-1347) and then everything from position
+    ``n_logical`` of the shortened chain on (:1348-1356); together that keeps the first ``n_logical`` sites whose
+    index is not the index of an erased qubit."""
+    erased = {q for q, ch in enumerate(error) if ch == "E"}
+    mask, kept, site = 0, 0, 0
+    while kept < n_logical:
+        if site not in erased:
+            mask |= 1 << site
+            kept += 1
+        site += 1
+        if site > 31:
+            raise NotImplementedError("erasure pattern pushes the read-out beyond the first 32 sites")
+    return mask
+
+
 def symbols_from_errors(errors: Sequence[str], n_logical: int) -> np.ndarray:
     """uint8 [B, k + 2n] product-state symbols: '+' on the logical sites, then the Pauli bits."""
     n = len(errors[0])
@@ -206,8 +226,6 @@ def symbols_from_errors(errors: Sequence[str], n_logical: int) -> np.ndarray:
             raise ValueError(f"The error length is {2 * raw.size}, expected {2 * n}.")
         if not valid[raw].all():
             bad = err[int(np.argmin(valid[raw]))]
-            if bad == "E":
-                raise NotImplementedError("erasure ('E') errors are not supported by the GPU engine yet")
             raise ValueError(f"Invalid Pauli encountered -- {bad}.")
         out[b, n_logical:] = lut[raw].reshape(-1)
     return out

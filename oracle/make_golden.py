@@ -49,8 +49,18 @@ def run_batch(name, L, errors, **kw):
     print(name, len(rows), "decodes", doc["reference_seconds"], "s")
 
 
+# erasure errors ('E' -> '++', decoding.py:283-320, 1341-1347), incl. erasures of qubits 0 / 1 whose indices
+# the reference hands to marginal() as site indices
+ERASURE_CASES = ["IIEIIIIIIIIII", "IIXIIEIIIIIII", "EIXIIIIIIIIII", "IEIIZIIIIIIII", "EEIIIIIIIIIII", "IIEIIIIIIIIIE",
+                 "XIIEIIIYIIIEI", "IIIIIIXEIIIII", "ZEIIIIIIIIIIE", "IIXIIEIIEIIIZ"]
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "erasure":
+        run_batch("erasure_3x3", 3, ERASURE_CASES, chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1,
+                  tolerance=1e-12)
+        return
     # config 1: README minimal example (README.md:38-61)
     run_batch("readme_3x3", 3, ["IIXIIIIIIIIII"], chi_max=64, bias_type="Bitflip", bias_prob=0.01,
               tolerance=1e-12)
@@ -71,6 +81,8 @@ def main():
               chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, tolerance=1e-12)
     run_batch("d5_chi16_bitflip", 5, O.seeded_errors(n5, 0.05, 12, 5, "Bitflip"),
               chi_max=16, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, tolerance=1e-12)
+    run_batch("erasure_3x3", 3, ERASURE_CASES, chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1,
+              tolerance=1e-12)
 
     # exact MPO tensor tables (reference values: mdopt/optimiser/utils.py:23-43)
     tables = {k: getattr(ref_opt, k).tolist() for k in

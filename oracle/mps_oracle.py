@@ -519,9 +519,12 @@ def decode_css(code, error, chi_max=int(1e4), cut=1e-17, bias_type="Depolarising
         mps = apply_constraints(mps, checks[0], check_t, order=orders.get("xc"), **kw)
     if has_z:
         mps = apply_constraints(mps, checks[1], check_t, order=orders.get("zc"), **kw)
-    if "E" in error:
-        raise NotImplementedError("oracle does not restate the erasure branch")
-    mps = marginal(mps, list(range(k, n_sites)), renormalise=renormalise).reverse()
+    erased = [q for q, ch in enumerate(error) if ch == "E"]
+    if erased:
+        # decoding.py:1341-1347: the QUBIT indices are handed to marginal() as SITE indices (kept as is)
+        mps = marginal(mps, erased, renormalise=renormalise)
+    # decoding.py:1351-1356 (there `error` is already the 2n-character site string)
+    mps = marginal(mps, list(range(k, len(bits) + k - len(erased))), renormalise=renormalise).reverse()
     if len(mps) > 12:
         raise NotImplementedError("Dephasing-DMRG read-out (> 12 logical sites) is out of scope")
     return readout(mps.dense(flatten=True, renormalise=renormalise, norm=2))

@@ -33,6 +33,8 @@ int decode_impl(const mdopt_decode_desc* d, const int32_t* program, const double
   P.renormalise = d->renormalise; P.trace_stride = d->trace_stride; P.trace_max = d->trace_max;
   P.n_ops = d->n_ops; P.cut_sweep = d->cut_sweep; P.cut_move = d->cut_move; P.rank_tol = d->rank_tol;
   P.bias_p = d->bias_p;
+  P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
+  P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
   E.st.P = P;
   sm->cnt = Counters{};
   const int ncls = 1 << d->n_logical;
@@ -109,6 +111,8 @@ int program_impl(const mdopt_decode_desc* d, const int32_t* program, const doubl
   P.renormalise = d->renormalise; P.trace_stride = d->trace_stride; P.trace_max = d->trace_max;
   P.n_ops = d->n_ops; P.cut_sweep = d->cut_sweep; P.cut_move = d->cut_move; P.rank_tol = d->rank_tol;
   P.bias_p = d->bias_p;
+  P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
+  P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
   E.st.P = P;
   sm->cnt = Counters{};
   E.st.centre = *centre_io; E.st.mirrored = 0; E.st.status = ST_OK; E.st.n_traced = 0;

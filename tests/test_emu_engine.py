@@ -21,8 +21,10 @@ def emu_decode(code, errors, chi, cut, bias, mode, strategy="Optimised", renorma
             continue
         prog = schedule.build_decode_program(code, hx, hz, renormalise, strategy, None, bias_type, bias)
         sym = schedule.symbols_from_errors([e], prog.n_logical)
+        mask = schedule.readout_kept_mask(e, prog.n_logical)
         dist, succ, st, tr, cnt = H.decode(prog, sym, chi, cut, bias if bias_type == "Bitflip" else -1.0,
-                                           renormalise, mode, trace_max=trace_max)
+                                           renormalise, mode, trace_max=trace_max,
+                                           kept_mask=0 if mask == (1 << prog.n_logical) - 1 else mask)
         out.append((dist[0], int(succ[0]), int(st[0]), tr[0], cnt))
     return out
 
@@ -155,3 +157,15 @@ def test_depolarising_bias_matches_reference(mode):
     for r, (dist, ok, st, _, _) in zip(rows, res):
         assert st == 0 and ok == r["success"], r["error"]
         np.testing.assert_allclose(dist, r["dist"], rtol=1e-10, atol=1e-14)
+
+
+def test_erasure_errors_match_reference():
+    """'E' -> '++' and the reference's erased-qubit marginal (decoding.py:1341-1347), incl. erasures of qubits 0/1."""
+    g = load_golden("erasure_3x3")
+    kw = g["kwargs"]
+    res = emu_decode(surface_code(3), [r["error"] for r in g["results"]], kw["chi_max"], kw["cut"], kw["bias_prob"],
+                     schedule.MODE_FAST)
+    for r, (dist, ok, st, _, _) in zip(g["results"], res):
+        assert st == 0 and ok == r["success"], r["error"]
+        both = "X" in r["error"] and "Z" in r["error"]
+        np.testing.assert_allclose(dist, r["dist"], rtol=5e-2 if both else 1e-10, atol=1e-13)

@@ -191,3 +191,20 @@ def test_non_ok_status_paths(api):
     with pytest.raises(ValueError):
         schedule.append_strings([], schedule.TensorTable(), [[[0], [1], [], [3]]], [XOR_LEFT, XOR_BULK, SWAP, SWAP], 28,
                                 True, [])
+
+
+def test_erasure_errors(api):
+    """Erasure errors against the reference fixtures: 'E' -> '++' product sites, and the read-out keeps the first
+    two sites whose index is not an erased *qubit* index (decoding.py:1341-1356)."""
+    g = load_golden("erasure_3x3")
+    errors = [r["error"] for r in g["results"]]
+    for mode in ("fast", "svd"):
+        dist, success, status = api["decode_css_batch"](api["surface_code"](3), errors,
+                                                        contraction_strategy="Optimised", mode=mode,
+                                                        return_status=True, **g["kwargs"])
+        assert (status == 0).all()
+        ocode = O.surface_code(3)
+        for b, r in enumerate(g["results"]):
+            assert int(success[b]) == r["success"], r["error"]
+            truncating = O.decode_truncates(ocode, r["error"], contraction_strategy="Optimised", **g["kwargs"])
+            np.testing.assert_allclose(dist[b], r["dist"], rtol=0.15 if truncating else 1e-10, atol=1e-13)

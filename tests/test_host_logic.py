@@ -69,6 +69,11 @@ def test_program_layout():
 def test_symbols_and_flags():
     syms = schedule.symbols_from_errors(["IXZY"], 2)
     assert syms.tolist() == [[2, 2, 0, 0, 1, 0, 0, 1, 1, 1]]
+    assert schedule.symbols_from_errors(["EX"], 1).tolist() == [[2, 2, 2, 1, 0]]
+    assert schedule.readout_kept_mask("IIXE", 2) == 0b11
+    assert schedule.readout_kept_mask("EIXI", 2) == 0b110
+    assert schedule.readout_kept_mask("EEXI", 2) == 0b1100
+    assert schedule.readout_kept_mask("IEIE", 2) == 0b101
     assert schedule.error_flags("IIII") == (True, False, False)
     assert schedule.error_flags("IYII") == (False, False, False)
     assert schedule.error_flags("XYZI") == (False, True, True)

@@ -10,12 +10,12 @@ from conftest import load_golden
 
 
 @pytest.mark.parametrize("name", ["readme_3x3", "gating_3x3", "d3_chi64_bitflip", "d3_chi64_bitflip_cut0",
-                                  "d3_chi64_depol", "d3_chi8_bitflip", "d5_chi16_bitflip"])
+                                  "d3_chi64_depol", "d3_chi8_bitflip", "d5_chi16_bitflip", "erasure_3x3"])
 def test_oracle_matches_reference_outputs(name):
     g = load_golden(name)
     kw = dict(g["kwargs"])
     code = O.surface_code(g["lattice_size"])
-    truncating = name in ("d3_chi8_bitflip", "d5_chi16_bitflip", "gating_3x3")
+    truncating = name in ("d3_chi8_bitflip", "d5_chi16_bitflip", "gating_3x3", "erasure_3x3")
     for row in g["results"]:
         dist, ok = O.decode_css(code, row["error"], contraction_strategy="Optimised", **kw)
         assert int(ok) == row["success"], row["error"]
