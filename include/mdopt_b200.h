@@ -68,6 +68,8 @@ typedef struct mdopt_decode_desc {
                            n_logical bits set, bit n_head-1 set.  0: the first n_logical sites.  Only erasures of
                            qubits with index < n_logical change it (decoding.py:1341-1347 passes qubit indices to
                            marginal() as site indices) */
+  double readout_rel;   /* success = v[0] >= max(v) - max(readout_rel * max(v), readout_abs) */
+  double readout_abs;   /* decode_css: 1e-9 / 1e-12 (decoding.py:1367-1376); decode_custom: 1e-12 / 0 (:1600-1604) */
 } mdopt_decode_desc;
 
 int mdopt_b200_abi_version(void);

@@ -10,6 +10,7 @@ class DecodeDesc(C.Structure):
         ("renormalise", C.c_int32), ("trace_stride", C.c_int32), ("trace_max", C.c_int32), ("n_ops", C.c_int32),
         ("cut_sweep", C.c_double), ("cut_move", C.c_double), ("rank_tol", C.c_double), ("bias_p", C.c_double),
         ("n_head", C.c_int32), ("kept_mask", C.c_uint32),
+        ("readout_rel", C.c_double), ("readout_abs", C.c_double),
     ]
 
 
@@ -52,12 +53,13 @@ def bind(lib: C.CDLL) -> C.CDLL:
 
 
 def make_desc(n_sites, n_logical, chi_max, mode, renormalise, n_ops, cut_sweep, bias_p, trace_stride=0,
-              trace_max=0, cut_move=CUT_MOVE, rank_tol=DEFAULT_RANK_TOL, kept_mask=0) -> DecodeDesc:
+              trace_max=0, cut_move=CUT_MOVE, rank_tol=DEFAULT_RANK_TOL, kept_mask=0, readout_rel=1e-9,
+              readout_abs=1e-12) -> DecodeDesc:
     kept_mask = int(kept_mask)
     n_head = kept_mask.bit_length() if kept_mask else 0
     return DecodeDesc(int(n_sites), int(n_logical), int(chi_max), int(mode), int(bool(renormalise)),
                       int(trace_stride), int(trace_max), int(n_ops), float(cut_sweep), float(cut_move),
-                      float(rank_tol), float(bias_p), n_head, kept_mask)
+                      float(rank_tol), float(bias_p), n_head, kept_mask, float(readout_rel), float(readout_abs))
 
 
 def chi_capacity(chi: int) -> int:

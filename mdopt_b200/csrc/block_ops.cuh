@@ -72,6 +72,8 @@ struct DecodeParams {
   double bias_p;      // bit-flip bias probability; < 0 disables the bias
   int n_head;         // read-out: number of leading sites in the dense stage (>= n_logical)
   unsigned kept_mask; // read-out: which of them are kept (the others are traced out)
+  double readout_rel; // tolerant arg-max: eps = max(readout_rel * max v, readout_abs)
+  double readout_abs;
 };
 
 // Persistent per-CTA engine state (shared memory; see Engine in mps_core.cuh).

@@ -231,6 +231,7 @@ int launch_decode(const mdopt_decode_desc* d, int n_ctas, const int32_t* program
   P.bias_p = d->bias_p;
   P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
   P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
+  P.readout_rel = d->readout_rel; P.readout_abs = d->readout_abs;
   // the work counter lives in the last 256 bytes of the workspace
   int* work_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + per * (size_t)n_ctas);
   e = cudaMemsetAsync(work_counter, 0, 256, st);
@@ -290,6 +291,7 @@ int launch_mps_program(const mdopt_decode_desc* d, const int32_t* program, const
   P.bias_p = d->bias_p;
   P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
   P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
+  P.readout_rel = d->readout_rel; P.readout_abs = d->readout_abs;
   mps_program_kernel<C_><<<batch, Cfg<C_>::NT, sizeof(Smem<C_>), st>>>(
       P, program, wtab, wdim, batch, sites_io, bonds_io, centre_io, dist, success, status,
       d->trace_stride > 0 ? trace : nullptr, reinterpret_cast<double*>(workspace));

@@ -610,7 +610,7 @@ struct Engine {
       }
       if (nan_seen) { *success = 0; if (st.status == ST_OK) st.status = ST_ZERO_NORM; }
       else {
-        double eps = fmax(1e-9 * top, 1e-12);
+        double eps = fmax(st.P.readout_rel * top, st.P.readout_abs);
         *success = (out[0] >= top - eps) ? 1 : 0;
       }
     }

@@ -44,6 +44,12 @@ def css_code_logicals_sites(code):
     return schedule.code_site_lists(code)[1]
 
 
+def _effective_chi(chi_max, n_sites: int) -> int:
+    """chi_max clipped to the largest Schmidt rank an n_sites-qubit chain can have (2^floor(N/2)): a larger
+    chi_max never truncates, so short chains may keep the reference's default chi_max=1e4."""
+    return int(min(int(chi_max), 1 << min(n_sites // 2, 30)))
+
+
 def _code_key(code) -> Tuple:
     """Structural identity of a code object (object ids are recycled once a code is garbage collected)."""
     mats = (code.x_stabs_binary(), code.z_stabs_binary(), code.x_logicals_binary(), code.z_logicals_binary())
@@ -104,8 +110,7 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
             groups.setdefault((has_x, has_z, mask), []).append(b)
     if not groups:
         return (dist, success, status) if return_status else (dist, success)
-    chi = int(min(int(chi_max), 1 << 30))
-    eng = engine.get_engine(n_sites, k, chi)
+    eng = engine.get_engine(n_sites, k, _effective_chi(chi_max, n_sites))
     for (has_x, has_z, mask), idx in groups.items():
         prog = _program_for(code, has_x, has_z, renormalise, contraction_strategy, orders, bias_type, bias_prob)
         syms = schedule.symbols_from_errors([errors[b] for b in idx], k)
@@ -147,4 +152,83 @@ def decode_css(code, error: str, num_runs: int = int(1), chi_max: int = int(1e4)
                                      bias_prob=bias_prob, renormalise=renormalise, silent=True,
                                      contraction_strategy=contraction_strategy, tolerance=tolerance, orders=orders,
                                      mode=mode)
+    return dist[0], int(success[0])
+
+
+def decode_custom_batch(stabilizers: Sequence[str], x_logicals: Sequence[str], z_logicals: Sequence[str],
+                        errors: Sequence[str], chi_max: int = int(1e4), cut: float = float(1e-17),
+                        bias_type: str = "Depolarising", bias_prob: float = float(0.1), renormalise: bool = True,
+                        silent: bool = True, contraction_strategy: str = "Naive", tolerance: float = float(1e-12),
+                        orders: Optional[dict] = None, mode: str = "fast", return_status: bool = False):
+    """Batched ``decode_custom`` (reference decoding.py:1407-1628): a code given by stabiliser / logical Pauli
+    strings; every constraint group is always applied, success uses the relative tolerance 1e-12 (:1600-1604)."""
+    from mdopt_b200 import engine
+
+    depol = bias_type != "Bitflip"
+    if not 0 <= bias_prob <= 1:
+        raise ValueError(f"The channel parameter should be a probability, given {bias_prob} at site 0.")
+    k = len(x_logicals) + len(z_logicals)
+    n = len(stabilizers[0])
+    n_sites = 2 * n + k
+    if not 1 <= k <= 6:
+        raise NotImplementedError("the dense read-out supports 1..6 logical sites")
+    if mode == "fast" and cut > 1e-14:
+        mode = "svd"
+    errors = list(errors)
+    B = len(errors)
+    dist = np.zeros((B, 1 << k))
+    success = np.zeros(B, dtype=np.int32)
+    status = np.zeros(B, dtype=np.int32)
+    default_mask = (1 << k) - 1
+    groups: Dict[int, List[int]] = {}
+    for b, err in enumerate(errors):
+        if len(err) != n:
+            raise ValueError(f"The error length is {2 * len(err)}, expected {2 * n}.")
+        if err == "I" * n:
+            dist[b, 0], success[b] = 1.0, 1   # early exit returns [1, 0, 0, 0] (decoding.py:1472-1475)
+        else:
+            groups.setdefault(schedule.readout_kept_mask(err, k) if "E" in err else default_mask, []).append(b)
+    if groups:
+        key = ("custom", tuple(stabilizers), tuple(x_logicals), tuple(z_logicals), bool(renormalise),
+               contraction_strategy, None if not orders else tuple(sorted((kk, tuple(v)) for kk, v in orders.items())),
+               depol, float(bias_prob) if depol else None)
+        if key not in _PROGRAM_CACHE:
+            _PROGRAM_CACHE[key] = schedule.build_custom_program(
+                stabilizers, x_logicals, z_logicals, renormalise, contraction_strategy, orders,
+                "Depolarising" if depol else "Bitflip", bias_prob)
+        prog = _PROGRAM_CACHE[key]
+        eng = engine.get_engine(n_sites, k, _effective_chi(chi_max, n_sites))
+        for mask, idx in groups.items():
+            syms = schedule.symbols_from_errors([errors[b] for b in idx], k)
+            d, s, st = eng.decode_host(prog, syms, cut=cut, bias_p=(-1.0 if depol else bias_prob),
+                                       renormalise=renormalise, mode=mode,
+                                       kept_mask=(0 if mask == default_mask else mask), readout=(1e-12, 0.0))
+            dist[idx], success[idx], status[idx] = d, s, st
+    return (dist, success, status) if return_status else (dist, success)
+
+
+def decode_custom(stabilizers: List[str], x_logicals: List[str], z_logicals: List[str], error: str,
+                  num_runs: int = int(1), chi_max: int = int(1e4), cut: float = float(1e-17),
+                  bias_type: str = "Depolarising", bias_prob: float = float(0.1), renormalise: bool = True,
+                  multiply_by_stabiliser: bool = False, silent: bool = False, contraction_strategy: str = "Naive",
+                  optimiser: str = "Dephasing DMRG", tolerance: float = float(1e-12), orders: Optional[dict] = None,
+                  mode: str = "fast"):
+    """Error-based decoding of a code given by Pauli strings (reference decoding.py:1407-1628)."""
+    if not silent:
+        logging.info("Starting the decoding.")
+    if error == "I" * len(error):
+        if not silent:
+            logging.info("No error detected.")
+        return [1.0, 0.0, 0.0, 0.0], 1
+    if multiply_by_stabiliser:
+        raise NotImplementedError("multiply_by_stabiliser draws from the unseeded global RNG; not provided")
+    num_logicals = len(x_logicals) + len(z_logicals)
+    num_sites = len(stabilizers[0]) * 2 + num_logicals
+    if 2 * len(error) != num_sites - num_logicals:
+        raise ValueError(f"The error length is {2 * len(error)}, expected {num_sites - num_logicals}.")
+    pauli_to_mps(error)
+    dist, success = decode_custom_batch(stabilizers, x_logicals, z_logicals, [error], chi_max=chi_max, cut=cut,
+                                        bias_type=bias_type, bias_prob=bias_prob, renormalise=renormalise,
+                                        contraction_strategy=contraction_strategy, tolerance=tolerance,
+                                        orders=orders, mode=mode)
     return dist[0], int(success[0])

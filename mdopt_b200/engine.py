@@ -91,10 +91,10 @@ class DecodeEngine:
         return self._programs[key]
 
     def _desc(self, program: schedule.Program, cut, bias_p, renormalise, mode, trace_stride=0, trace_max=0,
-              rank_tol=_abi.DEFAULT_RANK_TOL, kept_mask=0):
+              rank_tol=_abi.DEFAULT_RANK_TOL, kept_mask=0, readout=(1e-9, 1e-12)):
         return _abi.make_desc(self.n_sites, self.n_logical, self.chi_max, mode_id(mode), renormalise,
                               program.ops.size, cut, bias_p, trace_stride, trace_max, rank_tol=rank_tol,
-                              kept_mask=kept_mask)
+                              kept_mask=kept_mask, readout_rel=readout[0], readout_abs=readout[1])
 
     # ---- inputs already resident in HBM -----------------------------------------------------------
     def decode_device(self, program, d_symbols, cut=1e-17, bias_p=0.1, renormalise=True, mode="fast",
@@ -123,7 +123,7 @@ class DecodeEngine:
 
     # ---- host buffers in, host buffers out (the drop-in call) --------------------------------------
     def decode_host(self, program, symbols: np.ndarray, cut=1e-17, bias_p=0.1, renormalise=True, mode="fast",
-                    rank_tol=_abi.DEFAULT_RANK_TOL, kept_mask=0):
+                    rank_tol=_abi.DEFAULT_RANK_TOL, kept_mask=0, readout=(1e-9, 1e-12)):
         """H2D copy of the symbols, fused decode kernel, D2H of (dist, success, status); synchronous."""
         torch = self.torch
         dp = self.upload(program)
@@ -131,7 +131,8 @@ class DecodeEngine:
         if batch > self.max_batch:
             self._alloc(batch)
         self.h_sym[:batch].numpy()[...] = symbols
-        desc = self._desc(program, cut, bias_p, renormalise, mode, rank_tol=rank_tol, kept_mask=kept_mask)
+        desc = self._desc(program, cut, bias_p, renormalise, mode, rank_tol=rank_tol, kept_mask=kept_mask,
+                          readout=readout)
         with torch.cuda.device(self.device):
             rc = self.lib.mdopt_decode_batch_host(
                 C.byref(desc), self.cap, self.n_ctas, _vp(dp.ops), _vp(dp.wtab), _vp(dp.wdim), dp.wtab.shape[0],

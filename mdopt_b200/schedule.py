@@ -108,6 +108,63 @@ def code_site_lists(code):
     return checks, logicals
 
 
+def _pauli_support(pauli: str, offset: int) -> List[int]:
+    """Sites (2q + offset for the X part, 2q + offset + 1 for the Z part) of a Pauli string (decoding.py:755-781)."""
+    out = []
+    for q, ch in enumerate(pauli):
+        if ch not in _PAULI_BITS or ch == "E":
+            raise ValueError(f"Invalid Pauli encountered -- {ch}.")
+        x, z = _PAULI_BITS[ch]
+        if x:
+            out.append(2 * q + offset)
+        if z:
+            out.append(2 * q + offset + 1)
+    return out
+
+
+def custom_site_lists(stabilizers: Sequence[str], x_logicals: Sequence[str], z_logicals: Sequence[str]):
+    """Constraint-site groups of a code given by Pauli strings (reference decoding.py:755-916): returns
+    ``(checks, (x_logical_groups, z_logical_groups))`` in the same ``[[first], [bulk], [swap], [last]]`` form."""
+    k = len(x_logicals) + len(z_logicals)
+
+    def check_groups(sup):
+        inner = sup[1:-1]
+        return [[sup[0]], inner, [s for s in range(sup[0] + 1, sup[-1]) if s not in inner], [sup[-1]]]
+
+    def logical_groups(index, sup):
+        bulk = sup[:-1]
+        return [[index], bulk, [s for s in range(index + 1, sup[-1]) if s not in bulk], [sup[-1]]]
+
+    checks = [check_groups(_pauli_support(st, k)) for st in stabilizers]
+    xl = [logical_groups(i, _pauli_support(lg, k)) for i, lg in enumerate(x_logicals)]
+    zl = [logical_groups(len(x_logicals) + i, _pauli_support(lg, k)) for i, lg in enumerate(z_logicals)]
+    return checks, (xl, zl)
+
+
+def build_custom_program(stabilizers: Sequence[str], x_logicals: Sequence[str], z_logicals: Sequence[str],
+                         renormalise: bool = True, strategy: str = "Naive", orders: Optional[dict] = None,
+                         bias_type: str = "Bitflip", bias_prob: float = 0.1) -> Program:
+    """Program for ``decode_custom`` (decoding.py:1407-1628): X logicals, Z logicals, then all checks in one
+    group -- no gating by the error's characters."""
+    k = len(x_logicals) + len(z_logicals)
+    n_sites = 2 * len(stabilizers[0]) + k
+    checks, (xl, zl) = custom_site_lists(stabilizers, x_logicals, z_logicals)
+    orders = orders or {}
+    table, ops, spans = TensorTable(), [], []
+    if bias_type != "Bitflip":
+        gid = table.add_gate(depolarising_bias(bias_prob))
+        for site in range(k, n_sites - 1):
+            ops.extend([OP_GATE2, site, gid, int(bool(renormalise))])
+    logical_t = [COPY_LEFT, XOR_BULK, SWAP, XOR_RIGHT]
+    check_t = [XOR_LEFT, XOR_BULK, SWAP, XOR_RIGHT]
+    for strings, tensors, key in ((xl, logical_t, "xl"), (zl, logical_t, "zl"), (checks, check_t, "c")):
+        ordered = order_strings(strings, n_sites, strategy, orders.get(key))
+        append_strings(ops, table, ordered, tensors, n_sites, renormalise, spans)
+    ops.extend([OP_MARGINAL, OP_END])
+    wtab, wdim = table.arrays()
+    return Program(np.array(ops, dtype=np.int32), wtab, wdim, n_sites, k, len(spans), spans)
+
+
 def order_strings(strings, n_sites: int, strategy: str, order: Optional[Sequence[int]] = None):
     """"Optimised" reorders the strings (optimiser/utils.py:270-279); "Naive" keeps them."""
     if strategy != "Optimised":

@@ -55,8 +55,36 @@ ERASURE_CASES = ["IIEIIIIIIIIII", "IIXIIEIIIIIII", "EIXIIIIIIIIII", "IEIIZIIIIII
                  "XIIEIIIYIIIEI", "IIIIIIXEIIIII", "ZEIIIIIIIIIIE", "IIXIIEIIEIIIZ"]
 
 
+FIVE_QUBIT = dict(stabilizers=["XZZXI", "IXZZX", "XIXZZ", "ZXIXZ"], x_logicals=["XXXXX"], z_logicals=["ZZZZZ"])
+
+
+def run_custom(name, errors, **kw):
+    """decode_custom on the five-qubit code (examples/decoding/quantum_five_qubit.ipynb)."""
+    from examples.decoding.decoding import decode_custom
+
+    rows = []
+    for e in errors:
+        dist, ok = decode_custom(FIVE_QUBIT["stabilizers"], FIVE_QUBIT["x_logicals"], FIVE_QUBIT["z_logicals"], e,
+                                 silent=True, **kw)
+        rows.append({"error": e, "dist": [float(x) for x in dist], "success": int(ok)})
+    with open(os.path.join(OUT, name + ".json"), "w") as fh:
+        json.dump({"name": name, "code": FIVE_QUBIT, "kwargs": kw, "results": rows}, fh, indent=0)
+    print(name, len(rows), "decodes")
+
+
+def five_qubit_errors():
+    singles = ["I" * q + p + "I" * (4 - q) for q in range(5) for p in "XYZ"]
+    return singles + ["XXIII", "IZIZI", "YIIIX", "IIXZI", "ZZZII", "XIYIZ", "IIIII", "EIIIX"]
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "custom":
+        run_custom("five_qubit_bitflip", five_qubit_errors(), chi_max=int(1e4), cut=1e-17, bias_type="Bitflip",
+                   bias_prob=0.01, contraction_strategy="Optimised")
+        run_custom("five_qubit_depol", five_qubit_errors(), chi_max=int(1e4), cut=1e-17, bias_type="Depolarising",
+                   bias_prob=0.1, contraction_strategy="Naive")
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "erasure":
         run_batch("erasure_3x3", 3, ERASURE_CASES, chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1,
                   tolerance=1e-12)
@@ -83,6 +111,11 @@ def main():
               chi_max=16, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, tolerance=1e-12)
     run_batch("erasure_3x3", 3, ERASURE_CASES, chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1,
               tolerance=1e-12)
+
+    run_custom("five_qubit_bitflip", five_qubit_errors(), chi_max=int(1e4), cut=1e-17, bias_type="Bitflip",
+               bias_prob=0.01, contraction_strategy="Optimised")
+    run_custom("five_qubit_depol", five_qubit_errors(), chi_max=int(1e4), cut=1e-17, bias_type="Depolarising",
+               bias_prob=0.1, contraction_strategy="Naive")
 
     # exact MPO tensor tables (reference values: mdopt/optimiser/utils.py:23-43)
     tables = {k: getattr(ref_opt, k).tolist() for k in

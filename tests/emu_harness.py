@@ -42,13 +42,14 @@ def _ptr(a):
 
 
 def decode(program: schedule.Program, symbols, chi_max, cut, bias_p, renormalise=True, mode=schedule.MODE_FAST,
-           trace_max=0, rank_tol=_abi.DEFAULT_RANK_TOL, kept_mask=0):
+           trace_max=0, rank_tol=_abi.DEFAULT_RANK_TOL, kept_mask=0, readout=(1e-9, 1e-12)):
     cap = _abi.chi_capacity(max(chi_max, 1))
     B = symbols.shape[0]
     ncls = 1 << program.n_logical
     stride = (4 + 2 * cap) if trace_max else 0
     desc = _abi.make_desc(program.n_sites, program.n_logical, chi_max, mode, renormalise, program.ops.size, cut,
-                          bias_p, stride, trace_max, rank_tol=rank_tol, kept_mask=kept_mask)
+                          bias_p, stride, trace_max, rank_tol=rank_tol, kept_mask=kept_mask,
+                          readout_rel=readout[0], readout_abs=readout[1])
     dist = np.zeros((B, ncls))
     success = np.zeros(B, dtype=np.int32)
     status = np.zeros(B, dtype=np.int32)

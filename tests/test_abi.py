@@ -31,4 +31,4 @@ def test_pure_host_queries():
 
 
 def test_desc_layout_matches_header():
-    assert ctypes.sizeof(_abi.DecodeDesc) == 8 * 4 + 4 * 8 + 2 * 4
+    assert ctypes.sizeof(_abi.DecodeDesc) == 8 * 4 + 4 * 8 + 2 * 4 + 2 * 8

@@ -169,3 +169,24 @@ def test_erasure_errors_match_reference():
         assert st == 0 and ok == r["success"], r["error"]
         both = "X" in r["error"] and "Z" in r["error"]
         np.testing.assert_allclose(dist, r["dist"], rtol=5e-2 if both else 1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["five_qubit_bitflip", "five_qubit_depol"])
+def test_decode_custom_program(name):
+    """decode_custom's program (X logicals, Z logicals, all checks, relative success tolerance 1e-12)."""
+    g = load_golden(name)
+    c, kw = g["code"], g["kwargs"]
+    depol = kw["bias_type"] != "Bitflip"
+    prog = schedule.build_custom_program(c["stabilizers"], c["x_logicals"], c["z_logicals"], True,
+                                         kw["contraction_strategy"], None, kw["bias_type"], kw["bias_prob"])
+    assert prog.n_sites == 12 and prog.n_logical == 2 and prog.n_strings == 6
+    for r in g["results"]:
+        e = r["error"]
+        if e == "I" * 5:
+            continue
+        sym = schedule.symbols_from_errors([e], 2)
+        mask = schedule.readout_kept_mask(e, 2)
+        dist, succ, st, _, _ = H.decode(prog, sym, 64, kw["cut"], -1.0 if depol else kw["bias_prob"], True,
+                                        schedule.MODE_FAST, kept_mask=0 if mask == 3 else mask, readout=(1e-12, 0.0))
+        assert st[0] == 0 and int(succ[0]) == r["success"], e
+        np.testing.assert_allclose(dist[0], r["dist"], rtol=1e-10, atol=1e-14)

@@ -208,3 +208,26 @@ def test_erasure_errors(api):
             assert int(success[b]) == r["success"], r["error"]
             truncating = O.decode_truncates(ocode, r["error"], contraction_strategy="Optimised", **g["kwargs"])
             np.testing.assert_allclose(dist[b], r["dist"], rtol=0.15 if truncating else 1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["five_qubit_bitflip", "five_qubit_depol"])
+def test_decode_custom_five_qubit_code(api, name):
+    """decode_custom / decode_custom_batch against the reference's outputs for the five-qubit code
+    (non-CSS stabilisers XZZXI..., default chi_max=1e4, both bias types, incl. an erasure and the early exit)."""
+    from mdopt_b200.decoding import decode_custom, decode_custom_batch
+
+    g = load_golden(name)
+    c = g["code"]
+    errors = [r["error"] for r in g["results"]]
+    for mode in ("fast", "svd"):
+        dist, success, status = decode_custom_batch(c["stabilizers"], c["x_logicals"], c["z_logicals"], errors,
+                                                    mode=mode, return_status=True, **g["kwargs"])
+        assert (status == 0).all()
+        for b, r in enumerate(g["results"]):
+            assert int(success[b]) == r["success"], r["error"]
+            np.testing.assert_allclose(dist[b], r["dist"], rtol=1e-10, atol=1e-14)
+    one = decode_custom(c["stabilizers"], c["x_logicals"], c["z_logicals"], errors[0], silent=True, **g["kwargs"])
+    np.testing.assert_allclose(one[0], g["results"][0]["dist"], rtol=1e-10)
+    assert decode_custom(c["stabilizers"], c["x_logicals"], c["z_logicals"], "IIIII", silent=True) == ([1.0, 0.0, 0.0, 0.0], 1)
+    with pytest.raises(ValueError):
+        decode_custom(c["stabilizers"], c["x_logicals"], c["z_logicals"], "XX", silent=True)

@@ -115,3 +115,14 @@ def test_shor_notebook_known_answer():
                                   strategy="Optimised")
     out = O.marginal(mps, list(range(2, 20))).dense(flatten=True, renormalise=True, norm=1)
     np.testing.assert_allclose(out, SHOR_KNOWN, atol=5e-9)
+
+
+@pytest.mark.parametrize("name", ["five_qubit_bitflip", "five_qubit_depol"])
+def test_decode_custom_five_qubit_code(name):
+    """decode_custom (decoding.py:1407-1628) on the five-qubit code of examples/decoding/quantum_five_qubit.ipynb."""
+    g = load_golden(name)
+    c = g["code"]
+    for row in g["results"]:
+        dist, ok = O.decode_custom(c["stabilizers"], c["x_logicals"], c["z_logicals"], row["error"], **g["kwargs"])
+        assert int(ok) == row["success"], row["error"]
+        np.testing.assert_allclose(np.asarray(dist, dtype=float), row["dist"], rtol=1e-11, atol=1e-14)
