@@ -62,8 +62,12 @@ def make_desc(n_sites, n_logical, chi_max, mode, renormalise, n_ops, cut_sweep, 
                       float(rank_tol), float(bias_p), n_head, kept_mask, float(readout_rel), float(readout_abs))
 
 
+CAPACITIES = (8, 16, 32, 64, 128, 256)  # <= 64: work matrices in shared memory; 128/256: global-memory tier
+MAX_CAPACITY = CAPACITIES[-1]
+
+
 def chi_capacity(chi: int) -> int:
-    for cap in (8, 16, 32, 64):
+    for cap in CAPACITIES:
         if chi <= cap:
             return cap
     return 0

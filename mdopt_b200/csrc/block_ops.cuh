@@ -11,16 +11,19 @@
 // hit a single shared-memory bank).  "X" is the 2*CHI x 2*CHI work matrix, "P2" a CHI x 2*CHI page.
 #pragma once
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef MDOPT_EMU
 #include <algorithm>
 #define MD_DEV inline
+#define MD_HD inline
 #define MD_SYNC() ((void)0)
 #define MD_PAR_FOR(i, n) for (int i = 0; i < (n); ++i)
 #define MD_LEADER if (true)
 #else
 #define MD_DEV __device__ __forceinline__
+#define MD_HD __host__ __device__ inline
 #define MD_SYNC() __syncthreads()
 #define MD_PAR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
 #define MD_LEADER if (threadIdx.x == 0)
@@ -93,12 +96,34 @@ struct EngineState {
   int mirrored;        // frame: 0 normal, 1 mirrored (moving the centre left)
 };
 
+// Capacities up to SMEM_CHI_MAX keep the two work matrices in shared memory; larger ones (the large-chi
+// tier) keep the same layout in a per-CTA slice of the global workspace (L2-resident at chi = 128) and only
+// the O(chi) vectors in shared memory.
+constexpr int SMEM_CHI_MAX = 64;
+template <int CHI, bool IN_SMEM>
+struct MatStore {
+  double X[2 * CHI * (2 * CHI + 1)];   // work matrix (up to 2CHI x 2CHI)
+  double P2[CHI * (2 * CHI + 1)];      // coefficient page (up to CHI x 2CHI)
+};
 template <int CHI>
-struct Smem {
+struct MatStore<CHI, false> {
+  double* X;
+  double* P2;
+};
+// doubles of global scratch a CTA needs for X and P2 (0 when they live in shared memory)
+MD_HD constexpr size_t mat_store_doubles(int chi) {
+  return chi <= SMEM_CHI_MAX ? 0 : (size_t)3 * chi * (2 * chi + 1);
+}
+
+template <int CHI>
+struct Smem : MatStore<CHI, (CHI <= SMEM_CHI_MAX)> {
   static constexpr int LD = 2 * CHI + 1;
   static constexpr int N2 = 2 * CHI;
-  double X[N2 * LD];   // work matrix (up to 2CHI x 2CHI)
-  double P2[CHI * LD];  // coefficient page (up to CHI x 2CHI)
+  static constexpr bool MATS_IN_SMEM = (CHI <= SMEM_CHI_MAX);
+  // bind X / P2 to a slice of global memory (no-op for the shared-memory capacities)
+  MD_DEV void bind_mats(double* g) {
+    if constexpr (!MATS_IN_SMEM) { this->X = g; this->P2 = g + (size_t)N2 * LD; }
+  }
   static constexpr int NPART = (NCH * N2 * 3 / 2 > 256) ? NCH * N2 * 3 / 2 : 256;
   double part[NPART];
   double vn1[N2], vn2[N2], tau[N2], sig[N2], wv[N2];

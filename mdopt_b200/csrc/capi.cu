@@ -14,6 +14,8 @@ const ChiOps* ops_for(int chi_cap) {
     case 16: return mdopt::chi_ops_16();
     case 32: return mdopt::chi_ops_32();
     case 64: return mdopt::chi_ops_64();
+    case 128: return mdopt::chi_ops_128();
+    case 256: return mdopt::chi_ops_256();
     default: return nullptr;
   }
 }
@@ -59,6 +61,8 @@ int mdopt_chi_capacity(int chi) {
   if (chi <= 16) return 16;
   if (chi <= 32) return 32;
   if (chi <= 64) return 64;
+  if (chi <= 128) return 128;  // large-chi tier: work matrices in global memory
+  if (chi <= 256) return 256;
   return 0;
 }
 
@@ -115,7 +119,8 @@ int mdopt_decode_batch_host(const mdopt_decode_desc* desc, int chi_cap, int n_ct
 }
 
 size_t mdopt_mps_program_workspace_bytes(int chi_cap, int batch) {
-  return 2 * (size_t)(2 * chi_cap) * (2 * chi_cap) * sizeof(double) * (size_t)batch;
+  const size_t mats = chi_cap <= 64 ? 0 : (size_t)3 * chi_cap * (2 * chi_cap + 1);  // mat_store_doubles()
+  return (2 * (size_t)(2 * chi_cap) * (2 * chi_cap) + mats) * sizeof(double) * (size_t)batch;
 }
 
 size_t mdopt_site_stride(int chi_cap) { return (size_t)chi_cap * 2 * chi_cap; }

@@ -12,11 +12,11 @@ namespace {
 
 template <int CHI>
 struct Cfg {
-  static constexpr int NT = (CHI * 8 < 64) ? 64 : CHI * 8;  // threads per CTA
+  static constexpr int NT = (CHI * 8 < 64) ? 64 : (CHI * 8 > 1024 ? 1024 : CHI * 8);  // threads per CTA
 };
 
 __host__ __device__ inline size_t ws_doubles_per_cta(int chi, int n_sites) {
-  size_t d = (size_t)n_sites * chi * 2 * chi + 2 * (size_t)(2 * chi) * (2 * chi);
+  size_t d = (size_t)n_sites * chi * 2 * chi + 2 * (size_t)(2 * chi) * (2 * chi) + mat_store_doubles(chi);
   size_t ints = ((size_t)n_sites + 1 + 1) / 2;  // bond dims, packed two per double slot
   d += ints;
   return (d + 31) & ~(size_t)31;
@@ -43,7 +43,9 @@ decode_kernel(DecodeParams P, const int* __restrict__ prog, const double* __rest
     st.sites = base;
     st.scr0 = base + (size_t)P.n_sites * Engine<CHI>::SITE_STRIDE;
     st.scr1 = st.scr0 + (size_t)(2 * CHI) * (2 * CHI);
-    st.bd = reinterpret_cast<int*>(st.scr1 + (size_t)(2 * CHI) * (2 * CHI));
+    double* mats = st.scr1 + (size_t)(2 * CHI) * (2 * CHI);
+    s.bind_mats(mats);
+    st.bd = reinterpret_cast<int*>(mats + mat_store_doubles(CHI));
     st.wtab = wtab;
     st.wdim = wdim;
     st.P = P;
@@ -109,8 +111,9 @@ mps_program_kernel(DecodeParams P, const int* __restrict__ prog, const double* _
       EngineState& st = s.st;
       st.sites = sites_io + (size_t)b * P.n_sites * Engine<CHI>::SITE_STRIDE;
       st.bd = bonds_io + (size_t)b * (P.n_sites + 1);
-      st.scr0 = ws + (size_t)blockIdx.x * 2 * (2 * CHI) * (2 * CHI);
+      st.scr0 = ws + (size_t)blockIdx.x * (2 * (size_t)(2 * CHI) * (2 * CHI) + mat_store_doubles(CHI));
       st.scr1 = st.scr0 + (size_t)(2 * CHI) * (2 * CHI);
+      s.bind_mats(st.scr1 + (size_t)(2 * CHI) * (2 * CHI));
       st.wtab = wtab; st.wdim = wdim; st.P = P;
       s.cnt = Counters{};
       st.centre = centre_io[b]; st.mirrored = 0; st.status = ST_OK; st.n_traced = 0;
@@ -250,29 +253,38 @@ int launch_decode(const mdopt_decode_desc* d, int n_ctas, const int32_t* program
 template <int C_>
 int launch_svd(int sms, int batch, int m, int n, const double* a, int chi_max, double cut, int renormalise,
                double* u, double* s, double* vh, int32_t* kept, double* trunc, int32_t* status, cudaStream_t st) {
-  cudaError_t e = set_smem_attr<C_>((const void*)svd_kernel<C_>);
-  if (e != cudaSuccess) return (int)e;
-  int per = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, svd_kernel<C_>, Cfg<C_>::NT, sizeof(Smem<C_>));
-  if (per < 1) per = 1;
-  int grid = batch < sms * per ? batch : sms * per;
-  svd_kernel<C_><<<grid, Cfg<C_>::NT, sizeof(Smem<C_>), st>>>(batch, m, n, a, chi_max, cut, renormalise, u, s, vh,
-                                                               kept, trunc, status);
-  return (int)cudaGetLastError();
+  // the stand-alone kernels work out of shared memory only; the large-chi tier goes through the MPS program
+  if constexpr (C_ > SMEM_CHI_MAX) {
+    return MDOPT_E_CAPACITY;
+  } else {
+    cudaError_t e = set_smem_attr<C_>((const void*)svd_kernel<C_>);
+    if (e != cudaSuccess) return (int)e;
+    int per = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, svd_kernel<C_>, Cfg<C_>::NT, sizeof(Smem<C_>));
+    if (per < 1) per = 1;
+    int grid = batch < sms * per ? batch : sms * per;
+    svd_kernel<C_><<<grid, Cfg<C_>::NT, sizeof(Smem<C_>), st>>>(batch, m, n, a, chi_max, cut, renormalise, u, s, vh,
+                                                                 kept, trunc, status);
+    return (int)cudaGetLastError();
+  }
 }
 
 template <int C_>
 int launch_site_apply(int sms, int batch, int rows, int vl, int vr, int mr, int bn, const double* m_in,
                       const double* a_site, const double* w, double* theta, cudaStream_t st) {
-  cudaError_t e = set_smem_attr<C_>((const void*)site_apply_kernel<C_>);
-  if (e != cudaSuccess) return (int)e;
-  int per = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, site_apply_kernel<C_>, Cfg<C_>::NT, sizeof(Smem<C_>));
-  if (per < 1) per = 1;
-  int grid = batch < sms * per ? batch : sms * per;
-  site_apply_kernel<C_><<<grid, Cfg<C_>::NT, sizeof(Smem<C_>), st>>>(batch, rows, vl, vr, mr, bn, m_in, a_site, w,
-                                                                      theta);
-  return (int)cudaGetLastError();
+  if constexpr (C_ > SMEM_CHI_MAX) {
+    return MDOPT_E_CAPACITY;
+  } else {
+    cudaError_t e = set_smem_attr<C_>((const void*)site_apply_kernel<C_>);
+    if (e != cudaSuccess) return (int)e;
+    int per = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, site_apply_kernel<C_>, Cfg<C_>::NT, sizeof(Smem<C_>));
+    if (per < 1) per = 1;
+    int grid = batch < sms * per ? batch : sms * per;
+    site_apply_kernel<C_><<<grid, Cfg<C_>::NT, sizeof(Smem<C_>), st>>>(batch, rows, vl, vr, mr, bn, m_in, a_site, w,
+                                                                        theta);
+    return (int)cudaGetLastError();
+  }
 }
 
 template <int C_>
@@ -280,7 +292,7 @@ int launch_mps_program(const mdopt_decode_desc* d, const int32_t* program, const
                        int batch, double* sites_io, int32_t* bonds_io, int32_t* centre_io, double* dist,
                        int32_t* success, int32_t* status, double* trace, void* workspace, size_t workspace_bytes,
                        cudaStream_t st) {
-  const size_t per = 2 * (size_t)(2 * C_) * (2 * C_) * sizeof(double);
+  const size_t per = (2 * (size_t)(2 * C_) * (2 * C_) + mat_store_doubles(C_)) * sizeof(double);
   if (workspace_bytes < per * (size_t)batch) return MDOPT_E_BADARG;
   cudaError_t e = set_smem_attr<C_>((const void*)mps_program_kernel<C_>);
   if (e != cudaSuccess) return (int)e;

@@ -30,5 +30,7 @@ const ChiOps* chi_ops_8();
 const ChiOps* chi_ops_16();
 const ChiOps* chi_ops_32();
 const ChiOps* chi_ops_64();
+const ChiOps* chi_ops_128();
+const ChiOps* chi_ops_256();
 
 }  // namespace mdopt

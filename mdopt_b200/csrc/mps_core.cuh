@@ -37,6 +37,12 @@ struct Engine {
   static constexpr int LD = Smem<CHI>::LD;
   static constexpr int N2 = Smem<CHI>::N2;
   static constexpr int SITE_STRIDE = CHI * 2 * CHI;
+#ifndef MDOPT_EMU
+  // register-resident QR / Jacobi routines (block_ops.cuh) exist for the shared-memory capacities only
+  static constexpr bool REG_PATH = (CHI <= SMEM_CHI_MAX);
+#else
+  static constexpr bool REG_PATH = false;
+#endif
 
   Smem<CHI>& s;
   EngineState& st;
@@ -187,17 +193,20 @@ struct Engine {
     int Knew = 0;
     const int kmax = chi_lim < CHI ? chi_lim : CHI;
     if (!use_svd) {
-#ifndef MDOPT_EMU
       long long t0 = MD_CLOCK();
-      // 8 lanes per column; a thread group owns one column for C <= CHI (every centre move) and two
-      // (c, c + CHI) for wider matrices
-      if (C <= CHI) qrcp_reg<CHI, 8, 1>(s, orig, R, C, kmax, st.P.rank_tol);
-      else qrcp_reg<CHI, 8, 2>(s, orig, R, C, kmax, st.P.rank_tol);
-      MD_LEADER { s.cnt.cyc_qr += (double)(MD_CLOCK() - t0); }
-#else
-      load_x(orig, R, C);
-      qrcp<CHI>(s, R, C, kmax, st.P.rank_tol);
+#ifndef MDOPT_EMU
+      if constexpr (REG_PATH) {
+        // 8 lanes per column; a thread group owns one column for C <= CHI (every centre move) and two
+        // (c, c + CHI) for wider matrices
+        if (C <= CHI) qrcp_reg<CHI, 8, 1>(s, orig, R, C, kmax, st.P.rank_tol);
+        else qrcp_reg<CHI, 8, 2>(s, orig, R, C, kmax, st.P.rank_tol);
+      } else
 #endif
+      {
+        load_x(orig, R, C);
+        qrcp<CHI>(s, R, C, kmax, st.P.rank_tol);
+      }
+      MD_LEADER { s.cnt.cyc_qr += (double)(MD_CLOCK() - t0); }
       Knew = s.iscr[0];
       if (s.iscr[1]) {  // more than chi_lim significant directions: genuine truncation needed
         use_svd = 1;
@@ -205,42 +214,41 @@ struct Engine {
       }
     }
     if (!use_svd) {
-#ifndef MDOPT_EMU
+      const int lay = REG_PATH ? 2 : 0;
       if (Knew == 0) {  // zero matrix: keep a single zero direction (the state has zero norm)
-        MD_PAR_FOR(i, R) s.P2[i] = (i == 0) ? 1.0 : 0.0;
-        MD_PAR_FOR(c, C) s.X[c] = 0.0;
-        MD_LEADER { s.iscr[7] = 2; }
+        if (lay == 2) {
+          MD_PAR_FOR(i, R) s.P2[i] = (i == 0) ? 1.0 : 0.0;
+          MD_PAR_FOR(c, C) s.X[c] = 0.0;
+        } else {
+          MD_PAR_FOR(i, R) s.X[i * LD] = (i == 0) ? 1.0 : 0.0;
+          MD_PAR_FOR(c, C) s.P2[c] = 0.0;
+        }
+        MD_LEADER { s.iscr[7] = lay; }
         MD_SYNC();
         return 1;
       }
       long long t1 = MD_CLOCK();
-      form_q_reg<CHI>(s, R, Knew);
-      MD_LEADER { s.iscr[7] = 2; s.cnt.cyc_formq += (double)(MD_CLOCK() - t1); }
-      MD_SYNC();
-      return Knew;
-#else
-      if (Knew == 0) {
-        MD_PAR_FOR(i, R) s.X[i * LD] = (i == 0) ? 1.0 : 0.0;
-        MD_PAR_FOR(c, C) s.P2[c] = 0.0;
-        MD_LEADER { s.iscr[7] = 0; }
-        MD_SYNC();
-        return 1;
-      }
-      extract_coeff<CHI>(s, Knew, C);
-      form_q<CHI>(s, R, Knew);
-      MD_LEADER { s.iscr[7] = 0; }
-      MD_SYNC();
-      return Knew;
+#ifndef MDOPT_EMU
+      if constexpr (REG_PATH) {
+        form_q_reg<CHI>(s, R, Knew);
+      } else
 #endif
+      {
+        extract_coeff<CHI>(s, Knew, C);
+        form_q<CHI>(s, R, Knew);
+      }
+      MD_LEADER { s.iscr[7] = lay; s.cnt.cyc_formq += (double)(MD_CLOCK() - t1); }
+      MD_SYNC();
+      return Knew;
     }
     load_x(orig, R, C);
     // ---- Jacobi SVD path ----
     long long tj = MD_CLOCK();
 #ifndef MDOPT_EMU
-    jacobi_columns_dev<CHI>(s, R, C, 60);
-#else
-    jacobi_columns<CHI>(s, R, C);
+    if constexpr (REG_PATH) jacobi_columns_dev<CHI>(s, R, C, 60);
+    else
 #endif
+      jacobi_columns<CHI>(s, R, C);
     MD_LEADER { s.cnt.cyc_jacobi += (double)(MD_CLOCK() - tj); }
     long long tc = MD_CLOCK();
     if (s.iscr[5]) st.status = ST_NOT_CONVERGED;

@@ -1,2 +1,2 @@
-from mdopt_b200.decoding.decoding import (decode_css, decode_css_batch, decode_custom,  # noqa: F401
-                                          decode_custom_batch)
+from mdopt_b200.decoding.decoding import (css_code_stabilisers, decode_css, decode_css_batch,  # noqa: F401
+                                          decode_custom, decode_custom_batch, multiply_pauli_strings)

@@ -36,6 +36,47 @@ def bitflip_bias(prob_bias: float = float(0.5)) -> np.ndarray:
     return op
 
 
+_PAULI_BITS = {"I": 0, "X": 1, "Z": 2, "Y": 3}
+_BITS_PAULI = "IXZY"
+
+
+def multiply_pauli_strings(pauli1: str, pauli2: str) -> str:
+    """Site-wise product of two Pauli strings, phases dropped (reference decoding.py:1042-1095)."""
+    if len(pauli1) != len(pauli2):
+        raise ValueError(f"The Pauli strings must have the same length, but got {len(pauli1)} and {len(pauli2)}.")
+    return "".join(_BITS_PAULI[_PAULI_BITS[a] ^ _PAULI_BITS[b]] for a, b in zip(pauli1, pauli2))
+
+
+def css_code_stabilisers(code) -> Tuple[List[str], List[str]]:
+    """Stabilisers of a CSS code as Pauli strings (reference decoding.py:463-509).  As there, the rows of
+    ``x_stabs_binary()`` (the checks that detect X errors) are written with the letter Z and the rows of
+    ``z_stabs_binary()`` with X (:492-507)."""
+    n = len(code)
+
+    def strings(matrix, pauli):
+        out = []
+        for row in matrix.rows():
+            support = {int(c) for c in row}
+            out.append("".join(pauli if q in support else "I" for q in range(n)))
+        return out
+
+    return strings(code.x_stabs_binary(), "Z"), strings(code.z_stabs_binary(), "X")
+
+
+def _state_errors(errors: Sequence[str], stabilisers: Sequence[str], rng) -> List[str]:
+    """``multiply_by_stabiliser=True`` (decoding.py:1237-1240, 1480-1483): the product state is built from the
+    error times one randomly drawn stabiliser; erasure errors are left alone.  The reference draws from numpy's
+    global RNG; pass ``rng`` (a numpy Generator) for a reproducible draw."""
+    out = []
+    for err in errors:
+        if "E" in err or err == "I" * len(err):
+            out.append(err)
+            continue
+        pick = rng.integers(len(stabilisers)) if rng is not None else np.random.randint(len(stabilisers))
+        out.append(multiply_pauli_strings(err, stabilisers[int(pick)]))
+    return out
+
+
 def css_code_constraint_sites(code):
     return schedule.code_site_lists(code)[0]
 
@@ -70,7 +111,8 @@ def _program_for(code, has_x, has_z, renormalise, strategy, orders, bias_type="B
 def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: float = float(1e-17),
                      bias_type: str = "Depolarising", bias_prob: float = float(0.1), renormalise: bool = True,
                      silent: bool = True, contraction_strategy: str = "Naive", tolerance: float = float(1e-12),
-                     orders: Optional[dict] = None, mode: str = "fast", return_status: bool = False):
+                     orders: Optional[dict] = None, mode: str = "fast", return_status: bool = False,
+                     multiply_by_stabiliser: bool = False, rng=None):
     """Decode many independent syndromes on the current GPU.
 
     Returns ``(dist float64[B, 2^k], success int32[B])`` (plus ``status int32[B]`` if asked); row b equals
@@ -110,10 +152,16 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
             groups.setdefault((has_x, has_z, mask), []).append(b)
     if not groups:
         return (dist, success, status) if return_status else (dist, success)
+    # the constraint groups stay gated by the characters of the ORIGINAL error (decoding.py:1230-1231 run before
+    # the multiplication at :1237-1240); only the product state sees the multiplied string
+    state_errors = errors
+    if multiply_by_stabiliser:
+        stabs_x, stabs_z = css_code_stabilisers(code)
+        state_errors = _state_errors(errors, stabs_x + stabs_z, rng)
     eng = engine.get_engine(n_sites, k, _effective_chi(chi_max, n_sites))
     for (has_x, has_z, mask), idx in groups.items():
         prog = _program_for(code, has_x, has_z, renormalise, contraction_strategy, orders, bias_type, bias_prob)
-        syms = schedule.symbols_from_errors([errors[b] for b in idx], k)
+        syms = schedule.symbols_from_errors([state_errors[b] for b in idx], k)
         d, s, st = eng.decode_host(prog, syms, cut=cut, bias_p=(-1.0 if depol else bias_prob),
                                    renormalise=renormalise, mode=mode,
                                    kept_mask=(0 if mask == default_mask else mask))
@@ -127,7 +175,7 @@ def decode_css(code, error: str, num_runs: int = int(1), chi_max: int = int(1e4)
                bias_type: str = "Depolarising", bias_prob: float = float(0.1), renormalise: bool = True,
                multiply_by_stabiliser: bool = False, silent: bool = False, contraction_strategy: str = "Naive",
                optimiser: str = "Dephasing DMRG", tolerance: float = float(1e-12), orders: Optional[dict] = None,
-               mode: str = "fast"):
+               mode: str = "fast", rng=None):
     """Error-based decoding of a CSS code by MPS marginalisation (reference decoding.py:1164-1404).
 
     Returns ``(|marginal| over the 2^k logical classes, success)`` with index 0 = I, 1 = X, 2 = Z, 3 = Y for
@@ -139,8 +187,6 @@ def decode_css(code, error: str, num_runs: int = int(1), chi_max: int = int(1e4)
         if not silent:
             logging.info("No error detected.")
         return [1.0, 0.0, 0.0, 0.0], 1
-    if multiply_by_stabiliser:
-        raise NotImplementedError("multiply_by_stabiliser draws from the unseeded global RNG; not provided")
     num_logicals = code.num_x_logicals() + code.num_z_logicals()
     num_sites = 2 * len(code) + num_logicals
     if 2 * len(error) != num_sites - num_logicals:
@@ -151,7 +197,7 @@ def decode_css(code, error: str, num_runs: int = int(1), chi_max: int = int(1e4)
     dist, success = decode_css_batch(code, [error], chi_max=chi_max, cut=cut, bias_type=bias_type,
                                      bias_prob=bias_prob, renormalise=renormalise, silent=True,
                                      contraction_strategy=contraction_strategy, tolerance=tolerance, orders=orders,
-                                     mode=mode)
+                                     mode=mode, multiply_by_stabiliser=multiply_by_stabiliser, rng=rng)
     return dist[0], int(success[0])
 
 
@@ -159,7 +205,8 @@ def decode_custom_batch(stabilizers: Sequence[str], x_logicals: Sequence[str], z
                         errors: Sequence[str], chi_max: int = int(1e4), cut: float = float(1e-17),
                         bias_type: str = "Depolarising", bias_prob: float = float(0.1), renormalise: bool = True,
                         silent: bool = True, contraction_strategy: str = "Naive", tolerance: float = float(1e-12),
-                        orders: Optional[dict] = None, mode: str = "fast", return_status: bool = False):
+                        orders: Optional[dict] = None, mode: str = "fast", return_status: bool = False,
+                        multiply_by_stabiliser: bool = False, rng=None):
     """Batched ``decode_custom`` (reference decoding.py:1407-1628): a code given by stabiliser / logical Pauli
     strings; every constraint group is always applied, success uses the relative tolerance 1e-12 (:1600-1604)."""
     from mdopt_b200 import engine
@@ -198,8 +245,9 @@ def decode_custom_batch(stabilizers: Sequence[str], x_logicals: Sequence[str], z
                 "Depolarising" if depol else "Bitflip", bias_prob)
         prog = _PROGRAM_CACHE[key]
         eng = engine.get_engine(n_sites, k, _effective_chi(chi_max, n_sites))
+        state_errors = _state_errors(errors, list(stabilizers), rng) if multiply_by_stabiliser else errors
         for mask, idx in groups.items():
-            syms = schedule.symbols_from_errors([errors[b] for b in idx], k)
+            syms = schedule.symbols_from_errors([state_errors[b] for b in idx], k)
             d, s, st = eng.decode_host(prog, syms, cut=cut, bias_p=(-1.0 if depol else bias_prob),
                                        renormalise=renormalise, mode=mode,
                                        kept_mask=(0 if mask == default_mask else mask), readout=(1e-12, 0.0))
@@ -212,7 +260,7 @@ def decode_custom(stabilizers: List[str], x_logicals: List[str], z_logicals: Lis
                   bias_type: str = "Depolarising", bias_prob: float = float(0.1), renormalise: bool = True,
                   multiply_by_stabiliser: bool = False, silent: bool = False, contraction_strategy: str = "Naive",
                   optimiser: str = "Dephasing DMRG", tolerance: float = float(1e-12), orders: Optional[dict] = None,
-                  mode: str = "fast"):
+                  mode: str = "fast", rng=None):
     """Error-based decoding of a code given by Pauli strings (reference decoding.py:1407-1628)."""
     if not silent:
         logging.info("Starting the decoding.")
@@ -220,8 +268,6 @@ def decode_custom(stabilizers: List[str], x_logicals: List[str], z_logicals: Lis
         if not silent:
             logging.info("No error detected.")
         return [1.0, 0.0, 0.0, 0.0], 1
-    if multiply_by_stabiliser:
-        raise NotImplementedError("multiply_by_stabiliser draws from the unseeded global RNG; not provided")
     num_logicals = len(x_logicals) + len(z_logicals)
     num_sites = len(stabilizers[0]) * 2 + num_logicals
     if 2 * len(error) != num_sites - num_logicals:
@@ -230,5 +276,6 @@ def decode_custom(stabilizers: List[str], x_logicals: List[str], z_logicals: Lis
     dist, success = decode_custom_batch(stabilizers, x_logicals, z_logicals, [error], chi_max=chi_max, cut=cut,
                                         bias_type=bias_type, bias_prob=bias_prob, renormalise=renormalise,
                                         contraction_strategy=contraction_strategy, tolerance=tolerance,
-                                        orders=orders, mode=mode)
+                                        orders=orders, mode=mode, multiply_by_stabiliser=multiply_by_stabiliser,
+                                        rng=rng)
     return dist[0], int(success[0])

@@ -50,7 +50,7 @@ class DecodeEngine:
         self.cap = _abi.chi_capacity(self.chi_max)
         if self.cap == 0:
             raise _lib.MdoptCudaError(
-                f"chi_max={chi_max} exceeds the largest compiled capacity (64) of the shared-memory engine"
+                f"chi_max={chi_max} exceeds the largest compiled capacity ({_abi.MAX_CAPACITY})"
             )
         if not 1 <= self.n_logical <= 6:
             raise NotImplementedError("the dense read-out supports 1..6 logical sites (Dephasing DMRG is out of scope)")
@@ -58,6 +58,10 @@ class DecodeEngine:
             self.n_ctas = int(self.lib.mdopt_decode_num_ctas(self.cap))
             if self.n_ctas <= 0:
                 raise _lib.MdoptCudaError("decode kernel cannot be made resident on this device")
+            # every resident CTA owns one MPS slice; at large chi the slices are sized against free HBM
+            free_bytes, _total = torch.cuda.mem_get_info()
+            per_cta = int(self.lib.mdopt_decode_workspace_bytes(self.cap, self.n_sites, 1))
+            self.n_ctas = max(1, min(self.n_ctas, int(0.8 * free_bytes) // max(per_cta, 1)))
             self.ws_bytes = int(self.lib.mdopt_decode_workspace_bytes(self.cap, self.n_sites, self.n_ctas))
             self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
             self.counters = torch.zeros(16, dtype=torch.float64, device=self.device)
@@ -196,13 +200,32 @@ def unpack_mps(sites: np.ndarray, bonds: np.ndarray) -> List[np.ndarray]:
 def run_program_on_mps(tensors, centre: int, ops: np.ndarray, wtab: np.ndarray, wdim: np.ndarray, chi_max: int,
                        cut: float, renormalise: bool, mode="svd", n_logical: int = 1, want_dist: bool = False,
                        trace_max: int = 0, cap: Optional[int] = None):
-    """Upload an MPS, run a program on it in place with one CTA, download the result."""
-    lib, torch = _lib.require_gpu()
+    """Upload an MPS, run a program on it in place with one CTA, download the result.
+
+    Without an explicit ``cap`` the compiled capacity is chosen from the input bonds and ``chi_max`` and raised
+    (64 -> 128 -> 256) when an intermediate bond outgrows it, so an untruncated contraction behaves like the
+    reference's up to bond dimension 256."""
     max_bond = max(max(t.shape[0], t.shape[2]) for t in tensors)
-    if cap is None:
-        cap = _abi.chi_capacity(max(min(int(chi_max), 64), max_bond))
-    if cap == 0:
-        raise _lib.MdoptCudaError("MPS exceeds the largest compiled capacity (64)")
+    if cap is not None:
+        caps = [int(cap)]
+    else:
+        first = _abi.chi_capacity(max(min(int(chi_max), 64), max_bond))
+        if first == 0:
+            raise _lib.MdoptCudaError(f"MPS exceeds the largest compiled capacity ({_abi.MAX_CAPACITY})")
+        limit = _abi.chi_capacity(min(int(chi_max), _abi.MAX_CAPACITY)) or _abi.MAX_CAPACITY
+        caps = [c for c in _abi.CAPACITIES if first <= c <= max(first, limit)]
+    for i, c in enumerate(caps):
+        res = _run_program_at_capacity(tensors, centre, ops, wtab, wdim, chi_max, cut, renormalise, mode, n_logical,
+                                       want_dist, trace_max, c)
+        if res["status"] != _abi.ST_CAPACITY:
+            return res
+    raise _lib.MdoptCudaError(
+        f"a tensor exceeded the engine capacity (bond dimension > {caps[-1]} or MPO bond > 2)")
+
+
+def _run_program_at_capacity(tensors, centre, ops, wtab, wdim, chi_max, cut, renormalise, mode, n_logical, want_dist,
+                             trace_max, cap):
+    lib, torch = _lib.require_gpu()
     sites, bonds = pack_mps(tensors, cap)
     n = len(tensors)
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -229,7 +252,7 @@ def run_program_on_mps(tensors, centre: int, ops: np.ndarray, wtab: np.ndarray, 
     torch.cuda.synchronize()
     status = int(d_status.item())
     if status == _abi.ST_CAPACITY:
-        raise _lib.MdoptCudaError("a tensor exceeded the engine capacity (bond dimension > 64 or MPO bond > 2)")
+        return {"status": status}
     out = unpack_mps(d_sites.cpu().numpy(), d_bonds.cpu().numpy())
     res = {"tensors": out, "centre": int(d_centre.item()), "status": status}
     if want_dist:

@@ -85,6 +85,31 @@ def main():
         run_custom("five_qubit_depol", five_qubit_errors(), chi_max=int(1e4), cut=1e-17, bias_type="Depolarising",
                    bias_prob=0.1, contraction_strategy="Naive")
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "stabiliser":
+        # multiply_by_stabiliser=True (decoding.py:1237-1240): the draw comes from numpy's global RNG, so seed it,
+        # record which stabiliser np.random.choice returns and replay the same seed for the decode
+        from examples.decoding.decoding import css_code_stabilisers
+        code = surface(3)
+        sx, sz = css_code_stabilisers(code)
+        kw = dict(chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, tolerance=1e-12)
+        rows = []
+        for seed, e in enumerate(["IIXIIIIIIIIII", "IIXIIZIIIIIII", "ZIIIIIIIIIIIZ", "IYIIIIXIIIIII"]):
+            np.random.seed(seed)
+            pick = str(np.random.choice(sx + sz))
+            np.random.seed(seed)
+            dist, ok = decode_css(code, e, multiply_by_stabiliser=True, silent=True,
+                                  contraction_strategy="Optimised", **kw)
+            rows.append({"error": e, "stabiliser": pick, "dist": [float(x) for x in dist], "success": int(ok)})
+        with open(os.path.join(OUT, "stabiliser_3x3.json"), "w") as fh:
+            json.dump({"name": "stabiliser_3x3", "lattice_size": 3, "kwargs": kw, "results": rows}, fh, indent=0)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "bigchi":
+        # large-chi tier (capacity 128): d=5 still truncates at chi_max=128, so this pins success flags and
+        # the marginals to the degenerate-truncation tolerance, like d5_chi64_bitflip
+        errs = [e for e in O.seeded_errors(41, 0.05, 40, 321, "Bitflip") if "X" in e][:5]
+        run_batch("d5_chi128_bitflip", 5, errs, chi_max=128, cut=1e-17, bias_type="Bitflip", bias_prob=0.1,
+                  tolerance=1e-12)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "erasure":
         run_batch("erasure_3x3", 3, ERASURE_CASES, chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1,
                   tolerance=1e-12)

@@ -486,15 +486,31 @@ def readout(logical_dense):
     return v, int(v[0] >= top - eps)
 
 
+def multiply_pauli_strings(p1, p2):
+    """Reference: decoding.py:1042-1095 (phase-free Pauli product, table written out there)."""
+    table = {("I", "I"): "I", ("I", "X"): "X", ("I", "Y"): "Y", ("I", "Z"): "Z",
+             ("X", "I"): "X", ("X", "X"): "I", ("X", "Y"): "Z", ("X", "Z"): "Y",
+             ("Y", "I"): "Y", ("Y", "X"): "Z", ("Y", "Y"): "I", ("Y", "Z"): "X",
+             ("Z", "I"): "Z", ("Z", "X"): "Y", ("Z", "Y"): "X", ("Z", "Z"): "I"}
+    if len(p1) != len(p2):
+        raise ValueError(f"The Pauli strings must have the same length, but got {len(p1)} and {len(p2)}.")
+    return "".join(table[(a, b)] for a, b in zip(p1, p2))
+
+
 def decode_css(code, error, chi_max=int(1e4), cut=1e-17, bias_type="Depolarising", bias_prob=0.1,
-               renormalise=True, contraction_strategy="Naive", tolerance=1e-12, orders=None, record=None):
+               renormalise=True, contraction_strategy="Naive", tolerance=1e-12, orders=None, record=None,
+               stabiliser=None):
     """Reference: decoding.py:1164-1404, dense read-out branch (<= 12 logical sites) only.
 
     ``orders`` optionally maps 'xl','zl','xc','zc' to explicit MPO orders (used with "Optimised").
+    ``stabiliser``: the Pauli string ``multiply_by_stabiliser=True`` would have drawn (decoding.py:1237-1240;
+    the reference draws it from numpy's global RNG, here it is an explicit input).
     """
     if error == "I" * len(error):
         return [1.0, 0.0, 0.0, 0.0], 1  # decoding.py:1225-1228
     has_x, has_z = "X" in error, "Z" in error  # literal-character gating, decoding.py:1230-1231
+    if stabiliser is not None and "E" not in error:  # after the gating, before the product state
+        error = multiply_pauli_strings(error, stabiliser)
     bits = pauli_to_mps(error)
     k = code.num_x_logicals() + code.num_z_logicals()
     n_sites = 2 * len(code) + k

@@ -21,6 +21,8 @@ int decode_impl(const mdopt_decode_desc* d, const int32_t* program, const double
                 double* counters) {
   Smem<CHI>* sm = new Smem<CHI>();
   std::vector<double> ws(ws_doubles(CHI, d->n_sites));
+  std::vector<double> mats(mat_store_doubles(CHI) + 1);
+  sm->bind_mats(mats.data());
   Engine<CHI> E(*sm);
   E.st.sites = ws.data();
   E.st.scr0 = E.st.sites + (size_t)d->n_sites * Engine<CHI>::SITE_STRIDE;
@@ -103,6 +105,8 @@ int program_impl(const mdopt_decode_desc* d, const int32_t* program, const doubl
                  int32_t* status, double* trace) {
   Smem<CHI>* sm = new Smem<CHI>();
   std::vector<double> ws(2 * (size_t)(2 * CHI) * (2 * CHI));
+  std::vector<double> mats(mat_store_doubles(CHI) + 1);
+  sm->bind_mats(mats.data());
   Engine<CHI> E(*sm);
   E.st.sites = sites_io; E.st.bd = bonds_io;
   E.st.scr0 = ws.data(); E.st.scr1 = E.st.scr0 + (size_t)(2 * CHI) * (2 * CHI);
@@ -135,6 +139,8 @@ int emu_decode_batch(const mdopt_decode_desc* d, int chi_cap, const int32_t* pro
     case 16: return decode_impl<16>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
     case 32: return decode_impl<32>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
     case 64: return decode_impl<64>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+    case 128: return decode_impl<128>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+    case 256: return decode_impl<256>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
   }
   return -2;
 }
@@ -146,6 +152,8 @@ int emu_mps_program(const mdopt_decode_desc* d, int chi_cap, const int32_t* prog
     case 16: return program_impl<16>(d, program, wtab, wdim, sites_io, bonds_io, centre_io, dist, success, status, trace);
     case 32: return program_impl<32>(d, program, wtab, wdim, sites_io, bonds_io, centre_io, dist, success, status, trace);
     case 64: return program_impl<64>(d, program, wtab, wdim, sites_io, bonds_io, centre_io, dist, success, status, trace);
+    case 128: return program_impl<128>(d, program, wtab, wdim, sites_io, bonds_io, centre_io, dist, success, status, trace);
+    case 256: return program_impl<256>(d, program, wtab, wdim, sites_io, bonds_io, centre_io, dist, success, status, trace);
   }
   return -2;
 }

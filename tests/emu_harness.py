@@ -62,6 +62,23 @@ def decode(program: schedule.Program, symbols, chi_max, cut, bias_p, renormalise
     return dist, success, status, trace, counters
 
 
+def program(tensors, centre, ops, wtab, wdim, chi_max, cut, mode=schedule.MODE_SVD, cap=None, renormalise=False):
+    """Run an op stream on one MPS through the host build of the engine (the mps_program kernel's body)."""
+    from mdopt_b200 import engine
+
+    if cap is None:
+        cap = _abi.chi_capacity(max(max(t.shape[0], t.shape[2]) for t in tensors))
+    sites, bonds = engine.pack_mps(tensors, cap)
+    ops = np.ascontiguousarray(ops, dtype=np.int32)
+    desc = _abi.make_desc(len(tensors), 1, min(int(chi_max), 1 << 30), mode, renormalise, ops.size, cut, -1.0)
+    centre_io = np.array([centre], dtype=np.int32)
+    status = np.zeros(1, dtype=np.int32)
+    rc = lib().emu_mps_program(C.byref(desc), cap, _ptr(ops), _ptr(wtab), _ptr(wdim), _ptr(sites), _ptr(bonds),
+                               _ptr(centre_io), None, None, _ptr(status), None)
+    assert rc == 0
+    return engine.unpack_mps(sites, bonds), int(centre_io[0]), int(status[0])
+
+
 def svd(a, chi_max, cut):
     a = np.ascontiguousarray(a, dtype=float)
     m, n = a.shape

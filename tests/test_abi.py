@@ -25,9 +25,13 @@ def test_header_symbols_are_bound_and_exported():
 
 def test_pure_host_queries():
     lib = _lib.load()
-    assert [lib.mdopt_chi_capacity(c) for c in (1, 8, 9, 16, 33, 64, 65)] == [8, 8, 16, 16, 64, 64, 0]
+    assert [lib.mdopt_chi_capacity(c) for c in (1, 8, 9, 16, 33, 64, 65, 128, 200, 256, 257)] == \
+        [8, 8, 16, 16, 64, 64, 128, 128, 256, 256, 0]
+    assert [_abi.chi_capacity(c) for c in (1, 64, 65, 256, 257)] == [8, 64, 128, 256, 0]
     assert lib.mdopt_site_stride(64) == 64 * 2 * 64
     assert lib.mdopt_mps_program_workspace_bytes(64, 2) == 2 * 2 * 128 * 128 * 8
+    # the large-chi tier adds its two work matrices (2chi x (2chi+1) and chi x (2chi+1)) to the workspace
+    assert lib.mdopt_mps_program_workspace_bytes(128, 1) == (2 * 256 * 256 + 3 * 128 * 257) * 8
 
 
 def test_desc_layout_matches_header():

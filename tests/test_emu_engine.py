@@ -190,3 +190,42 @@ def test_decode_custom_program(name):
                                         schedule.MODE_FAST, kept_mask=0 if mask == 3 else mask, readout=(1e-12, 0.0))
         assert st[0] == 0 and int(succ[0]) == r["success"], e
         np.testing.assert_allclose(dist[0], r["dist"], rtol=1e-10, atol=1e-14)
+
+
+def _random_canonical_mps(rng, n, chi):
+    """Right-canonical random MPS with bonds min(chi, 2^i, 2^(n-i)) and centre 0 (oracle object)."""
+    dims = [min(chi, 2 ** i, 2 ** (n - i)) for i in range(n + 1)]
+    tensors = []
+    for i in range(n):
+        a = rng.standard_normal((dims[i], 2 * dims[i + 1]))
+        q, _ = np.linalg.qr(a.T)
+        tensors.append(q.T.reshape(dims[i], 2, dims[i + 1]))
+    tensors[0] = tensors[0] / np.linalg.norm(tensors[0])
+    return O.MPS(tensors, 0)
+
+
+@pytest.mark.parametrize("mode", [schedule.MODE_FAST, schedule.MODE_SVD])
+def test_large_chi_tier_contract_matches_oracle(mode):
+    """Capacity 128 (work matrices outside shared memory): an untruncated XOR string on a bond-80 MPS grows
+    bonds past 64; the dense state must equal the oracle's mps_mpo_contract (contractor.py:177-378)."""
+    rng = np.random.default_rng(5)
+    n = 14
+    omps = _random_canonical_mps(rng, n, 80)
+    mpo = [O.XOR_LEFT] + [O.XOR_BULK, O.SWAP] * 3 + [O.XOR_BULK] * 4 + [O.XOR_RIGHT]
+    start = 1
+    ref = O.mps_mpo_contract(omps, mpo, start, chi_max=10 ** 4, cut=1e-14)
+    table = schedule.TensorTable()
+    ids = [table.add(np.asarray(t)) for t in mpo]
+    ops = [schedule.OP_SWEEP, start, len(mpo), 0, 0] + ids + [schedule.OP_END]
+    wtab, wdim = table.arrays()
+    tensors, centre, status = H.program([t.copy() for t in omps.tensors], 0, ops, wtab, wdim, 10 ** 4, 1e-14,
+                                        mode=mode, cap=128)
+    assert status == 0 and centre == start + len(mpo) - 1
+    assert max(t.shape[2] for t in tensors) > 64
+    ours = O.MPS(tensors, centre)
+    np.testing.assert_allclose(np.abs(ours.dense()), np.abs(ref.dense()), atol=1e-12)
+    # the capacity-64 build reports the overflow instead of truncating silently
+    small = _random_canonical_mps(rng, n, 64)
+    _, _, status64 = H.program([t.copy() for t in small.tensors], 0, ops, wtab, wdim, 10 ** 4, 1e-14, mode=mode,
+                               cap=64)
+    assert status64 == 2  # MDOPT_ST_CAPACITY

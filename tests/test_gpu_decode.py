@@ -82,6 +82,59 @@ def test_truncating_configs_success_agreement(api, name, min_agree):
         assert np.max(np.abs(dist - ref)) < 0.15
 
 
+class _ReplayRng:
+    """Stands in for the reference's global np.random draw: returns the recorded stabiliser indices in order."""
+
+    def __init__(self, picks):
+        self.picks = list(picks)
+
+    def integers(self, n):
+        return self.picks.pop(0)
+
+
+def test_multiply_by_stabiliser_matches_reference(api):
+    from mdopt_b200.decoding import css_code_stabilisers
+
+    g = load_golden("stabiliser_3x3")
+    code = api["surface_code"](3)
+    first, second = css_code_stabilisers(code)
+    stabs = first + second
+    errors = [r["error"] for r in g["results"]]
+    picks = [stabs.index(r["stabiliser"]) for r in g["results"]]
+    dist, success = api["decode_css_batch"](code, errors, contraction_strategy="Optimised",
+                                            multiply_by_stabiliser=True, rng=_ReplayRng(picks), **g["kwargs"])
+    for b, r in enumerate(g["results"]):
+        assert int(success[b]) == r["success"]
+        both = "X" in r["error"] and "Z" in r["error"]  # X+Z at chi=64 truncates inside degenerate multiplets
+        np.testing.assert_allclose(dist[b], r["dist"], rtol=5e-2 if both else 1e-10, atol=1e-13)
+    # the single-syndrome entry point takes the same switch
+    one = api["decode_css"](code, errors[0], contraction_strategy="Optimised", multiply_by_stabiliser=True,
+                            rng=_ReplayRng(picks[:1]), silent=True, **g["kwargs"])
+    np.testing.assert_allclose(one[0], g["results"][0]["dist"], rtol=1e-10, atol=1e-13)
+
+
+def test_large_chi_tier_decode(api):
+    """chi_max = 128 runs on the capacity-128 build (work matrices in global memory instead of shared memory).
+    d=5 still truncates inside degenerate multiplets there, so the bar is the one of d5_chi64_bitflip; the
+    d=3 batch never truncates and must match the chi_max=64 engine to 1e-10."""
+    g = load_golden("d5_chi128_bitflip")
+    kw = dict(g["kwargs"])
+    errors = [r["error"] for r in g["results"]]
+    dist, success, status = api["decode_css_batch"](api["surface_code"](5), errors, contraction_strategy="Optimised",
+                                                    return_status=True, **kw)
+    assert (status == 0).all()
+    ref = np.array([r["dist"] for r in g["results"]])
+    assert [int(x) for x in success] == [r["success"] for r in g["results"]]
+    print("d5 chi128 max abs deviation from the reference:", np.max(np.abs(dist - ref)))
+    assert np.max(np.abs(dist - ref)) < 0.15
+    # d=5 weight-1 errors at chi_max=256: same bar, exercises the 256 capacity end to end
+    one = ["I" * 12 + "X" + "I" * 28]
+    d256, s256, st256 = api["decode_css_batch"](api["surface_code"](5), one, chi_max=256, cut=1e-17,
+                                                bias_type="Bitflip", bias_prob=0.1,
+                                                contraction_strategy="Optimised", return_status=True)
+    assert st256[0] == 0 and s256[0] == 1 and abs(np.linalg.norm(d256[0]) - 1.0) < 1e-12
+
+
 def test_fast_and_svd_modes_agree(api):
     code = api["surface_code"](3)
     errors = O.seeded_errors(13, 0.15, 64, 99, "Bitflip")
@@ -178,8 +231,8 @@ def test_edge_batches(api):
         api["decode_css_batch"](code, ["IIXIIIIIIIIII"], chi_max=32, bias_type="Bitflip", bias_prob=1.5)
     from mdopt_b200 import _lib
 
-    with pytest.raises(_lib.MdoptCudaError):
-        api["decode_css_batch"](code, ["IIXIIIIIIIIII"], chi_max=128, bias_type="Bitflip")
+    with pytest.raises(_lib.MdoptCudaError):  # beyond the largest compiled capacity (256)
+        api["decode_css_batch"](code, ["IIXIIIIIIIIII"], chi_max=300, bias_type="Bitflip")
 
 
 def test_non_ok_status_paths(api):

@@ -177,6 +177,26 @@ def test_mps_mpo_contract_against_oracle(torch_mod, mode):
         mps_mpo_contract(CanonicalMPS(omps.tensors, 0), [O.XOR_LEFT] + [O.XOR_BULK] * 8 + [O.XOR_RIGHT], 0)
 
 
+@pytest.mark.parametrize("bond,cap_expected", [(80, 256), (40, 128)])
+def test_large_chi_tier_contract(torch_mod, bond, cap_expected):
+    """Untruncated XOR string on a 16-site MPS: bonds double past 64, the engine escalates to the 128 / 256
+    capacities and the dense state equals the oracle's (contractor.py:177-378) to 1e-12."""
+    from mdopt_b200.contractor import mps_mpo_contract
+    from mdopt_b200.mps import CanonicalMPS
+
+    rng = np.random.default_rng(21 + bond)
+    n = 16
+    omps = _random_canonical_mps(rng, n, bond)
+    mpo = [O.XOR_LEFT] + [O.XOR_BULK, O.SWAP] * 4 + [O.XOR_BULK] * 4 + [O.XOR_RIGHT]
+    for mode in ("fast", "svd"):
+        ref = O.mps_mpo_contract(omps, mpo, 1, chi_max=10 ** 4, cut=1e-14)
+        ours = mps_mpo_contract(CanonicalMPS([t.copy() for t in omps.tensors], 0), mpo, 1, chi_max=10 ** 4,
+                                cut=1e-14, mode=mode)
+        top = max(ours.bond_dimensions)
+        assert cap_expected // 2 < top <= cap_expected, top
+        np.testing.assert_allclose(np.abs(ours.dense()), np.abs(ref.dense()), atol=1e-12)
+
+
 def test_move_orth_centre_and_truncated_contract(torch_mod):
     from mdopt_b200.contractor import mps_mpo_contract
     from mdopt_b200.mps import CanonicalMPS

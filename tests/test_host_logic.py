@@ -8,6 +8,7 @@ import pytest
 import mps_oracle as O
 from mdopt_b200 import distributed as D
 from mdopt_b200 import schedule
+from conftest import load_golden
 from mdopt_b200.codes import surface_code
 from mdopt_b200.drivers import quantum_surface as drv
 from mdopt_b200.optimiser import utils as U
@@ -153,3 +154,22 @@ def test_two_rank_gloo_count_reduction():
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, 37, out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def test_stabiliser_helpers_follow_reference_conventions():
+    """css_code_stabilisers writes x_stabs_binary rows with Z and z_stabs_binary rows with X (decoding.py:492-507);
+    every stabiliser the reference drew for the fixture is in that list."""
+    from mdopt_b200.codes import surface_code
+    from mdopt_b200.decoding import css_code_stabilisers, multiply_pauli_strings
+
+    code = surface_code(3)
+    first, second = css_code_stabilisers(code)
+    assert all(set(s) <= {"I", "Z"} for s in first) and all(set(s) <= {"I", "X"} for s in second)
+    assert len(first) == code.num_x_stabs() and len(second) == code.num_z_stabs()
+    g = load_golden("stabiliser_3x3")
+    for r in g["results"]:
+        assert r["stabiliser"] in first + second
+    assert multiply_pauli_strings("IXYZ", "XXXX") == "XIZY"
+    assert multiply_pauli_strings("XZ", "ZX") == "YY"
+    with pytest.raises(ValueError):
+        multiply_pauli_strings("XX", "X")

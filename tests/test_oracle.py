@@ -126,3 +126,15 @@ def test_decode_custom_five_qubit_code(name):
         dist, ok = O.decode_custom(c["stabilizers"], c["x_logicals"], c["z_logicals"], row["error"], **g["kwargs"])
         assert int(ok) == row["success"], row["error"]
         np.testing.assert_allclose(np.asarray(dist, dtype=float), row["dist"], rtol=1e-11, atol=1e-14)
+
+
+def test_multiply_by_stabiliser_matches_reference():
+    """decoding.py:1237-1240 with the drawn stabiliser recorded in the fixture (oracle/make_golden.py stabiliser)."""
+    g = load_golden("stabiliser_3x3")
+    code = O.surface_code(3)
+    for r in g["results"]:
+        dist, ok = O.decode_css(code, r["error"], contraction_strategy="Optimised", stabiliser=r["stabiliser"],
+                                **g["kwargs"])
+        assert ok == r["success"]
+        np.testing.assert_allclose(dist, r["dist"], rtol=1e-12, atol=1e-15)
+    assert O.multiply_pauli_strings("IXYZ", "XXXX") == "XIZY"
