@@ -50,6 +50,9 @@ extern "C" {
 #define MDOPT_OP_GATE2 4    /* [4, site, gate_id, renormalise] two-site gate G[j][l][n][o] (16 doubles in wtab) on
                                (site, site+1), then split with chi=capacity / cut_move (depolarising bias) */
 
+#define MDOPT_OP_COMPRESS 5 /* [5, bond, renorm_spectrum] compress_bond (mdopt/mps/canonical.py:684-784, "svd"): centre to
+                               `bond`, split theta(bond, bond+1) with chi_max / cut_sweep, leave U.S at `bond` */
+
 typedef struct mdopt_decode_desc {
   int32_t n_sites;      /* MPS length N = 2n + k */
   int32_t n_logical;    /* k = kx + kz logical sites, 1 <= k <= 6 */

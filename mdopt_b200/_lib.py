@@ -19,6 +19,10 @@ class MdoptCudaError(RuntimeError):
 
 
 def lib_path() -> str:
+    """In-tree library; MDOPT_B200_LIB points at another build of the same ABI (kernel experiments)."""
+    override = os.environ.get("MDOPT_B200_LIB")
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 

@@ -26,7 +26,7 @@
 
 namespace mdopt {
 
-enum { OP_END = 0, OP_SWEEP = 1, OP_MOVE = 2, OP_MARGINAL = 3, OP_GATE2 = 4 };
+enum { OP_END = 0, OP_SWEEP = 1, OP_MOVE = 2, OP_MARGINAL = 3, OP_GATE2 = 4, OP_COMPRESS = 5 };
 enum { MODE_FAST = 0, MODE_SVD = 1 };
 enum { ST_OK = 0, ST_NOT_CONVERGED = 1, ST_CAPACITY = 2, ST_ZERO_NORM = 3 };
 
@@ -653,6 +653,24 @@ struct Engine {
         move_centre(prog[pc + 1]);
         if (st.status != ST_CAPACITY) gate2(prog[pc + 1], prog[pc + 2], prog[pc + 3]);
         pc += 4;
+      } else if (op == OP_COMPRESS) {
+        // compress_bond (canonical.py:684-784, "svd"): centre to `bond`, split theta(bond, bond+1) with the
+        // user's chi_max / cut (traced), then hand the spectrum back to site `bond` (U.S | V, :766-767)
+        const int bond = prog[pc + 1], rsv = prog[pc + 2];
+        move_centre(bond);
+        if (st.status != ST_CAPACITY) {
+          set_frame(0);
+          sweep(bond, 2, nullptr, st.P.chi_max, st.P.cut_sweep, 0, 0, rsv);
+          set_centre(bond + 1);
+        }
+        if (st.status != ST_CAPACITY) {
+          const double cut_back = st.P.cut_sweep < st.P.cut_move ? st.P.cut_sweep : st.P.cut_move;
+          set_frame(1);
+          sweep(st.P.n_sites - 2 - bond, 2, nullptr, CHI, cut_back, 0, 1, 0);
+          set_frame(0);
+          set_centre(bond);
+        }
+        pc += 3;
       } else if (op == OP_MARGINAL) {
         if (out != nullptr) marginal_readout(out, success);
         pc += 1;

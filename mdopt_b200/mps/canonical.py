@@ -2,7 +2,7 @@
 
 Mirror of the part of ``mdopt/mps/canonical.py`` the decode path touches: constructor and attributes
 (:87-140), ``copy`` (:142), ``reverse`` (:150), ``dense`` (:241), ``move_orth_centre`` (:345),
-``marginal`` (:906).  Tensors stay host NumPy arrays (the reference returns host arrays even on its GPU
+``compress_bond`` / ``compress`` (:684-904, "svd" strategy), ``marginal`` (:906).  Tensors stay host NumPy arrays (the reference returns host arrays even on its GPU
 backend, contractor.py:375-376); ``move_orth_centre`` and the MPO contraction run on the GPU engine.
 """
 from __future__ import annotations
@@ -128,6 +128,69 @@ class CanonicalMPS:
         wtab, wdim = table.arrays()
         res = engine.run_program_on_mps(self.tensors, centre, ops, wtab, wdim, self.chi_max, 1e-12, False, mode=mode)
         return CanonicalMPS(res["tensors"], res["centre"], self.tolerance, self.chi_max)
+
+    def _run_compress(self, bonds, chi_max, cut, renormalise, start_centre):
+        """OP_COMPRESS for each bond in order on the GPU; returns (new MPS, truncation error per bond)."""
+        from mdopt_b200 import engine, schedule
+        from mdopt_b200.optimiser.utils import IDENTITY
+
+        table = schedule.TensorTable()
+        table.add(IDENTITY)
+        wtab, wdim = table.arrays()
+        ops = []
+        for bond in bonds:
+            ops.extend([schedule.OP_COMPRESS, int(bond), int(bool(renormalise))])
+        ops.append(schedule.OP_END)
+        chi = int(min(int(chi_max), 1 << 30))
+        res = engine.run_program_on_mps(self.tensors, start_centre, np.array(ops, dtype=np.int32), wtab, wdim, chi,
+                                        float(cut), False, mode="svd", trace_max=4 * self.num_sites + 8)
+        errors = []
+        for row in res["trace"]:
+            rows, cols, kept, is_move = int(row[0]), int(row[1]), int(row[2]), int(row[3])
+            if rows == 0 and cols == 0:
+                break
+            if not is_move:  # the compressing split itself; centre moves are traced with is_move = 1
+                sv = row[4:4 + min(rows, cols)]
+                errors.append(float(np.sum(sv[kept:] ** 2)))
+        out = CanonicalMPS(res["tensors"], res["centre"], self.tolerance, self.chi_max)
+        return out, errors
+
+    def compress_bond(self, bond: int, chi_max: int = int(1e4), cut: float = float(1e-17),
+                      renormalise: bool = False, strategy: str = "svd", return_truncation_error: bool = False):
+        """Truncate one bond on the GPU (reference canonical.py:684-784): centre to ``bond``, SVD of the two-site
+        tensor with ``k = min(chi_max, #(s > cut))``, singular values absorbed into site ``bond``.  Only the
+        ``"svd"`` strategy runs on the engine."""
+        if bond not in range(self.num_bonds):
+            raise ValueError(f"Bond given {bond}, with the number of bonds in the MPS {self.num_bonds}.")
+        if strategy not in ["svd", "qr", "svd_advanced"]:
+            raise ValueError(f"Unsupported compression strategy: {strategy}")
+        if strategy != "svd":
+            raise NotImplementedError("the GPU engine provides the 'svd' compression strategy")
+        centre = self.orth_centre if self.orth_centre is not None else self.resolve_orth_centre()
+        out, errors = self._run_compress([bond], chi_max, cut, renormalise, centre)
+        return out, (errors[0] if return_truncation_error else None)
+
+    def compress(self, chi_max: int = int(1e4), cut: float = float(1e-17), renormalise: bool = False,
+                 strategy: str = "svd", return_truncation_errors: bool = False):
+        """``compress_bond`` for every bond (reference canonical.py:836-904): the centre first goes to the nearer
+        border; from the last site the chain is processed mirrored and the errors are reported in bond order."""
+        if strategy not in ["svd", "qr", "svd_advanced"]:
+            raise ValueError(f"Unsupported compression strategy: {strategy}")
+        if strategy != "svd":
+            raise NotImplementedError("the GPU engine provides the 'svd' compression strategy")
+        centre = self.orth_centre if self.orth_centre is not None else self.resolve_orth_centre()
+        from_last = centre != 0 and (centre == self.num_sites - 1 or centre > int(self.num_bonds / 2))
+        work = self
+        if from_last:  # :888-889 -- work on the mirrored chain
+            work = CanonicalMPS([np.ascontiguousarray(np.transpose(t)) for t in reversed(self.tensors)],
+                                self.num_sites - 1 - centre, self.tolerance, self.chi_max)
+            centre = work.orth_centre
+        out, errors = work._run_compress(list(range(self.num_bonds)), chi_max, cut, renormalise, centre)
+        if from_last:
+            out = CanonicalMPS([np.ascontiguousarray(np.transpose(t)) for t in reversed(out.tensors)],
+                               self.num_sites - 1 - out.orth_centre, self.tolerance, self.chi_max)
+            errors = errors[::-1]
+        return out, (errors if return_truncation_errors else [None])
 
     def marginal(self, sites_to_marginalise: List[int], renormalise: bool = False) -> "CanonicalMPS":
         """Trace sites out with (1,..,1)/sqrt(d); MUTATES and returns self (reference canonical.py:906-991).

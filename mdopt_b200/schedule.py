@@ -15,7 +15,7 @@ import numpy as np
 
 from mdopt_b200.optimiser.utils import (COPY_LEFT, SWAP, XOR_BULK, XOR_LEFT, XOR_RIGHT, ConstraintString, msro)
 
-OP_END, OP_SWEEP, OP_MOVE, OP_MARGINAL, OP_GATE2 = 0, 1, 2, 3, 4
+OP_END, OP_SWEEP, OP_MOVE, OP_MARGINAL, OP_GATE2, OP_COMPRESS = 0, 1, 2, 3, 4, 5
 MODE_FAST, MODE_SVD = 0, 1
 SYM_ZERO, SYM_ONE, SYM_PLUS = 0, 1, 2
 

@@ -103,6 +103,34 @@ def main():
         with open(os.path.join(OUT, "stabiliser_3x3.json"), "w") as fh:
             json.dump({"name": "stabiliser_3x3", "lattice_size": 3, "kwargs": kw, "results": rows}, fh, indent=0)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "compress":
+        # CanonicalMPS.compress / compress_bond (canonical.py:684-904, "svd") on a seeded real MPS with a generic
+        # spectrum: inputs, truncation errors, bond dimensions and the dense result
+        rng = np.random.default_rng(77)
+        n, chi = 9, 16
+        dims = [min(chi, 2 ** i, 2 ** (n - i)) for i in range(n + 1)]
+        tensors = []
+        for i in range(n):
+            q, _ = np.linalg.qr(rng.standard_normal((dims[i], 2 * dims[i + 1])).T)
+            tensors.append(q.T.reshape(dims[i], 2, dims[i + 1]))
+        tensors[0] = tensors[0] / np.linalg.norm(tensors[0])
+        cases = []
+        for (chi_max, cut, ren) in [(6, 1e-17, False), (6, 1e-17, True), (100, 0.05, False), (3, 1e-17, True)]:
+            mps = CanonicalMPS([t.copy() for t in tensors], 0, 1e-12, int(1e4))
+            out, errs = mps.compress(chi_max=chi_max, cut=cut, renormalise=ren, return_truncation_errors=True)
+            cases.append({"chi_max": chi_max, "cut": cut, "renormalise": ren, "errors": [float(e) for e in errs],
+                          "bond_dimensions": [int(b) for b in out.bond_dimensions],
+                          "dense": [float(x) for x in out.dense(flatten=True)]})
+        one = CanonicalMPS([t.copy() for t in tensors], 0, 1e-12, int(1e4))
+        cb, err = one.compress_bond(bond=4, chi_max=5, cut=1e-17, renormalise=False, return_truncation_error=True)
+        doc = {"tensors": [t.tolist() for t in tensors], "cases": cases,
+               "bond_case": {"bond": 4, "chi_max": 5, "error": float(err), "orth_centre": int(cb.orth_centre),
+                             "bond_dimensions": [int(b) for b in cb.bond_dimensions],
+                             "dense": [float(x) for x in cb.dense(flatten=True)]}}
+        with open(os.path.join(OUT, "compress_case.json"), "w") as fh:
+            json.dump(doc, fh)
+        print("compress_case", [c["bond_dimensions"] for c in cases])
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "bigchi":
         # large-chi tier (capacity 128): d=5 still truncates at chi_max=128, so this pins success flags and
         # the marginals to the degenerate-truncation tolerance, like d5_chi64_bitflip

@@ -273,6 +273,32 @@ def mps_mpo_contract(mps, mpo, start_site=0, renormalise=False, chi_max=int(1e4)
     return mps
 
 
+def compress_bond(mps, bond, chi_max=int(1e4), cut=1e-17, renormalise=False):
+    """Reference: canonical.py:684-784, strategy "svd".  Returns (new MPS, truncation error); the centre ends at
+    ``bond`` with the singular values absorbed into it (:766-767)."""
+    if bond not in range(len(mps) - 1):
+        raise ValueError(f"Bond given {bond}, with the number of bonds in the MPS {len(mps) - 1}.")
+    out = move_orth_centre(mps, bond, renormalise=False)
+    if out is mps:
+        out = mps.copy()
+    theta = np.tensordot(out.tensors[bond], out.tensors[bond + 1], (2, 0))
+    u, sv, v, err = split_two_site_tensor(theta, chi_max=chi_max, cut=cut, renormalise=renormalise)
+    out.tensors[bond] = u * sv[None, None, :]
+    out.tensors[bond + 1] = v
+    return out, err
+
+
+def compress(mps, chi_max=int(1e4), cut=1e-17, renormalise=False):
+    """Reference: canonical.py:836-904 for an MPS whose centre already sits on the first site (the centre is
+    moved to the nearest border first, :883-886; the mirrored "last" branch is not restated)."""
+    out = move_orth_centre(mps, 0, renormalise=False)
+    errors = []
+    for bond in range(len(mps) - 1):
+        out, err = compress_bond(out, bond, chi_max=chi_max, cut=cut, renormalise=renormalise)
+        errors.append(err)
+    return out, errors
+
+
 def marginal(mps, sites, renormalise=False):
     """Trace sites out with (1,..,1)/sqrt(d), absorbing right (left for the last site).  MUTATES ``mps``.
     Reference: canonical.py:906-991."""

@@ -62,7 +62,8 @@ def decode(program: schedule.Program, symbols, chi_max, cut, bias_p, renormalise
     return dist, success, status, trace, counters
 
 
-def program(tensors, centre, ops, wtab, wdim, chi_max, cut, mode=schedule.MODE_SVD, cap=None, renormalise=False):
+def program(tensors, centre, ops, wtab, wdim, chi_max, cut, mode=schedule.MODE_SVD, cap=None, renormalise=False,
+            trace_max=0):
     """Run an op stream on one MPS through the host build of the engine (the mps_program kernel's body)."""
     from mdopt_b200 import engine
 
@@ -70,12 +71,17 @@ def program(tensors, centre, ops, wtab, wdim, chi_max, cut, mode=schedule.MODE_S
         cap = _abi.chi_capacity(max(max(t.shape[0], t.shape[2]) for t in tensors))
     sites, bonds = engine.pack_mps(tensors, cap)
     ops = np.ascontiguousarray(ops, dtype=np.int32)
-    desc = _abi.make_desc(len(tensors), 1, min(int(chi_max), 1 << 30), mode, renormalise, ops.size, cut, -1.0)
+    stride = (4 + 2 * cap) if trace_max else 0
+    desc = _abi.make_desc(len(tensors), 1, min(int(chi_max), 1 << 30), mode, renormalise, ops.size, cut, -1.0,
+                          stride, trace_max)
     centre_io = np.array([centre], dtype=np.int32)
     status = np.zeros(1, dtype=np.int32)
+    trace = np.zeros((max(trace_max, 1), max(stride, 1)))
     rc = lib().emu_mps_program(C.byref(desc), cap, _ptr(ops), _ptr(wtab), _ptr(wdim), _ptr(sites), _ptr(bonds),
-                               _ptr(centre_io), None, None, _ptr(status), None)
+                               _ptr(centre_io), None, None, _ptr(status), _ptr(trace) if trace_max else None)
     assert rc == 0
+    if trace_max:
+        return engine.unpack_mps(sites, bonds), int(centre_io[0]), int(status[0]), trace
     return engine.unpack_mps(sites, bonds), int(centre_io[0]), int(status[0])
 
 

@@ -229,3 +229,35 @@ def test_large_chi_tier_contract_matches_oracle(mode):
     _, _, status64 = H.program([t.copy() for t in small.tensors], 0, ops, wtab, wdim, 10 ** 4, 1e-14, mode=mode,
                                cap=64)
     assert status64 == 2  # MDOPT_ST_CAPACITY
+
+
+def test_compress_program_matches_reference():
+    """OP_COMPRESS through the host build of the engine against the reference's compress() outputs: bond
+    dimensions, truncation error per bond (from the traced spectra) and the dense state."""
+    g = load_golden("compress_case")
+    tensors = [np.array(t) for t in g["tensors"]]
+    n = len(tensors)
+    table = schedule.TensorTable()
+    table.add(np.asarray(O.IDENTITY))
+    wtab, wdim = table.arrays()
+    for c in g["cases"]:
+        ops = []
+        for bond in range(n - 1):
+            ops += [schedule.OP_COMPRESS, bond, int(c["renormalise"])]
+        ops.append(schedule.OP_END)
+        out, centre, status, trace = H.program([t.copy() for t in tensors], 0, ops, wtab, wdim, c["chi_max"], c["cut"],
+                                               mode=schedule.MODE_SVD, cap=16, trace_max=4 * n)
+        assert status == 0 and centre == n - 2
+        assert [t.shape[2] for t in out[:-1]] == c["bond_dimensions"]
+        errs = []
+        for row in trace:
+            r, cc, kept, is_move = (int(v) for v in row[:4])
+            if r == 0 and cc == 0:
+                break
+            if not is_move:
+                sv = row[4:4 + min(r, cc)]
+                errs.append(float(np.sum(sv[kept:] ** 2)))
+        np.testing.assert_allclose(errs, c["errors"], rtol=1e-9, atol=1e-15)
+        dense = O.MPS(out, centre).dense(flatten=True)
+        sign = np.sign(np.dot(dense, c["dense"]))
+        np.testing.assert_allclose(sign * dense, c["dense"], atol=1e-11)

@@ -282,3 +282,68 @@ def test_shor_notebook_known_answer_on_gpu(torch_mod):
                                 strategy="Optimised", silent=True)
     out = mps.marginal(list(range(2, 20))).dense(flatten=True, renormalise=True, norm=1)
     np.testing.assert_allclose(np.abs(out), [0.61225663, 0.06778069, 0.28807136, 0.03189132], atol=5e-9)
+
+
+@pytest.mark.parametrize("stabs,xl,zl,strategy,norm,known", [
+    (["XZZXI", "IXZZX", "XIXZZ", "ZXIXZ"], ["XXXXX"], ["ZZZZZ"], "Optimised", 2,
+     [0.9999731, 0.00513518, 0.00513518, 0.0010249]),            # quantum_five_qubit.ipynb cell 28
+    (["XXI", "IXX"], ["XXX"], ["ZZZ"], "Naive", 1,
+     [7.72235375e-01, 2.26750465e-01, 7.83965408e-04, 2.30194740e-04]),  # quantum_three_qubit.ipynb cell 29
+])
+def test_custom_code_notebook_known_answers_on_gpu(torch_mod, stabs, xl, zl, strategy, norm, known):
+    """The notebooks' manual walk-through of a code given by Pauli strings, through the drop-in API on the GPU."""
+    from mdopt_b200 import schedule
+    from mdopt_b200.contractor import apply_one_site_operator
+    from mdopt_b200.decoding.decoding import bitflip_bias
+    from mdopt_b200.mps.utils import create_custom_product_state
+    from mdopt_b200.optimiser.utils import COPY_LEFT, SWAP, XOR_BULK, XOR_LEFT, XOR_RIGHT, apply_constraints
+
+    k, n = len(xl) + len(zl), len(stabs[0])
+    checks, (lx, lz) = schedule.custom_site_lists(stabs, xl, zl)
+    mps = create_custom_product_state("+" * k + "0" * (2 * n))
+    for site in range(k, 2 * n + k):
+        mps.tensors[site] = apply_one_site_operator(mps.tensors[site], bitflip_bias(0.01))
+    kw = dict(chi_max=10 ** 4, cut=1e-17, renormalise=True, strategy=strategy, silent=True)
+    for strings in (lx, lz):
+        mps = apply_constraints(mps, strings, [COPY_LEFT, XOR_BULK, SWAP, XOR_RIGHT], **kw)
+    mps = apply_constraints(mps, checks, [XOR_LEFT, XOR_BULK, SWAP, XOR_RIGHT], **kw)
+    out = mps.marginal(list(range(k, 2 * n + k))).dense(flatten=True, renormalise=True, norm=norm)
+    np.testing.assert_allclose(np.abs(out), known, atol=5e-8)
+
+
+def test_compress_on_gpu(torch_mod):
+    """CanonicalMPS.compress / compress_bond (canonical.py:684-904, "svd") on the GPU against the reference's
+    outputs for a seeded MPS: bond dimensions, truncation error per bond, dense state."""
+    from mdopt_b200.mps import CanonicalMPS
+
+    g = load_golden("compress_case")
+    tensors = [np.array(t) for t in g["tensors"]]
+    for c in g["cases"]:
+        mps = CanonicalMPS([t.copy() for t in tensors], 0)
+        out, errs = mps.compress(chi_max=c["chi_max"], cut=c["cut"], renormalise=c["renormalise"],
+                                 return_truncation_errors=True)
+        assert out.bond_dimensions == c["bond_dimensions"]
+        np.testing.assert_allclose(errs, c["errors"], rtol=1e-9, atol=1e-15)
+        dense = out.dense(flatten=True)
+        np.testing.assert_allclose(np.sign(np.dot(dense, c["dense"])) * dense, c["dense"], atol=1e-11)
+        assert mps.compress(chi_max=c["chi_max"])[1] == [None]
+    b = g["bond_case"]
+    out, err = CanonicalMPS([t.copy() for t in tensors], 0).compress_bond(b["bond"], chi_max=b["chi_max"],
+                                                                          return_truncation_error=True)
+    assert out.orth_centre == b["orth_centre"] and out.bond_dimensions == b["bond_dimensions"]
+    np.testing.assert_allclose(err, b["error"], rtol=1e-9)
+    dense = out.dense(flatten=True)
+    np.testing.assert_allclose(np.sign(np.dot(dense, b["dense"])) * dense, b["dense"], atol=1e-11)
+    # centre on the last site: the chain is processed mirrored, errors come back in bond order
+    c = g["cases"][0]
+    n = len(tensors)
+    right = CanonicalMPS([t.copy() for t in tensors], 0).move_orth_centre(n - 1, renormalise=False)
+    out2, errs2 = right.compress(chi_max=c["chi_max"], cut=c["cut"], return_truncation_errors=True)
+    assert len(errs2) == n - 1 and max(out2.bond_dimensions) <= c["chi_max"]
+    mirrored = CanonicalMPS([np.ascontiguousarray(np.transpose(t)) for t in reversed(right.tensors)], 0)
+    out3, errs3 = mirrored.compress(chi_max=c["chi_max"], cut=c["cut"], return_truncation_errors=True)
+    np.testing.assert_allclose(errs2, errs3[::-1], rtol=1e-9, atol=1e-15)
+    with pytest.raises(ValueError):
+        right.compress_bond(n - 1)
+    with pytest.raises(ValueError):
+        right.compress(strategy="lu")

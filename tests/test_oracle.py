@@ -138,3 +138,44 @@ def test_multiply_by_stabiliser_matches_reference():
         assert ok == r["success"]
         np.testing.assert_allclose(dist, r["dist"], rtol=1e-12, atol=1e-15)
     assert O.multiply_pauli_strings("IXYZ", "XXXX") == "XIZY"
+
+
+def _custom_walkthrough(stabs, xl, zl, strategy, norm):
+    """The notebooks' manual decode of a code given by Pauli strings: |+..+0..0>, bit-flip bias 0.01, X and Z
+    logicals, then all stabiliser checks (cut 1e-17, chi 1e4, renormalise), marginal, dense."""
+    k, n = len(xl) + len(zl), len(stabs[0])
+    checks, (lx, lz) = O.custom_sites(stabs, xl, zl)
+    mps = O.product_state("+" * k + "0" * (2 * n))
+    mps = O.apply_bitflip_bias(mps, range(k, 2 * n + k), 0.01)
+    kw = dict(chi_max=10 ** 4, cut=1e-17, renormalise=True, strategy=strategy)
+    for strings in (lx, lz):
+        mps = O.apply_constraints(mps, strings, [O.COPY_LEFT, O.XOR_BULK, O.SWAP, O.XOR_RIGHT], **kw)
+    mps = O.apply_constraints(mps, checks, [O.XOR_LEFT, O.XOR_BULK, O.SWAP, O.XOR_RIGHT], **kw)
+    return O.marginal(mps, list(range(k, 2 * n + k))).dense(flatten=True, renormalise=True, norm=norm)
+
+
+def test_five_and_three_qubit_notebook_known_answers():
+    """Printed outputs of examples/decoding/quantum_five_qubit.ipynb (cell 28, L2-normalised, "Optimised") and
+    examples/decoding/quantum_three_qubit.ipynb (cell 29, L1-normalised, "Naive")."""
+    five = _custom_walkthrough(["XZZXI", "IXZZX", "XIXZZ", "ZXIXZ"], ["XXXXX"], ["ZZZZZ"], "Optimised", 2)
+    np.testing.assert_allclose(five, [0.9999731, 0.00513518, 0.00513518, 0.0010249], atol=5e-8)
+    three = _custom_walkthrough(["XXI", "IXX"], ["XXX"], ["ZZZ"], "Naive", 1)
+    np.testing.assert_allclose(three, [7.72235375e-01, 2.26750465e-01, 7.83965408e-04, 2.30194740e-04], atol=5e-9)
+
+
+def test_compress_matches_reference():
+    """CanonicalMPS.compress / compress_bond (canonical.py:684-904, "svd") against the reference's outputs on a
+    seeded MPS (oracle/make_golden.py compress)."""
+    g = load_golden("compress_case")
+    tensors = [np.array(t) for t in g["tensors"]]
+    for c in g["cases"]:
+        out, errs = O.compress(O.MPS([t.copy() for t in tensors], 0), chi_max=c["chi_max"], cut=c["cut"],
+                               renormalise=c["renormalise"])
+        assert out.bond_dimensions == c["bond_dimensions"]
+        np.testing.assert_allclose(errs, c["errors"], rtol=1e-10, atol=1e-16)
+        np.testing.assert_allclose(out.dense(flatten=True), c["dense"], atol=1e-12)
+    b = g["bond_case"]
+    out, err = O.compress_bond(O.MPS([t.copy() for t in tensors], 0), b["bond"], chi_max=b["chi_max"])
+    assert out.orth_centre == b["orth_centre"] and out.bond_dimensions == b["bond_dimensions"]
+    np.testing.assert_allclose(err, b["error"], rtol=1e-10)
+    np.testing.assert_allclose(out.dense(flatten=True), b["dense"], atol=1e-12)
