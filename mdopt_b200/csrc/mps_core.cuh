@@ -129,7 +129,20 @@ struct Engine {
             for (int b = 0; b < TM; ++b) part[a][b] = 0.0;
           const double* mrow = Min + row0 * ld + q * mr;
           const double* arow = As + pu * Bn + m0;
-          if (row0 + TR <= rows && m0 + TM <= Bn) {  // interior tile: no bounds checks in the inner loop
+          if (row0 + TR <= rows && m0 + TM <= Bn && (Bn & 1) == 0) {
+            // interior tile, even row length: the two site-tensor entries come as one 16-byte load (adjacent
+            // lanes then read adjacent 16-byte words instead of two stride-2 8-byte streams)
+            static_assert(TM == 2, "the vector load below assumes two columns per thread");
+            for (int m = 0; m < mr; ++m) {
+              const double2 av = *reinterpret_cast<const double2*>(arow + (size_t)m * 2 * Bn);
+#pragma unroll
+              for (int a = 0; a < TR; ++a) {
+                const double x = mrow[a * ld + m];
+                part[a][0] += x * av.x;
+                part[a][1] += x * av.y;
+              }
+            }
+          } else if (row0 + TR <= rows && m0 + TM <= Bn) {  // interior tile: no bounds checks in the inner loop
             for (int m = 0; m < mr; ++m) {
               double av[TM];
 #pragma unroll
@@ -300,7 +313,7 @@ struct Engine {
 
   // ---- site j <- U (R = st.K*2 rows, Knew columns), frame layout (k, r, k') ----
   MD_DEV double u_at(int lay, int row, int kn, int Knew) const {
-    if (lay == 2) return s.P2[row * Knew + kn];
+    if (lay == 2) return s.P2[row * Knew + (kn ^ q_swizzle(row, Knew))];
     if (lay == 1) return s.X[row * LD + s.order[kn]] / s.sig[s.order[kn]];
     return s.X[row * LD + kn];
   }

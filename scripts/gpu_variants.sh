@@ -9,6 +9,6 @@ v = sys.argv[1]
 d = json.loads(open(f"gpurun_out/var_{v}.json").read().strip().splitlines()[-1])
 r = d["roofline"]; cs = r["cycle_split"]; tot = cs["cyc_total"]
 print("VARIANT", v, "value %.1f" % d["value"], "cyc/reflector %.0f" % (cs["cyc_qr"] / r["qr_reflectors"]),
-      {k[4:]: round(x / tot, 3) for k, x in cs.items() if k not in ("cyc_total", "cyc_pad")}, flush=True)
+      {k[4:]: round(x / tot, 3) for k, x in cs.items() if k not in ("cyc_total",)}, flush=True)
 PY
 done
