@@ -568,6 +568,8 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
   for (int k = 0; k < CPT; ++k) {
     const int col = col0 + k * NCOL;
     open[k] = col < C;
+    // closing record of a column: pivot row (N2 while open) and diagonal R entry
+    if (part == 0 && col < N2) { s.perm[col] = N2; s.sig[col] = 0.0; }
 #pragma unroll
     for (int idx = 0; idx < RPT; ++idx) {
       int r = 2 * TPC * (idx >> 1) + 2 * part + (idx & 1);
@@ -604,38 +606,56 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
     if (j >= kmax) { more = 1; break; }
     const int ko = (bi >= NCOL) ? bi / NCOL : 0;      // which of my columns could be the pivot
     const bool owner = (col0 + ko * NCOL == bi);
+    // pivot row entry a = x[row j] of column bi: every lane picks its candidate (register slot jslot is
+    // warp-uniform, one indexed jump) and the value is broadcast with a full-mask shuffle OUTSIDE the
+    // owner branch -- a sub-warp mask inside divergent code costs a MATCH + WARPSYNC sequence
+    const int jslot = ((j / (2 * TPC)) << 1) | (j & 1), jpart = (j >> 1) % TPC;
+    double apiv;
+    {
+      double a[CPT];
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) a[k] = 0.0;
+#define MD_QR_SLOT(I)                                                                 \
+  case I:                                                                             \
+    if constexpr ((I) < RPT) {                                                        \
+      _Pragma("unroll") for (int k = 0; k < CPT; ++k) a[k] = x[k][(I) < RPT ? (I) : 0]; \
+    }                                                                                 \
+    break;
+      switch (jslot) {
+        MD_QR_SLOT(0) MD_QR_SLOT(1) MD_QR_SLOT(2) MD_QR_SLOT(3) MD_QR_SLOT(4) MD_QR_SLOT(5) MD_QR_SLOT(6)
+        MD_QR_SLOT(7) MD_QR_SLOT(8) MD_QR_SLOT(9) MD_QR_SLOT(10) MD_QR_SLOT(11) MD_QR_SLOT(12)
+        MD_QR_SLOT(13) MD_QR_SLOT(14) MD_QR_SLOT(15)
+        default: break;
+      }
+#undef MD_QR_SLOT
+      double asel = a[0];
+#pragma unroll
+      for (int k = 1; k < CPT; ++k) asel = (k == ko) ? a[k] : asel;
+      apiv = __shfl_sync(0xffffffffu, asel, (lane & ~(TPC - 1)) | jpart);
+    }
     if (owner) {
-      // pivot row entry a = x[row j]; beta = -sign(a) * ||x[j:]||  (the norm is already known)
-      const int jslot = ((j / (2 * TPC)) << 1) | (j & 1), jpart = (j >> 1) % TPC;
 #pragma unroll
       for (int k = 0; k < CPT; ++k) {
         if (k == ko) {
-          double a = 0.0;
-          // jslot is warp-uniform: one indexed jump instead of a chain of RPT selects
-#define MD_QR_SLOT(I) case I: if constexpr ((I) < RPT) a = x[k][(I) < RPT ? (I) : 0]; break;
-          switch (jslot) {
-            MD_QR_SLOT(0) MD_QR_SLOT(1) MD_QR_SLOT(2) MD_QR_SLOT(3) MD_QR_SLOT(4) MD_QR_SLOT(5) MD_QR_SLOT(6)
-            MD_QR_SLOT(7) MD_QR_SLOT(8) MD_QR_SLOT(9) MD_QR_SLOT(10) MD_QR_SLOT(11) MD_QR_SLOT(12)
-            MD_QR_SLOT(13) MD_QR_SLOT(14) MD_QR_SLOT(15)
-            default: break;
-          }
-#undef MD_QR_SLOT
-          a = __shfl_sync(((1u << TPC) - 1u) << (lane & ~(TPC - 1)), a, (lane & ~(TPC - 1)) | jpart);
-          const double beta = -copysign(sqrt(nn_me[k]), a);
-          const double d = a - beta;
-          const double inv = 1.0 / (beta * d);
-          const double tau = -d * d * inv;   // (beta - a) / beta
-          const double scal = beta * inv;    // 1 / (a - beta)
+          double a = apiv;
+          // The reflector is published UNSCALED: v = (0, .., 0, a - beta, x[j+1:]) with tau = -1/(beta (a - beta)),
+          // i.e. H_j = I - tau v v^T with the 1/(a - beta)^2 of the textbook form folded into tau.  The column
+          // goes out first (it does not depend on the square root / reciprocal chain); only v[j] and tau
+          // follow.  The column's registers are left as they are: a closed column gets w = 0 in every later
+          // update and is rebuilt from (registers, pivot row, beta) at the final write-out.
 #pragma unroll
           for (int i2 = 0; i2 < RPT / 2; ++i2) {
             const int r0 = 2 * TPC * i2 + 2 * part;
             double2 v;
-            v.x = (r0 > j) ? x[k][2 * i2] * scal : ((r0 == j) ? 1.0 : 0.0);
-            v.y = (r0 + 1 > j) ? x[k][2 * i2 + 1] * scal : ((r0 + 1 == j) ? 1.0 : 0.0);
+            v.x = (r0 >= j) ? x[k][2 * i2] : 0.0;
+            v.y = (r0 + 1 >= j) ? x[k][2 * i2 + 1] : 0.0;
             *reinterpret_cast<double2*>(Vall + j * N2 + r0) = v;
-            if (r0 == j) x[k][2 * i2] = beta; else if (r0 > j) x[k][2 * i2] = 0.0;
-            if (r0 + 1 == j) x[k][2 * i2 + 1] = beta; else if (r0 + 1 > j) x[k][2 * i2 + 1] = 0.0;
           }
+          const double beta = -copysign(sqrt(nn_me[k]), a);
+          const double d = a - beta;
+          const double tau = -1.0 / (beta * d);
+          if (part == jpart) Vall[j * N2 + j] = d;
+          if (part == 0) { s.perm[bi] = j; s.sig[bi] = beta; }
           open[k] = false;
           if (part == 0) s.tau[j] = tau;
         }
@@ -646,8 +666,7 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
 #pragma unroll
     for (int k = 0; k < CPT; ++k) any_open |= open[k];
     if (__any_sync(0xffffffffu, any_open)) {
-      // ---- apply H_j.  Closed columns are invariant (their entries below their own pivot row are exactly
-      //      zero, so v.x == 0); only the pivot column itself must be masked.  Row chunks entirely above
+      // ---- apply H_j to the open columns (closed ones get w = 0 and stay as they are).  Row chunks entirely above
       //      the pivot row or below the matrix are skipped (warp-uniform).  v is loaded once per chunk and
       //      used for all CPT columns of the thread group. ----
       const double tau = s.tau[j];
@@ -680,7 +699,7 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
         for (int k = 0; k < CPT; ++k) w[k] += __shfl_xor_sync(0xffffffffu, w[k], off);
       }
 #pragma unroll
-      for (int k = 0; k < CPT; ++k) w[k] = (owner && k == ko) ? 0.0 : w[k] * tau;
+      for (int k = 0; k < CPT; ++k) w[k] = open[k] ? w[k] * tau : 0.0;  // closed columns are final
       double nn[CPT];
 #pragma unroll
       for (int k = 0; k < CPT; ++k) nn[k] = 0.0;
@@ -745,10 +764,14 @@ __device__ __noinline__ void qrcp_reg(Smem<CHI>& s, const double* orig, int R, i
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
       const int col = col0 + k * NCOL;
+      const int jc = (col < C) ? s.perm[col] : N2;
+      const double bet = (col < C) ? s.sig[col] : 0.0;
 #pragma unroll
       for (int idx = 0; idx < RPT; ++idx) {
         int r = 2 * TPC * (idx >> 1) + 2 * part + (idx & 1);
-        if (col < C && r < K) s.X[r * LD + col] = x[k][idx];
+        // closed column: R entries above its pivot row, beta on it, zero below; open column (negligible
+        // remainder): its rows < K
+        if (col < C && r < K) s.X[r * LD + col] = (r < jc) ? x[k][idx] : ((r == jc) ? bet : 0.0);
       }
     }
   }
@@ -939,43 +962,46 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     if (tid == 0) s.iscr[6] = 0;
     __syncthreads();
     for (int rnd = 0; rnd < n - 1; ++rnd) {
+      // every lane runs the load / dot / shuffle sequence (invalid slots contribute zeros), so the three
+      // reductions are plain full-mask shuffles in converged code; only the rotation itself is conditional
+      int a = 0, b = 0;
+      bool valid = false;
       if (slot < npair) {
-        int a, b;
         if (slot == 0) { a = n - 1; b = rnd; }
         else { a = (rnd + slot) % (n - 1); b = (rnd - slot + (n - 1)) % (n - 1); }
-        if (a < C && b < C) {  // uniform over the 8 lanes of the slot
-          double xa[RPT], xb[RPT];
-          double saa = 0.0, sbb = 0.0, sab = 0.0;
+        valid = (a < C && b < C);  // uniform over the 8 lanes of the slot
+      }
+      {
+        double xa[RPT], xb[RPT];
+        double saa = 0.0, sbb = 0.0, sab = 0.0;
+#pragma unroll
+        for (int idx = 0; idx < RPT; ++idx) {
+          const int r = 8 * idx + sub;
+          const bool ok = valid && r < R;
+          xa[idx] = ok ? X[r * LD + a] : 0.0;
+          xb[idx] = ok ? X[r * LD + b] : 0.0;
+          saa += xa[idx] * xa[idx]; sbb += xb[idx] * xb[idx]; sab += xa[idx] * xb[idx];
+        }
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) {
+          saa += __shfl_xor_sync(0xffffffffu, saa, off);
+          sbb += __shfl_xor_sync(0xffffffffu, sbb, off);
+          sab += __shfl_xor_sync(0xffffffffu, sab, off);
+        }
+        if (valid && sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) {
+          const double zeta = (sbb - saa) / (2.0 * sab);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = rsqrt(1.0 + t * t);
+          const double sn = c * t;
 #pragma unroll
           for (int idx = 0; idx < RPT; ++idx) {
             const int r = 8 * idx + sub;
-            const bool ok = r < R;
-            xa[idx] = ok ? X[r * LD + a] : 0.0;
-            xb[idx] = ok ? X[r * LD + b] : 0.0;
-            saa += xa[idx] * xa[idx]; sbb += xb[idx] * xb[idx]; sab += xa[idx] * xb[idx];
-          }
-          const unsigned m = 0xFFu << ((tid & 31) & ~7);
-#pragma unroll
-          for (int off = 1; off < 8; off <<= 1) {
-            saa += __shfl_xor_sync(m, saa, off);
-            sbb += __shfl_xor_sync(m, sbb, off);
-            sab += __shfl_xor_sync(m, sab, off);
-          }
-          if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) {
-            const double zeta = (sbb - saa) / (2.0 * sab);
-            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            const double c = rsqrt(1.0 + t * t);
-            const double sn = c * t;
-#pragma unroll
-            for (int idx = 0; idx < RPT; ++idx) {
-              const int r = 8 * idx + sub;
-              if (r < R) {
-                X[r * LD + a] = c * xa[idx] - sn * xb[idx];
-                X[r * LD + b] = sn * xa[idx] + c * xb[idx];
-              }
+            if (r < R) {
+              X[r * LD + a] = c * xa[idx] - sn * xb[idx];
+              X[r * LD + b] = sn * xa[idx] + c * xb[idx];
             }
-            if (sub == 0) atomicAdd(&s.iscr[6], 1);
           }
+          if (sub == 0) atomicAdd(&s.iscr[6], 1);
         }
       }
       __syncthreads();
