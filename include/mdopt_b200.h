@@ -55,7 +55,8 @@ extern "C" {
 
 typedef struct mdopt_decode_desc {
   int32_t n_sites;      /* MPS length N = 2n + k */
-  int32_t n_logical;    /* k = kx + kz logical sites, 1 <= k <= 6 */
+  int32_t n_logical;    /* k = kx + kz logical sites, 1 <= k <= 12 (the reference's dense read-out limit,
+                           decoding.py:1358; needs chi_cap >= 2^(k-1) for k <= 6, 2^ceil(k/2) above) */
   int32_t chi_max;      /* decode_css(chi_max=...) */
   int32_t mode;         /* MDOPT_MODE_* */
   int32_t renormalise;  /* decode_css(renormalise=...) */

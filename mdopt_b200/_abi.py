@@ -66,6 +66,12 @@ CAPACITIES = (8, 16, 32, 64, 128, 256)  # <= 64: work matrices in shared memory;
 MAX_CAPACITY = CAPACITIES[-1]
 
 
+def readout_min_capacity(n_logical: int) -> int:
+    """Smallest capacity whose read-out pages hold the dense stage for ``n_logical`` kept sites."""
+    k = int(n_logical)
+    return (1 << (k - 1)) if k <= 6 else (1 << ((k + 1) // 2))
+
+
 def chi_capacity(chi: int) -> int:
     for cap in CAPACITIES:
         if chi <= cap:

@@ -221,7 +221,11 @@ int launch_decode(const mdopt_decode_desc* d, int n_ctas, const int32_t* program
                   const int32_t* wdim, const uint8_t* symbols, int batch, double* dist, int32_t* success,
                   int32_t* status, double* trace, double* counters, void* workspace, size_t workspace_bytes,
                   cudaStream_t st) {
-  if ((size_t)(1 << d->n_logical) * CHI * 2 > (size_t)(2 * CHI) * (2 * CHI + 1)) return MDOPT_E_CAPACITY;
+  {  // the dense read-out pages hold 2^(k-1) x chi (k <= 6, one-sided) or 2^ceil(k/2) x chi (meeting in the middle)
+    const int k = d->n_logical;
+    const int need = (k <= 6) ? (1 << (k - 1)) : (1 << ((k + 1) / 2));
+    if (need > CHI) return MDOPT_E_CAPACITY;
+  }
   const size_t per = ws_doubles_per_cta(CHI, d->n_sites) * sizeof(double);
   const size_t need = per * (size_t)n_ctas + 256;
   if (workspace_bytes < need) return MDOPT_E_BADARG;

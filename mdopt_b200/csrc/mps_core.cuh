@@ -579,18 +579,34 @@ struct Engine {
     MD_PAR_FOR(t, L * 2) st.sites[(size_t)(kL - 1) * SITE_STRIDE + t] = T[t];
     MD_LEADER { st.bd[kL] = 1; }
     MD_SYNC();
-    // dense stage over the kL leading sites: D_j[(kept physical indices, most recent first), b]
+    // Dense stage over the kL leading sites, meeting in the middle so that up to 12 kept sites fit the shared
+    // work pages (the reference's dense read-out limit, decoding.py:1358-1379): the left part accumulates
+    // D[(kept bits of sites < jm), b], the right part E[b, (kept bits of sites >= jm)], and the result is
+    // out[iL + nL * iR] = sum_b D[iL, b] E[b, iR] (later sites are more significant, as after reverse()).
+    int nkept_total = 0;
+    for (int j = 0; j < kL; ++j) nkept_total += (kept >> j) & 1u;
+    int jm = 0;  // first site of the right part: the left part takes the first floor(nkept / 2) kept sites
+    {
+      int seen = 0;
+      const int want = (nkept_total <= 6) ? nkept_total : nkept_total / 2;
+      while (jm < kL && seen < want) { seen += (kept >> jm) & 1u; ++jm; }
+      if (nkept_total <= 6) jm = kL;  // small read-outs stay one-sided (right part empty)
+    }
     double* D0 = s.X;
     double* D1 = s.X + (N2 * LD) / 2;
+    double* E0 = s.P2;
+    double* E1 = s.P2 + (CHI * LD) / 2;
+    const int page = (CHI * LD) / 2;  // doubles per page (the smaller of the two pairs)
     int nb = 1, nidx = 1;
     MD_LEADER { D0[0] = 1.0; }
     MD_SYNC();
-    for (int j = 0; j < kL; ++j) {
+    for (int j = 0; j < jm; ++j) {
       const int Bl = nb;
       const int Br = (j == kL - 1) ? 1 : st.bd[j + 1];
       const double* A = st.sites + (size_t)j * SITE_STRIDE;
       const int last = (j == kL - 1);
       const int keep = (kept >> j) & 1u;
+      if ((size_t)nidx * (keep ? 2 : 1) * Br > (size_t)page) { st.status = ST_CAPACITY; MD_SYNC(); return; }
       if (keep) {
         MD_PAR_FOR(t, nidx * 2 * Br) {
           int b2 = t % Br; int r = t / Br; int idx = r % nidx; int p = r / nidx;
@@ -617,21 +633,76 @@ struct Engine {
       if (keep) nidx *= 2;
       nb = Br;
     }
-    MD_LEADER {
-      double nrm = 0.0, top = 0.0;
-      for (int i = 0; i < nidx; ++i) { double v = fabs(D0[i]); nrm += v * v; }
-      nrm = sqrt(nrm);
-      double inv = (ren && nrm > 1e-17) ? 1.0 / nrm : 1.0;
-      int nan_seen = 0;
-      for (int i = 0; i < nidx; ++i) {
-        double v = fabs(D0[i]) * inv;
-        out[i] = v;
-        if (v != v) nan_seen = 1;
-        if (v > top) top = v;
+    // right part, from the last head site down to jm: E[b, iR], the newly absorbed (earlier) site is the least
+    // significant bit of iR
+    int nR = 1, bR = 1;  // E0 is (bR x nR); empty right part: the 1 x 1 identity
+    MD_LEADER { E0[0] = 1.0; }
+    MD_SYNC();
+    for (int j = kL - 1; j >= jm; --j) {
+      const int Bl = st.bd[j];                 // left bond of site j
+      const int Br = bR;                       // = right bond of site j (1 for the last head site)
+      const double* A = st.sites + (size_t)j * SITE_STRIDE;
+      const int last = (j == kL - 1);
+      const int keep = (kept >> j) & 1u;
+      if ((size_t)Bl * nR * (keep ? 2 : 1) > (size_t)page) { st.status = ST_CAPACITY; MD_SYNC(); return; }
+      if (keep) {
+        MD_PAR_FOR(t, Bl * 2 * nR) {
+          int iR = t % nR; int r = t / nR; int p = r & 1; int bl = r >> 1;
+          double acc = 0.0;
+          for (int b = 0; b < Br; ++b) {
+            double a = last ? T[bl * 2 + p] : A[((size_t)bl * 2 + p) * Br + b];
+            acc += a * E0[b * nR + iR];
+          }
+          E1[bl * (2 * nR) + (2 * iR + p)] = acc;
+        }
+      } else {
+        MD_PAR_FOR(t, Bl * nR) {
+          int iR = t % nR; int bl = t / nR;
+          double acc = 0.0;
+          for (int b = 0; b < Br; ++b) {
+            double a = last ? (T[bl * 2] + T[bl * 2 + 1]) : (A[((size_t)bl * 2) * Br + b] + A[((size_t)bl * 2 + 1) * Br + b]);
+            acc += a * E0[b * nR + iR];
+          }
+          E1[bl * nR + iR] = acc * (1.0 / sqrt(2.0));
+        }
       }
-      if (nan_seen) { *success = 0; if (st.status == ST_OK) st.status = ST_ZERO_NORM; }
+      MD_SYNC();
+      double* tmp = E0; E0 = E1; E1 = tmp;
+      if (keep) nR *= 2;
+      bR = Bl;
+    }
+    // combine: |sum_b D[iL, b] E[b, iR]|, its 2-norm and its maximum (block reductions through s.part)
+    const int nL = nidx, ncls = nL * nR;
+    MD_PAR_FOR(i, ncls) {
+      const int iL = i % nL, iR = i / nL;
+      double acc = 0.0;
+      for (int b = 0; b < nb; ++b) acc += D0[iL * nb + b] * E0[b * nR + iR];
+      out[i] = fabs(acc);
+    }
+    MD_SYNC();
+    MD_PAR_FOR(ch, 64) {
+      double nrm = 0.0, top = 0.0; int bad = 0;
+      for (int i = ch; i < ncls; i += 64) { double v = out[i]; nrm += v * v; bad |= (v != v); top = fmax(top, v); }
+      s.part[ch] = nrm; s.part[64 + ch] = top; s.part[128 + ch] = bad ? 1.0 : 0.0;
+    }
+    MD_SYNC();
+    MD_LEADER {
+      double nrm = 0.0, top = 0.0, bad = 0.0;
+      for (int ch = 0; ch < 64; ++ch) { nrm += s.part[ch]; top = fmax(top, s.part[64 + ch]); bad += s.part[128 + ch]; }
+      nrm = sqrt(nrm);
+      s.dscr[4] = (ren && nrm > 1e-17) ? 1.0 / nrm : 1.0;
+      s.dscr[5] = top;
+      s.iscr[8] = (bad != 0.0 || nrm != nrm) ? 1 : 0;
+    }
+    MD_SYNC();
+    const double inv = s.dscr[4];
+    MD_PAR_FOR(i, ncls) out[i] = out[i] * inv;
+    MD_SYNC();
+    MD_LEADER {
+      if (s.iscr[8]) { *success = 0; if (st.status == ST_OK) st.status = ST_ZERO_NORM; }
       else {
-        double eps = fmax(st.P.readout_rel * top, st.P.readout_abs);
+        const double top = s.dscr[5] * inv;
+        const double eps = fmax(st.P.readout_rel * top, st.P.readout_abs);
         *success = (out[0] >= top - eps) ? 1 : 0;
       }
     }

@@ -217,8 +217,8 @@ def decode_custom_batch(stabilizers: Sequence[str], x_logicals: Sequence[str], z
     k = len(x_logicals) + len(z_logicals)
     n = len(stabilizers[0])
     n_sites = 2 * n + k
-    if not 1 <= k <= 6:
-        raise NotImplementedError("the dense read-out supports 1..6 logical sites")
+    if not 1 <= k <= 12:
+        raise NotImplementedError("the dense read-out supports 1..12 logical sites")
     if mode == "fast" and cut > 1e-14:
         mode = "svd"
     errors = list(errors)

@@ -47,13 +47,13 @@ class DecodeEngine:
         torch = self.torch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.n_sites, self.n_logical, self.chi_max = int(n_sites), int(n_logical), int(chi_max)
-        self.cap = _abi.chi_capacity(self.chi_max)
+        self.cap = _abi.chi_capacity(max(self.chi_max, _abi.readout_min_capacity(n_logical)))
         if self.cap == 0:
             raise _lib.MdoptCudaError(
                 f"chi_max={chi_max} exceeds the largest compiled capacity ({_abi.MAX_CAPACITY})"
             )
-        if not 1 <= self.n_logical <= 6:
-            raise NotImplementedError("the dense read-out supports 1..6 logical sites (Dephasing DMRG is out of scope)")
+        if not 1 <= self.n_logical <= 12:
+            raise NotImplementedError("the dense read-out supports 1..12 logical sites (Dephasing DMRG is out of scope)")
         with torch.cuda.device(self.device):
             self.n_ctas = int(self.lib.mdopt_decode_num_ctas(self.cap))
             if self.n_ctas <= 0:
@@ -159,7 +159,7 @@ _ENGINES: Dict[Tuple, DecodeEngine] = {}
 
 def get_engine(n_sites: int, n_logical: int, chi_max: int) -> DecodeEngine:
     lib, torch = _lib.require_gpu()
-    key = (torch.cuda.current_device(), n_sites, n_logical, _abi.chi_capacity(chi_max), chi_max)
+    key = (torch.cuda.current_device(), n_sites, n_logical, chi_max)
     if key not in _ENGINES:
         _ENGINES[key] = DecodeEngine(n_sites, n_logical, chi_max, max_batch=4096)
     return _ENGINES[key]
@@ -209,7 +209,8 @@ def run_program_on_mps(tensors, centre: int, ops: np.ndarray, wtab: np.ndarray, 
     if cap is not None:
         caps = [int(cap)]
     else:
-        first = _abi.chi_capacity(max(min(int(chi_max), 64), max_bond))
+        need = _abi.readout_min_capacity(n_logical) if want_dist else 1
+        first = _abi.chi_capacity(max(min(int(chi_max), 64), max_bond, need))
         if first == 0:
             raise _lib.MdoptCudaError(f"MPS exceeds the largest compiled capacity ({_abi.MAX_CAPACITY})")
         limit = _abi.chi_capacity(min(int(chi_max), _abi.MAX_CAPACITY)) or _abi.MAX_CAPACITY

@@ -204,8 +204,8 @@ class CanonicalMPS:
             raise ValueError("The list of sites to marginalise must be a subset of the list of all sites.")
         sites = sorted(set(sites_to_marginalise))
         k = sites[0]
-        if sites != list(range(k, self.num_sites)) or not 1 <= k <= 6:
-            raise NotImplementedError("the GPU marginal supports a contiguous tail k..N-1 with 1 <= k <= 6")
+        if sites != list(range(k, self.num_sites)) or not 1 <= k <= 12:
+            raise NotImplementedError("the GPU marginal supports a contiguous tail k..N-1 with 1 <= k <= 12")
         from mdopt_b200 import engine, schedule
         from mdopt_b200.optimiser.utils import IDENTITY
 

@@ -43,7 +43,7 @@ def _ptr(a):
 
 def decode(program: schedule.Program, symbols, chi_max, cut, bias_p, renormalise=True, mode=schedule.MODE_FAST,
            trace_max=0, rank_tol=_abi.DEFAULT_RANK_TOL, kept_mask=0, readout=(1e-9, 1e-12)):
-    cap = _abi.chi_capacity(max(chi_max, 1))
+    cap = _abi.chi_capacity(max(chi_max, 1, _abi.readout_min_capacity(program.n_logical)))
     B = symbols.shape[0]
     ncls = 1 << program.n_logical
     stride = (4 + 2 * cap) if trace_max else 0

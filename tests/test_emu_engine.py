@@ -6,7 +6,7 @@ import pytest
 
 import emu_harness as H
 import mps_oracle as O
-from conftest import load_golden
+from conftest import BLOCK_CASES, block_422_code, load_golden
 from mdopt_b200 import schedule
 from mdopt_b200.codes import surface_code
 
@@ -261,3 +261,20 @@ def test_compress_program_matches_reference():
         dense = O.MPS(out, centre).dense(flatten=True)
         sign = np.sign(np.dot(dense, c["dense"]))
         np.testing.assert_allclose(sign * dense, c["dense"], atol=1e-11)
+
+
+@pytest.mark.parametrize("num_blocks,chi,errors", BLOCK_CASES)
+def test_many_logical_sites_readout(num_blocks, chi, errors):
+    """8 and 12 logical sites (256 / 4096 classes): the dense read-out meets in the middle; every class
+    probability must equal the oracle's (decoding.py:1351-1379) on errors that never truncate."""
+    from mdopt_b200.codes import CssCode
+
+    args = block_422_code(num_blocks)
+    code, ocode = CssCode(*args), O.CssCode(*args)
+    kw = dict(chi_max=chi, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, contraction_strategy="Optimised",
+              tolerance=1e-12)
+    for (dist, ok, st, _, _), e in zip(emu_decode(code, errors, chi, 1e-17, 0.1, schedule.MODE_FAST), errors):
+        ref, ref_ok = O.decode_css(ocode, e, **kw)
+        assert st == 0 and len(dist) == 1 << (4 * num_blocks)
+        assert ok == ref_ok
+        np.testing.assert_allclose(dist, np.asarray(ref, float), rtol=1e-10, atol=1e-14)

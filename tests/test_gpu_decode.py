@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import mps_oracle as O
-from conftest import load_golden
+from conftest import BLOCK_CASES, block_422_code, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -133,6 +133,24 @@ def test_large_chi_tier_decode(api):
                                                 bias_type="Bitflip", bias_prob=0.1,
                                                 contraction_strategy="Optimised", return_status=True)
     assert st256[0] == 0 and s256[0] == 1 and abs(np.linalg.norm(d256[0]) - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("num_blocks,chi,errors", BLOCK_CASES)
+def test_many_logical_sites_readout(api, num_blocks, chi, errors):
+    """8 and 12 logical sites (256 / 4096 classes) through decode_css_batch: dense read-out meeting in the
+    middle, every class probability equal to the oracle's on errors that never truncate."""
+    from mdopt_b200.codes import CssCode
+
+    args = block_422_code(num_blocks)
+    code, ocode = CssCode(*args), O.CssCode(*args)
+    kw = dict(chi_max=chi, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, contraction_strategy="Optimised",
+              tolerance=1e-12)
+    dist, success, status = api["decode_css_batch"](code, errors, return_status=True, **kw)
+    assert dist.shape == (len(errors), 1 << (4 * num_blocks)) and (status == 0).all()
+    for b, e in enumerate(errors):
+        ref, ok = O.decode_css(ocode, e, **kw)
+        assert int(success[b]) == ok
+        np.testing.assert_allclose(dist[b], np.asarray(ref, float), rtol=1e-10, atol=1e-14)
 
 
 def test_fast_and_svd_modes_agree(api):
