@@ -153,6 +153,27 @@ def test_many_logical_sites_readout(api, num_blocks, chi, errors):
         np.testing.assert_allclose(dist[b], np.asarray(ref, float), rtol=1e-10, atol=1e-14)
 
 
+def test_large_chi_tier_depolarising(api):
+    """Depolarising bias + X/Y/Z errors on the capacity-128 build (OP_GATE2 and both constraint groups with the
+    work matrices in global memory): exact against the oracle wherever it reports no truncation."""
+    code, ocode = api["surface_code"](3), O.surface_code(3)
+    errors = [e for e in O.seeded_errors(13, 0.08, 24, 31, "Depolarising") if set(e) != {"I"}][:8]
+    kw = dict(chi_max=128, cut=1e-17, bias_type="Depolarising", bias_prob=0.1, contraction_strategy="Optimised",
+              tolerance=1e-12)
+    dist, success, status = api["decode_css_batch"](code, errors, return_status=True, **kw)
+    assert (status == 0).all()
+    exact = 0
+    for b, e in enumerate(errors):
+        ref, ok = O.decode_css(ocode, e, **kw)
+        if not O.decode_truncates(ocode, e, **kw):
+            exact += 1
+            assert int(success[b]) == ok
+            np.testing.assert_allclose(dist[b], np.asarray(ref, float), rtol=1e-10, atol=1e-14)
+        else:
+            np.testing.assert_allclose(dist[b], np.asarray(ref, float), rtol=0.15, atol=0.02)
+    assert exact >= 1
+
+
 def test_fast_and_svd_modes_agree(api):
     code = api["surface_code"](3)
     errors = O.seeded_errors(13, 0.15, 64, 99, "Bitflip")
