@@ -278,3 +278,15 @@ def test_many_logical_sites_readout(num_blocks, chi, errors):
         assert st == 0 and len(dist) == 1 << (4 * num_blocks)
         assert ok == ref_ok
         np.testing.assert_allclose(dist, np.asarray(ref, float), rtol=1e-10, atol=1e-14)
+
+
+def test_cluster_default_cut_is_svd_mode_parity():
+    """cut = 1e-8 at d=3 through the host build in MODE_SVD (what decode_css_batch selects for cut > 1e-14)."""
+    code, ocode = surface_code(3), O.surface_code(3)
+    errors = [e for e in O.seeded_errors(13, 0.08, 60, 77, "Bitflip") if "X" in e][:6]
+    kw = dict(chi_max=64, cut=1e-8, bias_type="Bitflip", bias_prob=0.1, contraction_strategy="Optimised",
+              tolerance=1e-12)
+    for (dist, ok, st, _, _), e in zip(emu_decode(code, errors, 64, 1e-8, 0.1, schedule.MODE_SVD), errors):
+        ref, ref_ok = O.decode_css(ocode, e, **kw)
+        assert st == 0 and ok == ref_ok
+        np.testing.assert_allclose(dist, np.asarray(ref, float), rtol=1e-10, atol=1e-13)

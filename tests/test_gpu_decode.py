@@ -174,6 +174,22 @@ def test_large_chi_tier_depolarising(api):
     assert exact >= 1
 
 
+def test_cluster_default_cut(api):
+    """cut = 1e-8 (the reference's cluster default, quantum_surface_cc.sh:23-24) discards singular values, so
+    decode_css_batch runs every split as an SVD with the reference's rule k = min(chi_max, #(s > cut)); at d=3
+    that is well posed and must match the oracle to 1e-10."""
+    code, ocode = api["surface_code"](3), O.surface_code(3)
+    errors = [e for e in O.seeded_errors(13, 0.08, 60, 77, "Bitflip") if "X" in e][:16]
+    kw = dict(chi_max=64, cut=1e-8, bias_type="Bitflip", bias_prob=0.1, contraction_strategy="Optimised",
+              tolerance=1e-12)
+    dist, success, status = api["decode_css_batch"](code, errors, return_status=True, **kw)
+    assert (status == 0).all()
+    for b, e in enumerate(errors):
+        ref, ok = O.decode_css(ocode, e, **kw)
+        assert int(success[b]) == ok
+        np.testing.assert_allclose(dist[b], np.asarray(ref, float), rtol=1e-10, atol=1e-13)
+
+
 def test_fast_and_svd_modes_agree(api):
     code = api["surface_code"](3)
     errors = O.seeded_errors(13, 0.15, 64, 99, "Bitflip")
