@@ -347,7 +347,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="syndromes per GPU per step")
-    ap.add_argument("--mode", default="fast", choices=["fast", "svd"])
+    ap.add_argument("--mode", default="svd", choices=["fast", "svd", "svd-gram"],
+                    help="svd (default): the reference algorithm with the orthogonality fast path; fast: QR steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -40,7 +40,9 @@ extern "C" {
 #define MDOPT_E_NOGPU (-3)
 
 #define MDOPT_MODE_FAST 0 /* rank-revealing QR steps, Jacobi SVD only where truncation is active */
-#define MDOPT_MODE_SVD 1  /* every split is an SVD with the reference's truncation rule */
+#define MDOPT_MODE_SVD 1  /* every split is an SVD with the reference's truncation rule; a split whose columns are
+                             already orthogonal (probe check, then Gram check) skips the Jacobi rotations */
+#define MDOPT_MODE_SVD_GRAM 2 /* same, with the deterministic Gram check only */
 
 /* Program opcodes (int32 stream); see mdopt_b200/schedule.py for the builder. */
 #define MDOPT_OP_END 0

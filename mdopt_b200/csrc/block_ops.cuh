@@ -95,6 +95,7 @@ struct EngineState {
   int centre;
   int K, Wq, Mr;       // carried-matrix dimensions: M(K, 2, Wq, Mr)
   int mirrored;        // frame: 0 normal, 1 mirrored (moving the centre left)
+  int in_x;            // 1: the carried matrix lives in s.X (ld LD) instead of scr0 (orthogonal fast path)
 };
 
 // Capacities up to SMEM_CHI_MAX keep the two work matrices in shared memory; larger ones (the large-chi
@@ -915,11 +916,40 @@ __device__ __noinline__ void form_q_reg(Smem<CHI>& s, int R, int K) {
   __syncthreads();
 }
 
+// truncation_rule with block-wide reductions instead of the leader's serial loops (same outputs; the sums are
+// accumulated in a different order, i.e. equal to rounding).  Needs blockDim.x >= C.
+template <int CHI>
+__device__ __forceinline__ void truncation_rule_dev(Smem<CHI>& s, int C, int chi_lim, double cut) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double sig_floor = sqrt(s.dscr[6]);
+  double v = 0.0;
+  int pred = 0;
+  if (tid < C) { v = s.sig[s.order[tid]]; pred = (v > cut && v > sig_floor); }
+  int k = __syncthreads_count(pred);
+  if (k > chi_lim) k = chi_lim;
+  double err = (tid < C && tid >= k) ? v * v : 0.0;
+  double kept = (tid < C && tid < k) ? v * v : 0.0;
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    err += __shfl_xor_sync(0xffffffffu, err, off);
+    kept += __shfl_xor_sync(0xffffffffu, kept, off);
+  }
+  if (lane == 0) { s.rot[warp] = err; s.rot[16 + warp] = kept; }
+  __syncthreads();
+  if (tid == 0) {
+    double e = 0.0, kp = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { e += s.rot[w]; kp += s.rot[16 + w]; }
+    s.iscr[0] = k; s.dscr[2] = e; s.dscr[3] = sqrt(kp);
+  }
+  __syncthreads();
+}
+
 // One-sided Jacobi, device version: 8 lanes per column pair, both columns of the pair in registers for
 // the round (load, 3 dot products reduced by shuffles, rotation, store), one CTA barrier per round.
 // Same round-robin order, rotation formula, thresholds and outputs as jacobi_columns<> above.
 template <int CHI>
-__device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int max_sweeps) {
+__device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int max_sweeps, int try_ortho = 0,
+                                                double* spill = nullptr) {
   constexpr int LD = Smem<CHI>::LD;
   constexpr int N2 = Smem<CHI>::N2;
   constexpr int RPT = N2 / 8;  // register rows per lane; slot idx holds matrix row 8*idx + sub
@@ -936,7 +966,9 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
   const double tol = EPS * sqrt((double)R);
   const double tol2 = tol * tol;
   const int per = (R + NCH - 1) / NCH;
-  // squared-norm floor below which a column counts as numerically zero
+  // squared-norm floor below which a column counts as numerically zero (the Gram pass below provides the
+  // norms itself, so the try_ortho path skips this extra pass over X)
+  if (!(try_ortho && C >= 2)) {
   MD_PAR_FOR(t, NCH * C) {
     int ch = t / C, c = t - ch * C;
     int i0 = ch * per, i1 = min(R, i0 + per);
@@ -955,9 +987,167 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     s.dscr[6] = mx * (4.0 * EPS) * (4.0 * EPS);
   }
   __syncthreads();
-  const double floor2 = s.dscr[6];
+  }  // !try_ortho
+  double floor2 = s.dscr[6];
   int sweeps = 0;
   int converged = (C < 2);
+  int ortho_done = 0;
+  if (!converged && try_ortho == 1) {
+    // ---- Probe check (Freivalds): for two fixed pseudo-random vectors z the identity X^T (X z) = D z with
+    // D = diag(|x_c|^2) holds for every z exactly when the columns are mutually orthogonal; a deviation above
+    // 1e-12 |x_c| |X z| in any component sends the call to the deterministic machinery below (Gram check /
+    // sweeps).  Three passes over X (8 flops per entry) instead of the R C^2 of the full Gram matrix.  What a
+    // pass can miss is non-orthogonality below 1e-12 relative, which leaves the factorisation X = (X/sigma) sigma
+    // exact and only perturbs the gauge at that level. ----
+    const int lane = tid & 31, warp = tid >> 5;
+    auto zval = [](int c, unsigned salt) -> double {
+      unsigned h = (unsigned)c * 2654435761u + salt;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      return 1.0 + (double)(h & 0xFFFFFu) * (1.0 / 1048576.0);   // in [1, 2)
+    };
+    double* z0 = s.vn1;       // probe vectors (C entries)
+    double* z1 = s.part;
+    double* y0 = s.wv;        // X z0   (R entries)
+    double* y1 = s.tau;       // X z1
+    for (int c = tid; c < C; c += blockDim.x) { z0[c] = zval(c, 0x9E3779B9u); z1[c] = zval(c, 0x7F4A7C15u); }
+    __syncthreads();
+    // pass 1: y = X z, four lanes per row (every lane runs the loop: 4*N2 == blockDim.x)
+    double ny0 = 0.0, ny1 = 0.0;
+    for (int r4 = tid; r4 < 4 * N2; r4 += blockDim.x) {
+      const int r = r4 >> 2, q = r4 & 3;
+      double a0s = 0.0, a1s = 0.0;
+      if (r < R) {
+        for (int c = q; c < C; c += 4) { const double x = X[r * LD + c]; a0s += x * z0[c]; a1s += x * z1[c]; }
+      }
+      a0s += __shfl_xor_sync(0xffffffffu, a0s, 1); a1s += __shfl_xor_sync(0xffffffffu, a1s, 1);
+      a0s += __shfl_xor_sync(0xffffffffu, a0s, 2); a1s += __shfl_xor_sync(0xffffffffu, a1s, 2);
+      if (q == 0 && r < R) { y0[r] = a0s; y1[r] = a1s; ny0 += a0s * a0s; ny1 += a1s * a1s; }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      ny0 += __shfl_xor_sync(0xffffffffu, ny0, off);
+      ny1 += __shfl_xor_sync(0xffffffffu, ny1, off);
+    }
+    if (lane == 0) { s.rot[warp] = ny0; s.rot[16 + warp] = ny1; }
+    __syncthreads();
+    ny0 = 0.0; ny1 = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ny0 += s.rot[w]; ny1 += s.rot[16 + w]; }
+    __syncthreads();
+    // pass 2: w = X^T y and the squared column norms, four lanes per column (rows interleaved)
+    int bad = 0;
+    double mxd = 0.0;
+    for (int c4 = tid; c4 < 4 * N2; c4 += blockDim.x) {
+      const int c = c4 >> 2, q = c4 & 3;
+      double w0 = 0.0, w1 = 0.0, d = 0.0;
+      if (c < C) {
+        for (int r = q; r < R; r += 4) { const double x = X[r * LD + c]; w0 += x * y0[r]; w1 += x * y1[r]; d += x * x; }
+      }
+      w0 += __shfl_xor_sync(0xffffffffu, w0, 1); w1 += __shfl_xor_sync(0xffffffffu, w1, 1); d += __shfl_xor_sync(0xffffffffu, d, 1);
+      w0 += __shfl_xor_sync(0xffffffffu, w0, 2); w1 += __shfl_xor_sync(0xffffffffu, w1, 2); d += __shfl_xor_sync(0xffffffffu, d, 2);
+      if (c < C) {
+        if (q == 0) s.vn2[c] = d;
+        mxd = fmax(mxd, d);
+        const double e0 = w0 - d * z0[c], e1 = w1 - d * z1[c];
+        if (e0 * e0 > 1e-24 * d * ny0 || e1 * e1 > 1e-24 * d * ny1) bad = 1;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) mxd = fmax(mxd, __shfl_xor_sync(0xffffffffu, mxd, off));
+    if (lane == 0) s.rot[warp] = mxd;
+    const int any_bad = __syncthreads_or(bad);
+    {
+      double mx = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, s.rot[w]);
+      floor2 = mx * (4.0 * EPS) * (4.0 * EPS);
+      if (tid == 0) s.dscr[6] = floor2;
+    }
+    converged = !any_bad;
+    ortho_done = converged;
+    if (tid == 0) s.cnt.flops_jacobi += 10.0 * R * C;
+    __syncthreads();
+  }
+  if (!converged && try_ortho) {
+    // ---- Gram check: are the columns already mutually orthogonal (to the rotation threshold)?  In the decode
+    // with bit-flip bias every bond stays in its Schmidt basis under the XOR / SWAP constraint tensors, so the
+    // matrix handed to an SVD-mode split needs no rotation at all; one register-tiled pass over X^T X (warp w
+    // owns columns 8w..8w+7, lane l pairs them with columns l, l+32, ..) replaces the round-robin sweep that
+    // would only have confirmed it.  Any pair above the threshold sends the call to the sweeps below. ----
+    constexpr int NBJ = (N2 + 31) / 32;     // column groups per lane
+    const int warp = tid >> 5, lane = tid & 31;
+    const int a0 = 8 * warp;
+    double g[8][NBJ];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int v = 0; v < NBJ; ++v) g[u][v] = 0.0;
+    // the Gram matrix is symmetric: a warp skips the 32-column groups that lie entirely left of its own
+    // columns (those pairs belong to the warps owning the other column); the first group it needs is
+    // warp-uniform, so each case below is a fully unrolled loop over compile-time column groups
+    bool use[NBJ];
+#pragma unroll
+    for (int v = 0; v < NBJ; ++v) use[v] = (32 * v + 31 >= a0);
+    if (a0 < C) {
+#define MD_GRAM_ROWS(V0)                                                                     \
+  _Pragma("unroll 2") for (int r = 0; r < R; ++r) {                                          \
+    const double* row = X + r * LD;                                                          \
+    double xa[8];                                                                            \
+    _Pragma("unroll") for (int u = 0; u < 8; ++u) xa[u] = (a0 + u < C) ? row[a0 + u] : 0.0;  \
+    _Pragma("unroll") for (int v = (V0); v < NBJ; ++v) {                                     \
+      const double xb = (lane + 32 * v < C) ? row[lane + 32 * v] : 0.0;                      \
+      _Pragma("unroll") for (int u = 0; u < 8; ++u) g[u][v] += xa[u] * xb;                   \
+    }                                                                                        \
+  }
+      switch (a0 / 32) {
+        case 0: MD_GRAM_ROWS(0) break;
+        case 1: if constexpr (NBJ > 1) { MD_GRAM_ROWS(1) } break;
+        case 2: if constexpr (NBJ > 2) { MD_GRAM_ROWS(2) } break;
+        default: if constexpr (NBJ > 3) { MD_GRAM_ROWS(3) } break;
+      }
+#undef MD_GRAM_ROWS
+      // publish the diagonal (squared column norms)
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < NBJ; ++v)
+          if (a0 + u == lane + 32 * v && a0 + u < C) s.vn2[a0 + u] = g[u][v];
+    }
+    __syncthreads();
+    {  // floor = (4 eps)^2 * largest squared column norm: block maximum of the diagonal
+      double mx = 0.0;
+      for (int c = tid; c < C; c += blockDim.x) mx = fmax(mx, s.vn2[c]);
+#pragma unroll
+      for (int off = 16; off; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      if (lane == 0) s.rot[warp] = mx;
+    }
+    __syncthreads();
+    {
+      double mx = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, s.rot[w]);
+      floor2 = mx * (4.0 * EPS) * (4.0 * EPS);
+      if (tid == 0) s.dscr[6] = floor2;
+    }
+    int bad = 0;
+    if (a0 < C) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < NBJ; ++v) {
+          const int ca = a0 + u, cb = lane + 32 * v;
+          if (use[v] && ca < C && cb < C && ca != cb) {
+            const double saa = s.vn2[ca], sbb = s.vn2[cb], sab = g[u][v];
+            if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) bad = 1;
+          }
+        }
+    }
+    converged = !__syncthreads_or(bad);
+    ortho_done = converged;
+    if (tid == 0) s.cnt.flops_jacobi += 1.0 * R * C * (C + 1);   // R (C^2 + C) / 2 multiply-adds
+  }
+  if (!converged && spill != nullptr) {
+    // the rotations are about to change X: keep the original for the coefficient product (flat, ld C)
+    MD_PAR_FOR(t, R * C) { int r = t / C, c = t - r * C; spill[t] = X[r * LD + c]; }
+    __syncthreads();
+  }
   while (!converged && sweeps < max_sweeps) {
     if (tid == 0) s.iscr[6] = 0;
     __syncthreads();
@@ -1013,18 +1203,22 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     __syncthreads();
   }
   // singular values = column norms; order by value (descending), ties by column index
-  MD_PAR_FOR(t, NCH * C) {
-    int ch = t / C, c = t - ch * C;
-    int i0 = ch * per, i1 = min(R, i0 + per);
-    double acc = 0.0;
-    for (int i = i0; i < i1; ++i) { double v = X[i * LD + c]; acc += v * v; }
-    s.part[ch * N2 + c] = acc;
-  }
-  __syncthreads();
-  MD_PAR_FOR(c, C) {
-    double acc = 0.0;
-    for (int ch = 0; ch < NCH; ++ch) acc += s.part[ch * N2 + c];
-    s.sig[c] = sqrt(acc);
+  if (ortho_done) {
+    MD_PAR_FOR(c, C) s.sig[c] = sqrt(s.vn2[c]);   // the Gram diagonal
+  } else {
+    MD_PAR_FOR(t, NCH * C) {
+      int ch = t / C, c = t - ch * C;
+      int i0 = ch * per, i1 = min(R, i0 + per);
+      double acc = 0.0;
+      for (int i = i0; i < i1; ++i) { double v = X[i * LD + c]; acc += v * v; }
+      s.part[ch * N2 + c] = acc;
+    }
+    __syncthreads();
+    MD_PAR_FOR(c, C) {
+      double acc = 0.0;
+      for (int ch = 0; ch < NCH; ++ch) acc += s.part[ch * N2 + c];
+      s.sig[c] = sqrt(acc);
+    }
   }
   __syncthreads();
   MD_PAR_FOR(c, C) {
@@ -1038,6 +1232,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
   }
   if (tid == 0) {
     s.iscr[4] = sweeps; s.iscr[5] = converged ? 0 : 1;
+    s.iscr[9] = (sweeps == 0 && C >= 2) ? 1 : 0;   // columns were orthogonal on entry: X is untouched
     s.cnt.n_jacobi_sweeps += sweeps;
     s.cnt.flops_jacobi += 2.0 * R * C;
   }

@@ -27,7 +27,7 @@
 namespace mdopt {
 
 enum { OP_END = 0, OP_SWEEP = 1, OP_MOVE = 2, OP_MARGINAL = 3, OP_GATE2 = 4, OP_COMPRESS = 5 };
-enum { MODE_FAST = 0, MODE_SVD = 1 };
+enum { MODE_FAST = 0, MODE_SVD = 1, MODE_SVD_GRAM = 2 };  // 2: SVD mode with the deterministic Gram check only
 enum { ST_OK = 0, ST_NOT_CONVERGED = 1, ST_CAPACITY = 2, ST_ZERO_NORM = 3 };
 
 // Per-CTA engine.  All persistent state lives in shared memory (s.st) so that it costs no registers in
@@ -83,7 +83,7 @@ struct Engine {
     }
     MD_LEADER { s.cnt.bytes_hbm += 8.0 * (A * 2 * B + A * 2 * vr * B); s.cnt.flops_apply += 3.0 * A * 2 * vr * B; }
     MD_SYNC();
-    MD_LEADER { st.K = A; st.Wq = vr; st.Mr = B; }
+    MD_LEADER { st.K = A; st.Wq = vr; st.Mr = B; st.in_x = 0; }
     MD_SYNC();
   }
 
@@ -92,9 +92,16 @@ struct Engine {
     const double* src = st.sites + (size_t)phys(j) * SITE_STRIDE;
     if (!st.mirrored) { MD_PAR_FOR(g, A * 2 * B) dst[g] = src[g]; }
     else {
-      MD_PAR_FOR(g, A * 2 * B) {  // phys tensor has dims (B, 2, A)
-        int a = g % A; int r = g / A; int p = r & 1; int b = r >> 1;
-        dst[(a * 2 + p) * B + b] = src[g];
+      // phys tensor has dims (B, 2, A): a transpose.  A warp moves a 4 (a) x 8 (b) patch: the global reads are
+      // eight fully used 32-byte sectors, the shared-memory writes collide at most 4-way (a plain linear walk
+      // over the source would be 16-way when 2B is a multiple of 16)
+      const int na = (A + 3) / 4, nbt = (B + 7) / 8;
+      MD_PAR_FOR(g, na * nbt * 2 * 32) {
+        const int l = g & 31; int t = g >> 5;
+        const int p = t & 1; t >>= 1;
+        const int ta = t % na, tb = t / na;
+        const int a = 4 * ta + (l & 3), b = 8 * tb + (l >> 2);
+        if (a < A && b < B) dst[(a * 2 + p) * B + b] = src[((size_t)b * 2 + p) * A + a];
       }
     }
     MD_LEADER { s.cnt.bytes_hbm += 8.0 * A * 2 * B; }
@@ -189,6 +196,26 @@ struct Engine {
     MD_SYNC();
   }
 
+  // ---- apply_site for a DIAGONAL coefficient matrix (orthogonal-columns fast path of the SVD mode): row k of
+  //      Min has its only entry in column s.order[k] = q*mr + m, so the contraction is a gather:
+  //      out[((k*2+p')*vr + w')*Bn + b] = Min[k, c_k] sum_p W(q,w',p,p') As[(m*2+p)*Bn + b] ----
+  //      The coefficient of row k is scale * s.sig[s.order[k]]; the result goes straight into s.X (ld LD), where
+  //      the next split looks for it (st.in_x), so the carried matrix never leaves the SM on this path.
+  MD_DEV void apply_site_diag(double scale, int rows, int vl, int vr, int mr, int Bn, const double* As) {
+    const int Cn = vr * Bn;
+    MD_PAR_FOR(t, rows * 2 * Cn) {
+      int b = t % Bn; int r = t / Bn;
+      int wo = r % vr; r /= vr;
+      int pd = r & 1; int k = r >> 1;
+      const int c = s.order[k];
+      const int q = c / mr, m = c - q * mr;
+      const double acc = w_at(vr, q, wo, 0, pd) * As[(m * 2 + 0) * Bn + b] + w_at(vr, q, wo, 1, pd) * As[(m * 2 + 1) * Bn + b];
+      s.X[(k * 2 + pd) * LD + wo * Bn + b] = scale * s.sig[c] * acc;
+    }
+    MD_LEADER { s.cnt.flops_apply += 4.0 * rows * 2 * Cn; st.in_x = 1; }
+    MD_SYNC();
+  }
+
   MD_DEV void load_x(const double* src, int R, int C) {
     MD_PAR_FOR(t, R * C) { int i = t / C, c = t - i * C; s.X[i * LD + c] = src[t]; }
     MD_LEADER { s.cnt.bytes_hbm += 8.0 * R * C; }
@@ -202,7 +229,7 @@ struct Engine {
   //   1  U = s.X[:, order[k]] / sig[order[k]],   coefficients = s.P2 (ld LD)     [Jacobi SVD path]
   //   2  U = s.P2 flat (ld st.K),                   coefficients = s.X rows (ld LD) [register QR path]
   MD_DEV int factor(const double* orig, int R, int C, int chi_lim, double cut, int is_move) {
-    int use_svd = (st.P.mode == MODE_SVD);
+    int use_svd = (st.P.mode != MODE_FAST);
     int Knew = 0;
     const int kmax = chi_lim < CHI ? chi_lim : CHI;
     if (!use_svd) {
@@ -254,18 +281,32 @@ struct Engine {
       MD_SYNC();
       return Knew;
     }
-    load_x(orig, R, C);
+    // the orthogonal fast path leaves the carried matrix in s.X (st.in_x); then orig (scr0) is stale and is only
+    // refreshed from X if the rotations have to run after all
+    const int x_loaded = (orig == st.scr0) && st.in_x;
+    if (!x_loaded) load_x(orig, R, C);
     // ---- Jacobi SVD path ----
     long long tj = MD_CLOCK();
 #ifndef MDOPT_EMU
-    if constexpr (REG_PATH) jacobi_columns_dev<CHI>(s, R, C, 60);
+    // SVD mode tries the orthogonality checks first (see jacobi_columns_dev); the truncating fallback of
+    // MODE_FAST comes from a QR gauge and goes straight to the sweeps
+    if constexpr (REG_PATH)
+      jacobi_columns_dev<CHI>(s, R, C, 60, st.P.mode == MODE_SVD ? 1 : (st.P.mode == MODE_SVD_GRAM ? 2 : 0),
+                              x_loaded ? st.scr0 : nullptr);
     else
 #endif
+    {
+      MD_LEADER { s.iscr[9] = 0; }
       jacobi_columns<CHI>(s, R, C);
+    }
     MD_LEADER { s.cnt.cyc_jacobi += (double)(MD_CLOCK() - tj); }
     long long tc = MD_CLOCK();
     if (s.iscr[5]) st.status = ST_NOT_CONVERGED;
-    truncation_rule<CHI>(s, C, chi_lim, cut);
+#ifndef MDOPT_EMU
+    if constexpr (REG_PATH) truncation_rule_dev<CHI>(s, C, chi_lim, cut);
+    else
+#endif
+      truncation_rule<CHI>(s, C, chi_lim, cut);
     Knew = s.iscr[0];
     if (st.trace != nullptr && st.n_traced < st.P.trace_max) {
       double* tr = st.trace + (size_t)st.n_traced * st.P.trace_stride;
@@ -284,8 +325,14 @@ struct Engine {
       MD_SYNC();
       return 1;
     }
+    MD_PAR_FOR(k, Knew) s.tau[k] = 1.0 / s.sig[s.order[k]];   // for U = X[:, order] / sigma (store_u)
     // coefficients M'[k, c] = (1/sigma_k) sum_i X[i, order[k]] orig[i, c]   (= sigma_k v_k^T)
-    {
+    if (s.iscr[9]) {
+      // no rotation happened: X == orig with orthogonal columns, so M' = diag(sigma) in the sorted order (the
+      // off-diagonal dot products are below the check's threshold).  It is not materialised: step() reads
+      // s.sig / s.order directly (layout 3).
+      MD_LEADER { s.iscr[7] = 3; }
+    } else {
       constexpr int TK = 8;
       const int nkt = (Knew + TK - 1) / TK;
       MD_PAR_FOR(t, nkt * C) {
@@ -314,7 +361,7 @@ struct Engine {
   // ---- site j <- U (R = st.K*2 rows, Knew columns), frame layout (k, r, k') ----
   MD_DEV double u_at(int lay, int row, int kn, int Knew) const {
     if (lay == 2) return s.P2[row * Knew + (kn ^ q_swizzle(row, Knew))];
-    if (lay == 1) return s.X[row * LD + s.order[kn]] / s.sig[s.order[kn]];
+    if (lay == 1 || lay == 3) return s.X[row * LD + s.order[kn]] * s.tau[kn];   // s.tau[kn] = 1 / sigma_kn
     return s.X[row * LD + kn];
   }
   MD_DEV void store_u(int j, int Kl, int Knew) {
@@ -347,7 +394,7 @@ struct Engine {
     if (!iso) {
       // theta = Mmat . T formed explicitly (contractor.py:328-342), R x (2*vr*Bn)
       if (2 * vr * Bn > N2) { st.status = ST_CAPACITY; return; }
-      load_x(st.scr0, R, C);
+      if (!st.in_x) load_x(st.scr0, R, C);
       stage_site(jn, s.P2, st.Mr, Bn);
       apply_site(s.X, LD, R, vl, vr, st.Mr, Bn, s.P2, st.scr1);
       C = 2 * vr * Bn;
@@ -356,9 +403,11 @@ struct Engine {
     int Knew = factor(orig, R, C, chi_lim, cut, is_move);
     if (st.status == ST_CAPACITY) return;
     const int lay = s.iscr[7];
-    double* coef = (lay == 2) ? s.X : s.P2;                 // coefficients M' (Knew x C, ld LD)
-    double* stage = (lay == 2) ? (s.X + CHI * LD) : s.X;    // staging area for the next site tensor
-    if (renorm_sv) {  // mps_mpo_contract(renormalise=True): s /= ||s|| (utils.py:126-129); ||s|| = ||M'||_F
+    double* coef = (lay == 2) ? s.X : s.P2;                 // coefficients M' (Knew x C, ld LD); layout 3: diagonal
+    double* stage = (lay == 2) ? (s.X + CHI * LD) : ((lay == 3) ? s.P2 : s.X);  // staging area for the next site
+    // layout 3 (orthogonal fast path): M' = diag(sigma) is not materialised; ||s|| comes from the truncation rule
+    const double dscale = (lay == 3 && renorm_sv && s.dscr[3] > 0.0) ? 1.0 / s.dscr[3] : 1.0;
+    if (renorm_sv && lay != 3) {  // mps_mpo_contract(renormalise=True): s /= ||s|| (utils.py:126-129); ||s|| = ||M'||_F
       MD_PAR_FOR(ch, 256) {
         double acc = 0.0;
         for (int t = ch; t < Knew * C; t += 256) { int k = t / C, c = t - k * C; double v = coef[k * LD + c]; acc += v * v; }
@@ -381,11 +430,19 @@ struct Engine {
       stage_site(jn, stage, st.Mr, Bn);
       MD_LEADER { s.cnt.cyc_io += (double)(MD_CLOCK() - ts); }
       long long ta = MD_CLOCK();
-      apply_site(coef, LD, Knew, vl, vr, st.Mr, Bn, stage, st.scr0);
+      if (lay == 3) apply_site_diag(dscale, Knew, vl, vr, st.Mr, Bn, stage);   // result stays in s.X (st.in_x)
+      else {
+        apply_site(coef, LD, Knew, vl, vr, st.Mr, Bn, stage, st.scr0);
+        MD_LEADER { st.in_x = 0; }
+      }
       MD_LEADER { s.cnt.cyc_apply += (double)(MD_CLOCK() - ta); }
     } else {
-      MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; st.scr0[t] = coef[k * LD + c]; }
-      MD_LEADER { s.cnt.bytes_hbm += 8.0 * Knew * C; }
+      if (lay == 3) {
+        MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; st.scr0[t] = (c == s.order[k]) ? dscale * s.sig[c] : 0.0; }
+      } else {
+        MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; st.scr0[t] = coef[k * LD + c]; }
+      }
+      MD_LEADER { s.cnt.bytes_hbm += 8.0 * Knew * C; st.in_x = 0; }
       MD_SYNC();
     }
     MD_LEADER { st.K = Knew; st.Wq = vr; st.Mr = Bn; s.cnt.n_steps += 1.0; set_dim_right(jn - 1, Knew); }
@@ -396,10 +453,13 @@ struct Engine {
   MD_DEV void carried_to_site(int j, int renorm) {
     const int n = st.K * 2 * st.Mr;
     double scale = 1.0;
+    // the carried matrix is flat in scr0, or (orthogonal fast path) in s.X with leading dimension LD
+    const int inx = st.in_x, Bc = st.Mr;
+    auto cv = [&](int t) -> double { return inx ? s.X[(t / Bc) * LD + (t % Bc)] : st.scr0[t]; };
     if (renorm) {
       MD_PAR_FOR(ch, 256) {
         double acc = 0.0;
-        for (int t = ch; t < n; t += 256) { double v = st.scr0[t]; acc += v * v; }
+        for (int t = ch; t < n; t += 256) { double v = cv(t); acc += v * v; }
         s.part[ch] = acc;
       }
       MD_SYNC();
@@ -414,14 +474,15 @@ struct Engine {
     }
     double* dst = st.sites + (size_t)phys(j) * SITE_STRIDE;
     const int A = st.K, B = st.Mr;
-    if (!st.mirrored) { MD_PAR_FOR(g, n) dst[g] = st.scr0[g] * scale; }
+    if (!st.mirrored) { MD_PAR_FOR(g, n) dst[g] = cv(g) * scale; }
     else {
       MD_PAR_FOR(g, n) {  // phys dims (B, 2, A)
         int a = g % A; int r = g / A; int p = r & 1; int b = r >> 1;
-        dst[g] = st.scr0[(a * 2 + p) * B + b] * scale;
+        dst[g] = cv((a * 2 + p) * B + b) * scale;
       }
     }
-    MD_LEADER { s.cnt.bytes_hbm += 16.0 * n; }
+    MD_SYNC();
+    MD_LEADER { s.cnt.bytes_hbm += 16.0 * n; st.in_x = 0; }
     MD_SYNC();
   }
 

@@ -85,6 +85,16 @@ def css_code_logicals_sites(code):
     return schedule.code_site_lists(code)[1]
 
 
+def _resolve_mode(mode: str, depolarising: bool, cut: float) -> str:
+    """"auto" -> the SVD mode for the bit-flip bias (Schmidt-basis fast path) or a cut that discards singular
+    values, the QR mode otherwise; an explicit "fast" with such a cut is also run as "svd"."""
+    if mode == "auto":
+        mode = "fast" if (depolarising and cut <= 1e-14) else "svd"
+    if mode == "fast" and cut > 1e-14:
+        mode = "svd"
+    return mode
+
+
 def _effective_chi(chi_max, n_sites: int) -> int:
     """chi_max clipped to the largest Schmidt rank an n_sites-qubit chain can have (2^floor(N/2)): a larger
     chi_max never truncates, so short chains may keep the reference's default chi_max=1e4."""
@@ -111,15 +121,20 @@ def _program_for(code, has_x, has_z, renormalise, strategy, orders, bias_type="B
 def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: float = float(1e-17),
                      bias_type: str = "Depolarising", bias_prob: float = float(0.1), renormalise: bool = True,
                      silent: bool = True, contraction_strategy: str = "Naive", tolerance: float = float(1e-12),
-                     orders: Optional[dict] = None, mode: str = "fast", return_status: bool = False,
+                     orders: Optional[dict] = None, mode: str = "auto", return_status: bool = False,
                      multiply_by_stabiliser: bool = False, rng=None):
     """Decode many independent syndromes on the current GPU.
 
     Returns ``(dist float64[B, 2^k], success int32[B])`` (plus ``status int32[B]`` if asked); row b equals
     what ``decode_css(code, errors[b], ...)`` returns.  All-identity errors take the reference's early exit
-    (``[1, 0, 0, 0], 1``, decoding.py:1225-1228).  ``mode="fast"`` (default) replaces non-truncating SVDs by
-    rank-revealing QR steps; it needs ``cut <= 1e-14`` (a larger cut changes which singular values are
-    kept, so those runs use ``mode="svd"`` automatically).
+    (``[1, 0, 0, 0], 1``, decoding.py:1225-1228).
+
+    ``mode``: ``"svd"`` runs the reference algorithm split by split (SVD with ``k = min(chi_max, #(s > cut))``); with
+    the bit-flip bias every bond stays in its Schmidt basis under the XOR / SWAP constraint tensors, so almost every
+    split finds its columns already orthogonal (checked on the GPU) and needs no rotation -- this is the fastest path
+    there.  ``"fast"`` replaces non-truncating splits by rank-revealing QR steps (needs ``cut <= 1e-14``; better when
+    the bias mixes the basis, i.e. "Depolarising").  ``"auto"`` (default) picks ``"svd"`` for the bit-flip bias or a
+    non-negligible ``cut`` and ``"fast"`` otherwise.  ``"svd-gram"`` is ``"svd"`` with the deterministic Gram check only.
     """
     from mdopt_b200 import engine
 
@@ -129,8 +144,7 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
     k = code.num_x_logicals() + code.num_z_logicals()
     n = len(code)
     n_sites = 2 * n + k
-    if mode == "fast" and cut > 1e-14:
-        mode = "svd"
+    mode = _resolve_mode(mode, depol, cut)
     errors = list(errors)
     B = len(errors)
     if B == 0:
@@ -175,7 +189,7 @@ def decode_css(code, error: str, num_runs: int = int(1), chi_max: int = int(1e4)
                bias_type: str = "Depolarising", bias_prob: float = float(0.1), renormalise: bool = True,
                multiply_by_stabiliser: bool = False, silent: bool = False, contraction_strategy: str = "Naive",
                optimiser: str = "Dephasing DMRG", tolerance: float = float(1e-12), orders: Optional[dict] = None,
-               mode: str = "fast", rng=None):
+               mode: str = "auto", rng=None):
     """Error-based decoding of a CSS code by MPS marginalisation (reference decoding.py:1164-1404).
 
     Returns ``(|marginal| over the 2^k logical classes, success)`` with index 0 = I, 1 = X, 2 = Z, 3 = Y for
@@ -205,7 +219,7 @@ def decode_custom_batch(stabilizers: Sequence[str], x_logicals: Sequence[str], z
                         errors: Sequence[str], chi_max: int = int(1e4), cut: float = float(1e-17),
                         bias_type: str = "Depolarising", bias_prob: float = float(0.1), renormalise: bool = True,
                         silent: bool = True, contraction_strategy: str = "Naive", tolerance: float = float(1e-12),
-                        orders: Optional[dict] = None, mode: str = "fast", return_status: bool = False,
+                        orders: Optional[dict] = None, mode: str = "auto", return_status: bool = False,
                         multiply_by_stabiliser: bool = False, rng=None):
     """Batched ``decode_custom`` (reference decoding.py:1407-1628): a code given by stabiliser / logical Pauli
     strings; every constraint group is always applied, success uses the relative tolerance 1e-12 (:1600-1604)."""
@@ -219,8 +233,7 @@ def decode_custom_batch(stabilizers: Sequence[str], x_logicals: Sequence[str], z
     n_sites = 2 * n + k
     if not 1 <= k <= 12:
         raise NotImplementedError("the dense read-out supports 1..12 logical sites")
-    if mode == "fast" and cut > 1e-14:
-        mode = "svd"
+    mode = _resolve_mode(mode, depol, cut)
     errors = list(errors)
     B = len(errors)
     dist = np.zeros((B, 1 << k))
@@ -260,7 +273,7 @@ def decode_custom(stabilizers: List[str], x_logicals: List[str], z_logicals: Lis
                   bias_type: str = "Depolarising", bias_prob: float = float(0.1), renormalise: bool = True,
                   multiply_by_stabiliser: bool = False, silent: bool = False, contraction_strategy: str = "Naive",
                   optimiser: str = "Dephasing DMRG", tolerance: float = float(1e-12), orders: Optional[dict] = None,
-                  mode: str = "fast", rng=None):
+                  mode: str = "auto", rng=None):
     """Error-based decoding of a code given by Pauli strings (reference decoding.py:1407-1628)."""
     if not silent:
         logging.info("Starting the decoding.")

@@ -12,13 +12,13 @@ import numpy as np
 
 from mdopt_b200 import _abi, _lib, schedule
 
-_MODES = {"fast": schedule.MODE_FAST, "svd": schedule.MODE_SVD}
+_MODES = {"fast": schedule.MODE_FAST, "svd": schedule.MODE_SVD, "svd-gram": schedule.MODE_SVD_GRAM}
 
 
 def mode_id(mode) -> int:
     if isinstance(mode, str):
         if mode not in _MODES:
-            raise ValueError(f"mode must be 'fast' or 'svd', given {mode!r}")
+            raise ValueError(f"mode must be 'fast', 'svd' or 'svd-gram', given {mode!r}")
         return _MODES[mode]
     return int(mode)
 
