@@ -1006,22 +1006,32 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       return 1.0 + (double)(h & 0xFFFFFu) * (1.0 / 1048576.0);   // in [1, 2)
     };
     double* z0 = s.vn1;       // probe vectors (C entries)
-    double* z1 = s.part;
+    double* z1 = s.sig;
     double* y0 = s.wv;        // X z0   (R entries)
     double* y1 = s.tau;       // X z1
     for (int c = tid; c < C; c += blockDim.x) { z0[c] = zval(c, 0x9E3779B9u); z1[c] = zval(c, 0x7F4A7C15u); }
     __syncthreads();
-    // pass 1: y = X z, four lanes per row (every lane runs the loop: 4*N2 == blockDim.x)
-    double ny0 = 0.0, ny1 = 0.0;
-    for (int r4 = tid; r4 < 4 * N2; r4 += blockDim.x) {
-      const int r = r4 >> 2, q = r4 & 3;
+    // Thread t works on index t % N2 (a row in pass 1, a column in pass 2) and on the quarter t / N2 of the
+    // other dimension; consecutive lanes touch consecutive rows / columns, which is conflict-free with the odd
+    // leading dimension.  The four partial sums meet in shared memory (s.part viewed as [3][4][N2]).
+    const int idx = tid % N2, grp = tid / N2;      // blockDim.x == 4 * N2 for every capacity with CHI >= 8
+    double* pr = s.part;
+    // pass 1: y = X z
+    {
       double a0s = 0.0, a1s = 0.0;
-      if (r < R) {
-        for (int c = q; c < C; c += 4) { const double x = X[r * LD + c]; a0s += x * z0[c]; a1s += x * z1[c]; }
+      if (idx < R) {
+#pragma unroll 4
+        for (int c = grp; c < C; c += 4) { const double x = X[idx * LD + c]; a0s += x * z0[c]; a1s += x * z1[c]; }
       }
-      a0s += __shfl_xor_sync(0xffffffffu, a0s, 1); a1s += __shfl_xor_sync(0xffffffffu, a1s, 1);
-      a0s += __shfl_xor_sync(0xffffffffu, a0s, 2); a1s += __shfl_xor_sync(0xffffffffu, a1s, 2);
-      if (q == 0 && r < R) { y0[r] = a0s; y1[r] = a1s; ny0 += a0s * a0s; ny1 += a1s * a1s; }
+      pr[(0 * 4 + grp) * N2 + idx] = a0s;
+      pr[(1 * 4 + grp) * N2 + idx] = a1s;
+    }
+    __syncthreads();
+    double ny0 = 0.0, ny1 = 0.0;
+    if (grp == 0 && idx < R) {
+      const double a0s = (pr[idx] + pr[N2 + idx]) + (pr[2 * N2 + idx] + pr[3 * N2 + idx]);
+      const double a1s = (pr[4 * N2 + idx] + pr[5 * N2 + idx]) + (pr[6 * N2 + idx] + pr[7 * N2 + idx]);
+      y0[idx] = a0s; y1[idx] = a1s; ny0 = a0s * a0s; ny1 = a1s * a1s;
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
@@ -1032,24 +1042,28 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     __syncthreads();
     ny0 = 0.0; ny1 = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ny0 += s.rot[w]; ny1 += s.rot[16 + w]; }
+    // pass 2: w = X^T y and the squared column norms
+    {
+      double w0 = 0.0, w1 = 0.0, d = 0.0;
+      if (idx < C) {
+#pragma unroll 4
+        for (int r = grp; r < R; r += 4) { const double x = X[r * LD + idx]; w0 += x * y0[r]; w1 += x * y1[r]; d += x * x; }
+      }
+      pr[(0 * 4 + grp) * N2 + idx] = w0;
+      pr[(1 * 4 + grp) * N2 + idx] = w1;
+      pr[(2 * 4 + grp) * N2 + idx] = d;
+    }
     __syncthreads();
-    // pass 2: w = X^T y and the squared column norms, four lanes per column (rows interleaved)
     int bad = 0;
     double mxd = 0.0;
-    for (int c4 = tid; c4 < 4 * N2; c4 += blockDim.x) {
-      const int c = c4 >> 2, q = c4 & 3;
-      double w0 = 0.0, w1 = 0.0, d = 0.0;
-      if (c < C) {
-        for (int r = q; r < R; r += 4) { const double x = X[r * LD + c]; w0 += x * y0[r]; w1 += x * y1[r]; d += x * x; }
-      }
-      w0 += __shfl_xor_sync(0xffffffffu, w0, 1); w1 += __shfl_xor_sync(0xffffffffu, w1, 1); d += __shfl_xor_sync(0xffffffffu, d, 1);
-      w0 += __shfl_xor_sync(0xffffffffu, w0, 2); w1 += __shfl_xor_sync(0xffffffffu, w1, 2); d += __shfl_xor_sync(0xffffffffu, d, 2);
-      if (c < C) {
-        if (q == 0) s.vn2[c] = d;
-        mxd = fmax(mxd, d);
-        const double e0 = w0 - d * z0[c], e1 = w1 - d * z1[c];
-        if (e0 * e0 > 1e-24 * d * ny0 || e1 * e1 > 1e-24 * d * ny1) bad = 1;
-      }
+    if (grp == 0 && idx < C) {
+      const double w0 = (pr[idx] + pr[N2 + idx]) + (pr[2 * N2 + idx] + pr[3 * N2 + idx]);
+      const double w1 = (pr[4 * N2 + idx] + pr[5 * N2 + idx]) + (pr[6 * N2 + idx] + pr[7 * N2 + idx]);
+      const double d = (pr[8 * N2 + idx] + pr[9 * N2 + idx]) + (pr[10 * N2 + idx] + pr[11 * N2 + idx]);
+      s.vn2[idx] = d;
+      mxd = d;
+      const double e0 = w0 - d * z0[idx], e1 = w1 - d * z1[idx];
+      if (e0 * e0 > 1e-24 * d * ny0 || e1 * e1 > 1e-24 * d * ny1) bad = 1;
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) mxd = fmax(mxd, __shfl_xor_sync(0xffffffffu, mxd, off));
