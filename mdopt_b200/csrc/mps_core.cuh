@@ -203,14 +203,19 @@ struct Engine {
   //      the next split looks for it (st.in_x), so the carried matrix never leaves the SM on this path.
   MD_DEV void apply_site_diag(double scale, int rows, int vl, int vr, int mr, int Bn, const double* As) {
     const int Cn = vr * Bn;
-    MD_PAR_FOR(t, rows * 2 * Cn) {
-      int b = t % Bn; int r = t / Bn;
-      int wo = r % vr; r /= vr;
-      int pd = r & 1; int k = r >> 1;
+    // one 32-lane group per output row segment (k, p', w'): the index arithmetic is done once per segment and
+    // the lanes run along b (coalesced reads of the staged site, conflict-free writes of X)
+    MD_PAR_FOR(t, rows * 2 * vr * 32) {
+      const int l = t & 31; int r = t >> 5;
+      const int wo = r % vr; r /= vr;
+      const int pd = r & 1, k = r >> 1;
       const int c = s.order[k];
       const int q = c / mr, m = c - q * mr;
-      const double acc = w_at(vr, q, wo, 0, pd) * As[(m * 2 + 0) * Bn + b] + w_at(vr, q, wo, 1, pd) * As[(m * 2 + 1) * Bn + b];
-      s.X[(k * 2 + pd) * LD + wo * Bn + b] = scale * s.sig[c] * acc;
+      const double f0 = scale * s.sig[c] * w_at(vr, q, wo, 0, pd), f1 = scale * s.sig[c] * w_at(vr, q, wo, 1, pd);
+      const double* a0 = As + (m * 2 + 0) * Bn;
+      const double* a1 = As + (m * 2 + 1) * Bn;
+      double* dst = s.X + (k * 2 + pd) * LD + wo * Bn;
+      for (int b = l; b < Bn; b += 32) dst[b] = f0 * a0[b] + f1 * a1[b];
     }
     MD_LEADER { s.cnt.flops_apply += 4.0 * rows * 2 * Cn; st.in_x = 1; }
     MD_SYNC();
@@ -367,15 +372,16 @@ struct Engine {
   MD_DEV void store_u(int j, int Kl, int Knew) {
     double* dst = st.sites + (size_t)phys(j) * SITE_STRIDE;
     const int lay = s.iscr[7];
+    // 32-lane groups per output row, lanes along the fastest output index (no per-element divisions)
     if (!st.mirrored) {
-      MD_PAR_FOR(g, Kl * 2 * Knew) {
-        int kn = g % Knew, row = g / Knew;
-        dst[g] = u_at(lay, row, kn, Knew);
+      MD_PAR_FOR(t, Kl * 2 * 32) {
+        const int l = t & 31, row = t >> 5;
+        for (int kn = l; kn < Knew; kn += 32) dst[(size_t)row * Knew + kn] = u_at(lay, row, kn, Knew);
       }
     } else {  // phys tensor dims (Knew, 2, Kl)
-      MD_PAR_FOR(g, Kl * 2 * Knew) {
-        int k = g % Kl; int r = g / Kl; int p = r & 1; int kn = r >> 1;
-        dst[g] = u_at(lay, k * 2 + p, kn, Knew);
+      MD_PAR_FOR(t, Knew * 2 * 32) {
+        const int l = t & 31; const int r = t >> 5; const int p = r & 1, kn = r >> 1;
+        for (int k = l; k < Kl; k += 32) dst[(size_t)r * Kl + k] = u_at(lay, k * 2 + p, kn, Knew);
       }
     }
     MD_LEADER { s.cnt.bytes_hbm += 8.0 * Kl * 2 * Knew; }
