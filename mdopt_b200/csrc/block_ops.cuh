@@ -61,6 +61,19 @@ struct Counters {
 #define MD_CLOCK() clock64()
 #endif
 
+// 8-byte asynchronous global -> shared copy (cp.async, completes in the background; md_async_wait() before the
+// data is read or the destination reused).  The host build copies synchronously.
+#ifdef MDOPT_EMU
+inline void md_async_copy8(double* dst_shared, const double* src_global) { *dst_shared = *src_global; }
+inline void md_async_wait() {}
+#else
+__device__ __forceinline__ void md_async_copy8(double* dst_shared, const double* src_global) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src_global) : "memory");
+}
+__device__ __forceinline__ void md_async_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+#endif
+
 struct DecodeParams {
   int n_sites;        // MPS length N
   int n_logical;      // number of logical sites kL (they are sites 0..kL-1)

@@ -108,6 +108,25 @@ struct Engine {
     MD_SYNC();
   }
 
+  // ---- the same copy issued asynchronously (cp.async) so that it overlaps the factorisation; pair with
+  //      stage_wait() before the destination is read or reused ----
+  MD_DEV void stage_site_async(int j, double* dst, int A, int B) {
+    const double* src = st.sites + (size_t)phys(j) * SITE_STRIDE;
+    if (!st.mirrored) { MD_PAR_FOR(g, A * 2 * B) md_async_copy8(dst + g, src + g); }
+    else {
+      const int na = (A + 3) / 4, nbt = (B + 7) / 8;
+      MD_PAR_FOR(g, na * nbt * 2 * 32) {
+        const int l = g & 31; int t = g >> 5;
+        const int p = t & 1; t >>= 1;
+        const int ta = t % na, tb = t / na;
+        const int a = 4 * ta + (l & 3), b = 8 * tb + (l >> 2);
+        if (a < A && b < B) md_async_copy8(dst + (a * 2 + p) * B + b, src + ((size_t)b * 2 + p) * A + a);
+      }
+    }
+    MD_LEADER { s.cnt.bytes_hbm += 8.0 * A * 2 * B; }
+  }
+  MD_DEV void stage_wait() { md_async_wait(); MD_SYNC(); }
+
   // ---- out[((row*2+p')*vr + w')*Bn + m'] = sum_{q,p,m} Min[row, q*st.Mr+m] W(q,w',p,p') As[(m*2+p)*Bn + m'] ----
   MD_DEV void apply_site(const double* Min, int ld, int rows, int vl, int vr, int mr, int Bn,
                          const double* As, double* out) {
@@ -306,6 +325,7 @@ struct Engine {
     }
     MD_LEADER { s.cnt.cyc_jacobi += (double)(MD_CLOCK() - tj); }
     long long tc = MD_CLOCK();
+    if (s.iscr[10]) stage_wait();   // the prefetched site tensor has landed in s.P2 (see step())
     if (s.iscr[5]) st.status = ST_NOT_CONVERGED;
 #ifndef MDOPT_EMU
     if constexpr (REG_PATH) truncation_rule_dev<CHI>(s, C, chi_lim, cut);
@@ -406,8 +426,13 @@ struct Engine {
       C = 2 * vr * Bn;
       orig = st.scr1;
     }
+    // SVD modes on the shared-memory capacities: the next site tensor is fetched into s.P2 while the split runs
+    // (the orthogonal fast path does not touch P2); factor() waits for it before anything else writes P2
+    const int pre = REG_PATH && iso && st.P.mode != MODE_FAST;
+    if (pre) stage_site_async(jn, s.P2, st.Mr, Bn);
+    MD_LEADER { s.iscr[10] = pre; }
     int Knew = factor(orig, R, C, chi_lim, cut, is_move);
-    if (st.status == ST_CAPACITY) return;
+    if (st.status == ST_CAPACITY) { if (pre) stage_wait(); return; }
     const int lay = s.iscr[7];
     double* coef = (lay == 2) ? s.X : s.P2;                 // coefficients M' (Knew x C, ld LD); layout 3: diagonal
     double* stage = (lay == 2) ? (s.X + CHI * LD) : ((lay == 3) ? s.P2 : s.X);  // staging area for the next site
@@ -433,7 +458,7 @@ struct Engine {
     long long ts = MD_CLOCK();
     store_u(jn - 1, st.K, Knew);
     if (iso) {
-      stage_site(jn, stage, st.Mr, Bn);
+      if (!(pre && lay == 3)) stage_site(jn, stage, st.Mr, Bn);   // layout 3: already in s.P2 (prefetched)
       MD_LEADER { s.cnt.cyc_io += (double)(MD_CLOCK() - ts); }
       long long ta = MD_CLOCK();
       if (lay == 3) apply_site_diag(dscale, Knew, vl, vr, st.Mr, Bn, stage);   // result stays in s.X (st.in_x)
