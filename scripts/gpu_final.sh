@@ -2,6 +2,8 @@ set -x
 timeout 400 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 timeout 500 python bench.py > gpurun_out/r01_bench.json 2> gpurun_out/r01_bench.err
 tail -c 600 gpurun_out/r01_bench.json
+timeout 300 python bench.py --mode fast --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r01_bench_fast.json 2> gpurun_out/r01_bench_fast.err
+timeout 300 python bench.py --mode svd-gram --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r01_bench_gram.json 2> gpurun_out/r01_bench_gram.err
 timeout 200 python bench.py --steps 1 --warmup 1 --batch 168 --no-cpu-baseline > gpurun_out/prof_plain.log 2>&1 &&
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:decode_kernel -s 1 -c 1 -o gpurun_out/r01_decode_kernel_final python bench.py --steps 1 --warmup 1 --batch 168 --no-cpu-baseline > gpurun_out/prof_ncu.log 2>&1
 timeout 200 python bench.py --steps 2 --warmup 1 --batch 296 --no-cpu-baseline > gpurun_out/launch_plain.log 2>&1 &&
