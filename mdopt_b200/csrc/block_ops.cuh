@@ -142,7 +142,7 @@ struct Smem : MatStore<CHI, (CHI <= SMEM_CHI_MAX)> {
   static constexpr int NPART = (NCH * N2 * 3 / 2 > 256) ? NCH * N2 * 3 / 2 : 256;
   double part[NPART];
   double vn1[N2], vn2[N2], tau[N2], sig[N2], wv[N2];
-  double rot[N2 * 2];
+  alignas(16) double rot[N2 * 2];
   double W[16];         // current MPO site tensor (vL, vR, pU, pD), vL,vR <= 2
   double dscr[16];
   static constexpr int NFLAG = (N2 > 32) ? N2 : 32;
@@ -1054,7 +1054,12 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     if (lane == 0) { s.rot[warp] = ny0; s.rot[16 + warp] = ny1; }
     __syncthreads();
     ny0 = 0.0; ny1 = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ny0 += s.rot[w]; ny1 += s.rot[16 + w]; }
+    {  // 16-byte loads of the per-warp partials (blockDim.x / 32 is even for every capacity)
+      const double2* r2 = reinterpret_cast<const double2*>(s.rot);
+      const int nw2 = ((int)(blockDim.x >> 5) + 1) >> 1;
+#pragma unroll 4
+      for (int w = 0; w < nw2; ++w) { const double2 a = r2[w], b = r2[8 + w]; ny0 += a.x + a.y; ny1 += b.x + b.y; }
+    }
     // pass 2: w = X^T y and the squared column norms
     {
       double w0 = 0.0, w1 = 0.0, d = 0.0;
@@ -1084,7 +1089,10 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     const int any_bad = __syncthreads_or(bad);
     {
       double mx = 0.0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, s.rot[w]);
+      const double2* r2 = reinterpret_cast<const double2*>(s.rot);
+      const int nw2 = ((int)(blockDim.x >> 5) + 1) >> 1;
+#pragma unroll 4
+      for (int w = 0; w < nw2; ++w) { const double2 a = r2[w]; mx = fmax(mx, fmax(a.x, a.y)); }
       floor2 = mx * (4.0 * EPS) * (4.0 * EPS);
       if (tid == 0) s.dscr[6] = floor2;
     }

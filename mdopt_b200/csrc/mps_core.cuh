@@ -226,10 +226,11 @@ struct Engine {
     // the lanes run along b (coalesced reads of the staged site, conflict-free writes of X)
     MD_PAR_FOR(t, rows * 2 * vr * 32) {
       const int l = t & 31; int r = t >> 5;
-      const int wo = r % vr; r /= vr;
+      // vl, vr <= 2: no integer divisions
+      const int wo = (vr == 2) ? (r & 1) : 0; r = (vr == 2) ? (r >> 1) : r;
       const int pd = r & 1, k = r >> 1;
       const int c = s.order[k];
-      const int q = c / mr, m = c - q * mr;
+      const int q = (c >= mr) ? 1 : 0, m = c - q * mr;
       const double f0 = scale * s.sig[c] * w_at(vr, q, wo, 0, pd), f1 = scale * s.sig[c] * w_at(vr, q, wo, 1, pd);
       const double* a0 = As + (m * 2 + 0) * Bn;
       const double* a1 = As + (m * 2 + 1) * Bn;
