@@ -334,14 +334,16 @@ struct Engine {
 #endif
       truncation_rule<CHI>(s, C, chi_lim, cut);
     Knew = s.iscr[0];
-    if (st.trace != nullptr && st.n_traced < st.P.trace_max) {
-      double* tr = st.trace + (size_t)st.n_traced * st.P.trace_stride;
-      MD_LEADER { tr[0] = R; tr[1] = C; tr[2] = Knew; tr[3] = is_move; }
-      MD_PAR_FOR(c, N2) { if (4 + c < st.P.trace_stride) tr[4 + c] = (c < C) ? s.sig[s.order[c]] : 0.0; }
+    if (st.trace != nullptr) {   // uniform: the trace buffer is per launch
+      if (st.n_traced < st.P.trace_max) {
+        double* tr = st.trace + (size_t)st.n_traced * st.P.trace_stride;
+        MD_LEADER { tr[0] = R; tr[1] = C; tr[2] = Knew; tr[3] = is_move; }
+        MD_PAR_FOR(c, N2) { if (4 + c < st.P.trace_stride) tr[4 + c] = (c < C) ? s.sig[s.order[c]] : 0.0; }
+      }
+      MD_SYNC();
+      MD_LEADER { st.n_traced += 1; }
+      MD_SYNC();
     }
-    MD_SYNC();
-    MD_LEADER { st.n_traced += 1; }
-    MD_SYNC();
     if (Knew > CHI) { st.status = ST_CAPACITY; MD_SYNC(); return 0; }  // would overflow the site stride
     if (Knew == 0) {
       MD_SYNC();
