@@ -91,6 +91,7 @@ struct DecodeParams {
   unsigned kept_mask; // read-out: which of them are kept (the others are traced out)
   double readout_rel; // tolerant arg-max: eps = max(readout_rel * max v, readout_abs)
   double readout_abs;
+  int n_tensors;      // entries of the MPO tensor table (<= TABLE_SMEM of them are cached in shared memory)
 };
 
 // Persistent per-CTA engine state (shared memory; see Engine in mps_core.cuh).
@@ -148,6 +149,12 @@ struct Smem : MatStore<CHI, (CHI <= SMEM_CHI_MAX)> {
   static constexpr int NFLAG = (N2 > 32) ? N2 : 32;
   int perm[N2], order[N2], flag[NFLAG];
   int iscr[16];
+  // per-launch constants cached next to the engine: MPO tensor table (when it has <= TABLE_SMEM entries) and the
+  // bond dimensions of the chain (when it has < BOND_SMEM sites); both are read several times per step
+  static constexpr int TABLE_SMEM = 16, BOND_SMEM = 1024;
+  double wt_s[TABLE_SMEM * 16];
+  int wd_s[TABLE_SMEM * 4];
+  int bd_s[BOND_SMEM];
   Counters cnt;   // leader-only work counters of this CTA
   EngineState st;
 };

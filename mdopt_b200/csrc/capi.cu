@@ -87,7 +87,7 @@ int mdopt_decode_batch_device(const mdopt_decode_desc* desc, int chi_cap, int n_
   if (desc->n_logical < 1 || desc->n_logical > 12 || desc->n_sites <= desc->n_logical) return MDOPT_E_BADARG;
   const ChiOps* ops = ops_for(chi_cap);
   if (!ops || desc->chi_max < 1 || desc->chi_max > chi_cap) return MDOPT_E_CAPACITY;
-  return ops->decode(desc, n_ctas, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters,
+  return ops->decode(desc, n_ctas, program, wtab, wdim, n_tensors, symbols, batch, dist, success, status, trace, counters,
                      workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -135,7 +135,7 @@ int mdopt_mps_program_device(const mdopt_decode_desc* desc, int chi_cap, const i
   if (desc->n_logical < 1 || desc->n_logical > 12) return MDOPT_E_BADARG;
   const ChiOps* ops = ops_for(chi_cap);
   if (!ops) return MDOPT_E_CAPACITY;
-  return ops->mps_program(desc, program, wtab, wdim, batch, sites_io, bonds_io, centre_io, dist, success, status,
+  return ops->mps_program(desc, program, wtab, wdim, n_tensors, batch, sites_io, bonds_io, centre_io, dist, success, status,
                           trace, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -45,11 +45,16 @@ decode_kernel(DecodeParams P, const int* __restrict__ prog, const double* __rest
     st.scr1 = st.scr0 + (size_t)(2 * CHI) * (2 * CHI);
     double* mats = st.scr1 + (size_t)(2 * CHI) * (2 * CHI);
     s.bind_mats(mats);
-    st.bd = reinterpret_cast<int*>(mats + mat_store_doubles(CHI));
-    st.wtab = wtab;
-    st.wdim = wdim;
+    st.bd = (P.n_sites + 1 <= Smem<CHI>::BOND_SMEM) ? s.bd_s : reinterpret_cast<int*>(mats + mat_store_doubles(CHI));
+    const bool cache = P.n_tensors > 0 && P.n_tensors <= Smem<CHI>::TABLE_SMEM;
+    st.wtab = cache ? s.wt_s : wtab;
+    st.wdim = cache ? s.wd_s : wdim;
     st.P = P;
     s.cnt = Counters{};
+  }
+  if (P.n_tensors > 0 && P.n_tensors <= Smem<CHI>::TABLE_SMEM) {
+    for (int i = threadIdx.x; i < P.n_tensors * 16; i += blockDim.x) s.wt_s[i] = wtab[i];
+    for (int i = threadIdx.x; i < P.n_tensors * 4; i += blockDim.x) s.wd_s[i] = wdim[i];
   }
   __syncthreads();
   const int ncls = 1 << P.n_logical;
@@ -110,7 +115,7 @@ mps_program_kernel(DecodeParams P, const int* __restrict__ prog, const double* _
     if (threadIdx.x == 0) {
       EngineState& st = s.st;
       st.sites = sites_io + (size_t)b * P.n_sites * Engine<CHI>::SITE_STRIDE;
-      st.bd = bonds_io + (size_t)b * (P.n_sites + 1);
+      st.bd = (P.n_sites + 1 <= Smem<CHI>::BOND_SMEM) ? s.bd_s : bonds_io + (size_t)b * (P.n_sites + 1);
       st.scr0 = ws + (size_t)blockIdx.x * (2 * (size_t)(2 * CHI) * (2 * CHI) + mat_store_doubles(CHI));
       st.scr1 = st.scr0 + (size_t)(2 * CHI) * (2 * CHI);
       s.bind_mats(st.scr1 + (size_t)(2 * CHI) * (2 * CHI));
@@ -119,9 +124,14 @@ mps_program_kernel(DecodeParams P, const int* __restrict__ prog, const double* _
       st.centre = centre_io[b]; st.mirrored = 0; st.status = ST_OK; st.n_traced = 0;
       st.trace = trace ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
     }
+    const bool bd_cached = (P.n_sites + 1 <= Smem<CHI>::BOND_SMEM);
+    if (bd_cached)
+      for (int i = threadIdx.x; i <= P.n_sites; i += blockDim.x) s.bd_s[i] = bonds_io[(size_t)b * (P.n_sites + 1) + i];
     __syncthreads();
     E.run_ops(prog, dist ? dist + (size_t)b * ncls : nullptr, success ? success + b : nullptr);
     __syncthreads();
+    if (bd_cached)
+      for (int i = threadIdx.x; i <= P.n_sites; i += blockDim.x) bonds_io[(size_t)b * (P.n_sites + 1) + i] = s.bd_s[i];
     if (threadIdx.x == 0) { status[b] = s.st.status; centre_io[b] = s.st.centre; }
     __syncthreads();
   }
@@ -218,7 +228,7 @@ int num_ctas_impl() {
 
 template <int CHI>
 int launch_decode(const mdopt_decode_desc* d, int n_ctas, const int32_t* program, const double* wtab,
-                  const int32_t* wdim, const uint8_t* symbols, int batch, double* dist, int32_t* success,
+                  const int32_t* wdim, int n_tensors, const uint8_t* symbols, int batch, double* dist, int32_t* success,
                   int32_t* status, double* trace, double* counters, void* workspace, size_t workspace_bytes,
                   cudaStream_t st) {
   {  // the dense read-out pages hold 2^(k-1) x chi (k <= 6, one-sided) or 2^ceil(k/2) x chi (meeting in the middle)
@@ -239,6 +249,7 @@ int launch_decode(const mdopt_decode_desc* d, int n_ctas, const int32_t* program
   P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
   P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
   P.readout_rel = d->readout_rel; P.readout_abs = d->readout_abs;
+  P.n_tensors = n_tensors;
   // the work counter lives in the last 256 bytes of the workspace
   int* work_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + per * (size_t)n_ctas);
   e = cudaMemsetAsync(work_counter, 0, 256, st);
@@ -293,7 +304,7 @@ int launch_site_apply(int sms, int batch, int rows, int vl, int vr, int mr, int 
 
 template <int C_>
 int launch_mps_program(const mdopt_decode_desc* d, const int32_t* program, const double* wtab, const int32_t* wdim,
-                       int batch, double* sites_io, int32_t* bonds_io, int32_t* centre_io, double* dist,
+                       int n_tensors, int batch, double* sites_io, int32_t* bonds_io, int32_t* centre_io, double* dist,
                        int32_t* success, int32_t* status, double* trace, void* workspace, size_t workspace_bytes,
                        cudaStream_t st) {
   const size_t per = (2 * (size_t)(2 * C_) * (2 * C_) + mat_store_doubles(C_)) * sizeof(double);
@@ -308,6 +319,7 @@ int launch_mps_program(const mdopt_decode_desc* d, const int32_t* program, const
   P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
   P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
   P.readout_rel = d->readout_rel; P.readout_abs = d->readout_abs;
+  P.n_tensors = n_tensors;
   mps_program_kernel<C_><<<batch, Cfg<C_>::NT, sizeof(Smem<C_>), st>>>(
       P, program, wtab, wdim, batch, sites_io, bonds_io, centre_io, dist, success, status,
       d->trace_stride > 0 ? trace : nullptr, reinterpret_cast<double*>(workspace));

@@ -13,7 +13,7 @@ struct ChiOps {
   int (*num_ctas)();
   size_t (*ws_doubles_per_cta)(int n_sites);
   int (*decode)(const mdopt_decode_desc* d, int n_ctas, const int32_t* program, const double* wtab,
-                const int32_t* wdim, const uint8_t* symbols, int batch, double* dist, int32_t* success,
+                const int32_t* wdim, int n_tensors, const uint8_t* symbols, int batch, double* dist, int32_t* success,
                 int32_t* status, double* trace, double* counters, void* workspace, size_t workspace_bytes,
                 cudaStream_t st);
   int (*svd)(int sms, int batch, int m, int n, const double* a, int chi_max, double cut, int renormalise, double* u,
@@ -21,7 +21,7 @@ struct ChiOps {
   int (*site_apply)(int sms, int batch, int rows, int vl, int vr, int mr, int bn, const double* m_in,
                     const double* a_site, const double* w, double* theta, cudaStream_t st);
   int (*mps_program)(const mdopt_decode_desc* d, const int32_t* program, const double* wtab, const int32_t* wdim,
-                     int batch, double* sites_io, int32_t* bonds_io, int32_t* centre_io, double* dist,
+                     int n_tensors, int batch, double* sites_io, int32_t* bonds_io, int32_t* centre_io, double* dist,
                      int32_t* success, int32_t* status, double* trace, void* workspace, size_t workspace_bytes,
                      cudaStream_t st);
 };

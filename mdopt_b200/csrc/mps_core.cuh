@@ -524,8 +524,11 @@ struct Engine {
   MD_DEV void sweep(int start, int len, const int* tids, int chi_lim, double cut, int renorm_after,
                     int is_move, int renorm_sv) {
     carried_from_site(start, tids ? tids[0] : -1);
+    int next_tid = (tids && len > 1) ? tids[1] : -1;   // the program lives in global memory: fetch one step ahead
     for (int t = 1; t < len; ++t) {
-      step(start + t, tids ? tids[t] : -1, chi_lim, cut, is_move, renorm_sv);
+      const int cur = next_tid;
+      if (tids && t + 1 < len) next_tid = tids[t + 1];
+      step(start + t, cur, chi_lim, cut, is_move, renorm_sv);
       if (st.status == ST_CAPACITY) return;
     }
     if (st.Wq != 1) { st.status = ST_CAPACITY; return; }

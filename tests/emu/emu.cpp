@@ -38,6 +38,7 @@ int decode_impl(const mdopt_decode_desc* d, const int32_t* program, const double
   P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
   P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
   P.readout_rel = d->readout_rel; P.readout_abs = d->readout_abs;
+  P.n_tensors = 0;
   E.st.P = P;
   sm->cnt = Counters{};
   const int ncls = 1 << d->n_logical;
@@ -119,6 +120,7 @@ int program_impl(const mdopt_decode_desc* d, const int32_t* program, const doubl
   P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
   P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
   P.readout_rel = d->readout_rel; P.readout_abs = d->readout_abs;
+  P.n_tensors = 0;
   E.st.P = P;
   sm->cnt = Counters{};
   E.st.centre = *centre_io; E.st.mirrored = 0; E.st.status = ST_OK; E.st.n_traced = 0;
