@@ -28,8 +28,8 @@ LATTICE, CHI_MAX, ERROR_RATE, BIAS, CUT, SEED = 5, 64, 0.05, 0.1, 1e-17, 123
 WORKLOAD = f"surface_d{LATTICE}_bitflip_p{ERROR_RATE}_bias{BIAS}_chi{CHI_MAX}_cut{CUT}_optimised"
 REF_FLOP_PER_NONTRIVIAL = 47.98e9 + 1.70e9  # LAPACK-count of the reference's call sequence
 # dram__bytes_read.sum + dram__bytes_write.sum of decode_kernel<64> from the `ncu --set full` capture summarised
-# in profiles/r01_decode_kernel_ncu_summary.md: 12.16 GB for a launch of 143 non-trivial syndromes (default mode)
-DRAM_BYTES_PER_NONTRIVIAL = 12.16e9 / 143
+# in profiles/r01_decode_kernel_ncu_summary.md: 12.23 GB for a launch of 143 non-trivial syndromes (default mode)
+DRAM_BYTES_PER_NONTRIVIAL = 12.23e9 / 143
 
 
 def seeded_errors(n_qubits, rate, count, seed, offset=0):
