@@ -190,14 +190,41 @@ def test_cluster_default_cut(api):
         np.testing.assert_allclose(dist[b], np.asarray(ref, float), rtol=1e-10, atol=1e-13)
 
 
+def test_svd_mode_falls_back_to_rotations(api):
+    """The depolarising bias mixes the bond bases, so in SVD mode the orthogonality checks fail on many splits
+    (and pass on others): this walks the probe -> Gram -> Jacobi fallback, including the hand-over of a carried
+    matrix that the fast path left in shared memory.  Exact against the oracle wherever it does not truncate."""
+    code, ocode = api["surface_code"](3), O.surface_code(3)
+    errors = [e for e in O.seeded_errors(13, 0.08, 40, 57, "Depolarising") if set(e) != {"I"}][:10]
+    kw = dict(chi_max=64, cut=1e-17, bias_type="Depolarising", bias_prob=0.1, contraction_strategy="Optimised",
+              tolerance=1e-12)
+    exact = 0
+    results = {}
+    for mode in ("svd", "svd-gram", "fast"):
+        dist, success, status = api["decode_css_batch"](code, errors, return_status=True, mode=mode, **kw)
+        assert (status == 0).all()
+        results[mode] = dist
+        for b, e in enumerate(errors):
+            if not O.decode_truncates(ocode, e, **kw):
+                ref, ok = O.decode_css(ocode, e, **kw)
+                exact += 1
+                assert int(success[b]) == ok, (mode, e)
+                np.testing.assert_allclose(dist[b], np.asarray(ref, float), rtol=1e-10, atol=1e-14)
+    assert exact >= 3
+
+
 def test_fast_and_svd_modes_agree(api):
     code = api["surface_code"](3)
     errors = O.seeded_errors(13, 0.15, 64, 99, "Bitflip")
     kw = dict(chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, contraction_strategy="Optimised")
     d0, s0 = api["decode_css_batch"](code, errors, mode="fast", **kw)
     d1, s1 = api["decode_css_batch"](code, errors, mode="svd", **kw)
-    assert (s0 == s1).all()
+    d2, s2 = api["decode_css_batch"](code, errors, mode="svd-gram", **kw)
+    d3, s3 = api["decode_css_batch"](code, errors, **kw)   # "auto" = "svd" for the bit-flip bias
+    assert (s0 == s1).all() and (s1 == s2).all() and (s1 == s3).all()
     np.testing.assert_allclose(d0, d1, rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(d2, d1, rtol=1e-10, atol=1e-14)
+    np.testing.assert_array_equal(d3, d1)
 
 
 def test_matches_oracle_on_fresh_seeds_and_strategies(api):
