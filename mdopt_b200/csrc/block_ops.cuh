@@ -520,6 +520,100 @@ MD_DEV void jacobi_columns(Smem<CHI>& s, int R, int C, int max_sweeps = 60) {
   MD_SYNC();
 }
 
+// -------------------------------------------------------------------------------------------------
+// Orthogonality probe, portable version (host emulation and the large-chi tier; the shared-memory capacities use
+// the fused copy inside jacobi_columns_dev).  Freivalds test with two fixed pseudo-random vectors z:
+// X^T (X z) = diag(|x_c|^2) z holds for every z exactly when the columns of X are mutually orthogonal.
+// Returns 1 when every component agrees to 1e-12 |x_c| |X z|; then s.sig = column norms, s.order = their ranking
+// (descending, ties by column index), s.dscr[6] = the zero-column floor, and X is untouched.
+// -------------------------------------------------------------------------------------------------
+MD_HD double probe_z(int c, unsigned salt) {
+  unsigned h = (unsigned)c * 2654435761u + salt;
+  h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+  return 1.0 + (double)(h & 0xFFFFFu) * (1.0 / 1048576.0);   // in [1, 2)
+}
+
+template <int CHI>
+MD_DEV int ortho_probe(Smem<CHI>& s, int R, int C) {
+  constexpr int LD = Smem<CHI>::LD;
+  constexpr int N2 = Smem<CHI>::N2;
+  const double* X = s.X;
+  double* z0 = s.vn1;
+  double* z1 = s.sig;
+  double* y0 = s.wv;
+  double* y1 = s.tau;
+  double* pr = s.part;   // [3][4][N2] partial sums
+  MD_PAR_FOR(c, C) { z0[c] = probe_z(c, 0x9E3779B9u); z1[c] = probe_z(c, 0x7F4A7C15u); }
+  MD_SYNC();
+  // pass 1: y = X z; task t = (row t % N2, quarter t / N2 of the columns)
+  MD_PAR_FOR(t, 4 * N2) {
+    const int idx = t % N2, grp = t / N2;
+    double a0 = 0.0, a1 = 0.0;
+    if (idx < R) {
+      for (int c = grp; c < C; c += 4) { const double x = X[idx * LD + c]; a0 += x * z0[c]; a1 += x * z1[c]; }
+    }
+    pr[(0 * 4 + grp) * N2 + idx] = a0;
+    pr[(1 * 4 + grp) * N2 + idx] = a1;
+  }
+  MD_SYNC();
+  MD_PAR_FOR(r, R) {
+    y0[r] = (pr[r] + pr[N2 + r]) + (pr[2 * N2 + r] + pr[3 * N2 + r]);
+    y1[r] = (pr[4 * N2 + r] + pr[5 * N2 + r]) + (pr[6 * N2 + r] + pr[7 * N2 + r]);
+  }
+  MD_SYNC();
+  MD_LEADER {
+    double n0 = 0.0, n1 = 0.0;
+    for (int r = 0; r < R; ++r) { n0 += y0[r] * y0[r]; n1 += y1[r] * y1[r]; }
+    s.dscr[8] = n0; s.dscr[9] = n1;
+  }
+  // pass 2: w = X^T y and the squared column norms; task t = (column t % N2, quarter t / N2 of the rows)
+  MD_PAR_FOR(t, 4 * N2) {
+    const int idx = t % N2, grp = t / N2;
+    double w0 = 0.0, w1 = 0.0, d = 0.0;
+    if (idx < C) {
+      for (int r = grp; r < R; r += 4) { const double x = X[r * LD + idx]; w0 += x * y0[r]; w1 += x * y1[r]; d += x * x; }
+    }
+    pr[(0 * 4 + grp) * N2 + idx] = w0;
+    pr[(1 * 4 + grp) * N2 + idx] = w1;
+    pr[(2 * 4 + grp) * N2 + idx] = d;
+  }
+  MD_SYNC();
+  const double ny0 = s.dscr[8], ny1 = s.dscr[9];
+  MD_PAR_FOR(c, C) {
+    const double w0 = (pr[c] + pr[N2 + c]) + (pr[2 * N2 + c] + pr[3 * N2 + c]);
+    const double w1 = (pr[4 * N2 + c] + pr[5 * N2 + c]) + (pr[6 * N2 + c] + pr[7 * N2 + c]);
+    const double d = (pr[8 * N2 + c] + pr[9 * N2 + c]) + (pr[10 * N2 + c] + pr[11 * N2 + c]);
+    const double e0 = w0 - d * z0[c], e1 = w1 - d * z1[c];
+    s.vn2[c] = d;
+    s.flag[c] = (e0 * e0 > 1e-24 * d * ny0 || e1 * e1 > 1e-24 * d * ny1) ? 1 : 0;
+  }
+  MD_SYNC();
+  MD_LEADER {
+    int bad = 0;
+    double mx = 0.0;
+    for (int c = 0; c < C; ++c) { bad |= s.flag[c]; mx = fmax(mx, s.vn2[c]); }
+    s.iscr[11] = bad ? 0 : 1;
+    s.dscr[6] = mx * (4.0 * EPS) * (4.0 * EPS);
+    s.cnt.flops_jacobi += 10.0 * R * C;
+  }
+  MD_SYNC();
+  if (!s.iscr[11]) return 0;
+  MD_PAR_FOR(c, C) s.sig[c] = sqrt(s.vn2[c]);   // overwrites z1, which is no longer needed
+  MD_SYNC();
+  MD_PAR_FOR(c, C) {
+    const double v = s.sig[c];
+    int pos = 0;
+    for (int o = 0; o < C; ++o) {
+      const double w = s.sig[o];
+      pos += (w > v) || (w == v && o < c);
+    }
+    s.order[pos] = c;
+  }
+  MD_LEADER { s.iscr[4] = 0; s.iscr[5] = 0; }
+  MD_SYNC();
+  return 1;
+}
+
 // Reference truncation rule (mdopt/utils/utils.py:119): keep min(chi_max, #(sigma > cut)) values.
 // Requires s.sig / s.order from jacobi_columns.  Result in s.iscr[0]; s.dscr[2] = truncation error
 // sum_{i>=k} sigma_i^2, s.dscr[3] = ||sigma_kept||_2.

@@ -321,8 +321,18 @@ struct Engine {
     else
 #endif
     {
-      MD_LEADER { s.iscr[9] = 0; }
-      jacobi_columns<CHI>(s, R, C);
+      // portable path (host emulation, large-chi tier): the same probe, then the sweeps if it fails
+      int ortho = 0;
+      if (st.P.mode != MODE_FAST && C >= 2) ortho = ortho_probe<CHI>(s, R, C);
+      MD_LEADER { s.iscr[9] = ortho; }
+      if (!ortho) {
+        if (x_loaded) {  // the rotations are about to change X: refresh the flat copy the coefficient product reads
+          MD_PAR_FOR(t, R * C) { int r = t / C, c = t - r * C; st.scr0[t] = s.X[r * LD + c]; }
+          MD_SYNC();
+        }
+        jacobi_columns<CHI>(s, R, C);
+      }
+      MD_SYNC();
     }
     MD_LEADER { s.cnt.cyc_jacobi += (double)(MD_CLOCK() - tj); }
     long long tc = MD_CLOCK();
