@@ -271,18 +271,30 @@ def readout_kept_mask(error: str, n_logical: int) -> int:
 def symbols_from_errors(errors: Sequence[str], n_logical: int) -> np.ndarray:
     """uint8 [B, k + 2n] product-state symbols: '+' on the logical sites, then the Pauli bits."""
     n = len(errors[0])
-    out = np.full((len(errors), n_logical + 2 * n), SYM_PLUS, dtype=np.uint8)
+    B = len(errors)
+    out = np.full((B, n_logical + 2 * n), SYM_PLUS, dtype=np.uint8)
     lut = np.zeros((256, 2), dtype=np.uint8)
     valid = np.zeros(256, dtype=bool)
     for ch, bits in _PAULI_BITS.items():
         lut[ord(ch)] = bits
         valid[ord(ch)] = True
+    for err in errors:
+        if len(err) != n:
+            raise ValueError(f"The error length is {2 * len(err)}, expected {2 * n}.")
+    try:  # one buffer for the whole batch (the per-string path below reports the offending character)
+        raw = np.frombuffer("".join(errors).encode("ascii"), dtype=np.uint8).reshape(B, n)
+    except (UnicodeEncodeError, ValueError):
+        raw = None
+    if raw is not None and valid[raw].all():
+        out[:, n_logical:] = lut[raw].reshape(B, 2 * n)
+        return out
     for b, err in enumerate(errors):
-        raw = np.frombuffer(err.encode("ascii"), dtype=np.uint8)
-        if raw.size != n:
-            raise ValueError(f"The error length is {2 * raw.size}, expected {2 * n}.")
-        if not valid[raw].all():
-            bad = err[int(np.argmin(valid[raw]))]
+        try:
+            row = np.frombuffer(err.encode("ascii"), dtype=np.uint8)
+        except UnicodeEncodeError:
+            raise ValueError(f"Invalid Pauli encountered -- {err}.") from None
+        if not valid[row].all():
+            bad = err[int(np.argmin(valid[row]))]
             raise ValueError(f"Invalid Pauli encountered -- {bad}.")
-        out[b, n_logical:] = lut[raw].reshape(-1)
+        out[b, n_logical:] = lut[row].reshape(-1)
     return out
