@@ -15,9 +15,14 @@
 // afterwards.  For non-isometric W (XOR_RIGHT at the end of every string) theta is formed explicitly.
 // Orth-centre moves are the same step with an identity MPO, run in a mirrored frame when moving left.
 //
-// Two factorisation modes:
-//   MODE_SVD   every split is a one-sided Jacobi SVD with the reference's truncation rule
-//              k = min(chi_max, #(s > cut)) (utils.py:119); moves use cut = 1e-12 (canonical.py:399-405).
+// Factorisation modes:
+//   MODE_SVD   every split is an SVD with the reference's truncation rule k = min(chi_max, #(s > cut))
+//              (utils.py:119); moves use cut = 1e-12 (canonical.py:399-405).  Before any rotation the split checks
+//              whether its columns are already mutually orthogonal (probe check, then Gram check): then the SVD is
+//              X = (X / sigma) sigma with sigma the column norms, the coefficient matrix is diagonal and the next
+//              carried matrix a scaled gather of the next site tensor (layout 3, st.in_x).  With the bit-flip bias
+//              this holds for every split of a decode; otherwise one-sided Jacobi sweeps run.
+//   MODE_SVD_GRAM  the same with the deterministic Gram check only.
 //   MODE_FAST  rank-revealing Householder QR with column pivoting; only when more than chi_max
 //              columns carry weight above rank_tol * ||.|| does the step fall back to the Jacobi SVD.
 //              Non-truncating steps only re-gauge the bond, which leaves the state unchanged.
