@@ -536,7 +536,7 @@ struct Engine {
   }
 
   // ---- sweep of an MPO over frame st.sites start..start+len-1 (tids == nullptr: identity MPO = move) ----
-  MD_DEV void sweep(int start, int len, const int* tids, int chi_lim, double cut, int renorm_after,
+  MD_PHASE void sweep(int start, int len, const int* tids, int chi_lim, double cut, int renorm_after,
                     int is_move, int renorm_sv) {
     carried_from_site(start, tids ? tids[0] : -1);
     int next_tid = (tids && len > 1) ? tids[1] : -1;   // the program lives in global memory: fetch one step ahead
@@ -573,7 +573,7 @@ struct Engine {
   // ---- two-site gate on (site, site+1) with the centre at `site`, then split (depolarising bias:
   //      decoding.py:254-274 -- theta = "ijk,klm,jlno->inom", split with chi=1e4 / cut=1e-12, spectrum and
   //      centre renormalised).  The gate sits in the tensor table as 16 doubles G[j][l][n][o]. ----
-  MD_DEV void gate2(int site, int gid, int renorm) {
+  MD_PHASE void gate2(int site, int gid, int renorm) {
     const int L = st.bd[site], M = st.bd[site + 1], Rr = st.bd[site + 2];
     const int R = 2 * L, C = 2 * Rr;
     if (R > N2 || C > N2 || M > CHI) { st.status = ST_CAPACITY; return; }
@@ -627,7 +627,7 @@ struct Engine {
   }
 
   // ---- product state + bit-flip bias (mps/utils.py:439-512, decoding.py:140-190) ----
-  MD_DEV void init_product(const uint8_t* sym) {
+  MD_PHASE void init_product(const uint8_t* sym) {
     const int N = st.P.n_sites;
     const double d = (st.P.bias_p >= 0.0) ? sqrt(1.0 - st.P.bias_p) : 1.0;
     const double o = (st.P.bias_p >= 0.0) ? sqrt(st.P.bias_p) : 0.0;
@@ -653,7 +653,7 @@ struct Engine {
 
   // ---- marginal over st.sites kL..N-1, reverse, dense, |.|, L2 renorm, tolerant arg-max ----
   //   canonical.py:956-989, :150-161, :241-272; decoding.py:1362-1379
-  MD_DEV void marginal_readout(double* out, int* success) {
+  MD_PHASE void marginal_readout(double* out, int* success) {
     // kL = number of leading sites handled by the dense stage; those with their bit in kept_mask set are kept
     // (n_logical of them), the others are traced out like the tail (erasures of qubits < n_logical only)
     const int N = st.P.n_sites, kL = st.P.n_head, ren = st.P.renormalise;
