@@ -1,0 +1,615 @@
+// Monomial ("trellis") MPS engine: one WARP decodes one syndrome, every site tensor in sparse form.
+//
+// Same path as mps_core.cuh (mdopt/contractor/contractor.py:177-378 mps_mpo_contract, mdopt/mps/canonical.py:345-420
+// move_orth_centre, mdopt/optimiser/utils.py:284-345, canonical.py:906-991 marginal + :241-272 dense,
+// examples/decoding/decoding.py:1362-1379 read-out), same program, same formulation (factor the
+// carried matrix, one-site centre moves, the reference's truncation rule k = min(chi_max, #(s > cut))) -- specialised to
+// the structure a decode with product-state inputs and 0/1 constraint tensors has and *verifies* at every step:
+//
+//   every site tensor A[a, p, b] is p-MONOMIAL: for fixed p, each row a has at most one non-zero b and each column b
+//   at most one non-zero a (a partial permutation with weights).
+//
+// Reason: the bond basis never leaves the trellis states of the parity constraints.  For such tensors the carried
+// matrix X (rows (k, p), columns (w', b)) has ONE non-zero per row, so its columns have disjoint supports: they are
+// exactly orthogonal, the SVD is X = (X / sigma) diag(sigma) with sigma the column norms, no rotation is ever needed,
+// and U is again p-monomial.  A site tensor is 2*chi (value, target) pairs instead of 2*chi^2 doubles, a two-site
+// step is O(chi) work plus one sort of <= 2*chi column norms, and a whole step fits one warp.  The structure is
+// checked, not assumed: a row that would need two different targets, or two rows of equal p meeting in one column,
+// ends the syndrome with MDOPT_ST_NOT_MONOMIAL and the caller re-runs it on the dense engine (decode_kernel).
+//
+// Ordering of the new bond (the tie-break that makes truncating decodes well-posed; oracle/structured_svd.py states the
+// same rule for the reference's SVD hook): sigma descending, values within 1e-10 relative (chained) form one cluster,
+// inside a cluster the column whose first supporting row comes first goes first.
+//
+// The source compiles for the host with -DMDOPT_EMU (lane loops become plain loops) so the CPU test tier runs the
+// same index logic; the product is the CUDA build only.
+#pragma once
+#include "block_ops.cuh"
+
+#ifdef MDOPT_EMU
+#include <algorithm>
+#include <string.h>
+#define MW_FOR(i, n) for (int i = 0; i < (n); ++i)
+#define MW_SYNC() ((void)0)
+#define MW_ANY(x) (x)
+#define MW_LANE0 if (true)
+#else
+#define MW_FOR(i, n) for (int i = (int)(threadIdx.x & 31u); i < (n); i += 32)
+#define MW_SYNC() __syncwarp()
+#define MW_ANY(x) __any_sync(0xffffffffu, (x))
+#define MW_LANE0 if ((threadIdx.x & 31u) == 0)
+#endif
+
+namespace mdopt {
+
+enum { ST_NOT_MONOMIAL = 4 };
+enum { MODE_MONO = 3 };
+constexpr double MONO_TIE_REL2 = 2e-10;   // cluster width on sigma^2 (= 1e-10 relative on sigma)
+constexpr int MONO_ROW_BITS = 10;         // low key bits that carry the first supporting row (2*chi <= 1024)
+constexpr unsigned long long MONO_ROW_MASK = (1ull << MONO_ROW_BITS) - 1ull;
+
+// One site tensor in HBM: rows r = a*2 + p -> (target b or -1, value).  Only the first 2*dim_left rows are live.
+template <int CHI>
+struct MonoSite {
+  double val[2 * CHI];
+  int16_t tgt[2 * CHI];
+};
+
+// Per-warp shared memory.
+template <int CHI>
+struct MonoSmem {
+  static constexpr int N2 = 2 * CHI;
+  // carried matrix, row-singleton form: row r = (k, p') has its only entry cv[r] in column cc[r] (-1: empty row)
+  double cv[N2];
+  // per column: squared entry of the row with p = 0 / p = 1 that hits it; reused as 64-bit sort keys
+  double acc[2][N2];
+  double sig[N2];        // sigma per column
+  double sv[N2];         // staged next site, frame view: rows (m, p) -> (st, sv)
+  double uv[N2];         // outgoing U record (values), also the marginal chain's vector
+  int16_t cc[N2];
+  int16_t own[2][N2];    // k of the row with p = 0 / 1 that hits the column, -1 none
+  int16_t rank[N2];      // new bond index of a column, -1 dropped
+  int16_t order[N2];     // column at sorted position
+  int16_t st[N2];
+  int16_t ut[N2];
+  double W[16];          // current MPO tensor (vL, vR, pU, pD)
+  double red[4];
+};
+
+struct MonoCounters {
+  double bytes_hbm, n_steps, n_trunc, n_fallback;
+};
+
+#ifndef MDOPT_EMU
+__device__ __forceinline__ double mw_sum(double v) {
+#pragma unroll
+  for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+__device__ __forceinline__ double mw_max(double v) {
+#pragma unroll
+  for (int off = 16; off; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+__device__ __forceinline__ int mw_isum(int v) { return __reduce_add_sync(0xffffffffu, v); }
+#else
+inline double mw_sum(double v) { return v; }
+inline double mw_max(double v) { return v; }
+inline int mw_isum(int v) { return v; }
+#endif
+
+// -------------------------------------------------------------------------------------------------
+// Sort n 64-bit keys (shared memory, n <= NMAX = 32*EPL) in DESCENDING order, in place.
+// Device: bitonic network, EPL keys per lane in registers (element e = lane*EPL + j, so the two smallest strides
+// stay inside a lane and the others are one 64-bit shuffle each).  Host: std::sort.  Keys are unique or zero.
+// -------------------------------------------------------------------------------------------------
+#ifndef MDOPT_EMU
+template <int EPL>
+__device__ __forceinline__ void mw_sort_desc_impl(unsigned long long* keys, int n) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long k[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) { const int e = lane * EPL + j; k[j] = (e < n) ? keys[e] : 0ull; }
+  constexpr int N = 32 * EPL;
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride < EPL) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+          if ((j & stride) == 0) {
+            const int e = lane * EPL + j;
+            const bool desc = ((e & size) == 0);   // descending blocks first -> whole array descending at size == N
+            const unsigned long long a = k[j], b = k[j | stride];
+            const bool sw = desc ? (a < b) : (a > b);
+            k[j] = sw ? b : a; k[j | stride] = sw ? a : b;
+          }
+        }
+      } else {
+        const int lm = stride / EPL;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+          const int e = lane * EPL + j;
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[j], lm);
+          const bool lower = ((lane & lm) == 0);
+          const bool desc = ((e & size) == 0);
+          // the lower element of the pair keeps the larger key in a descending block
+          const bool take_max = (lower == desc);
+          k[j] = take_max ? (k[j] > o ? k[j] : o) : (k[j] < o ? k[j] : o);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) { const int e = lane * EPL + j; if (e < n) keys[e] = k[j]; }
+  __syncwarp();
+}
+template <int NMAX>
+__device__ __forceinline__ void mw_sort_desc(unsigned long long* keys, int n) {
+  __syncwarp();
+  if constexpr (NMAX >= 1024) { if (n > 512) { mw_sort_desc_impl<32>(keys, n); return; } }
+  if constexpr (NMAX >= 512) { if (n > 256) { mw_sort_desc_impl<16>(keys, n); return; } }
+  if constexpr (NMAX >= 256) { if (n > 128) { mw_sort_desc_impl<8>(keys, n); return; } }
+  if constexpr (NMAX >= 128) { if (n > 64) { mw_sort_desc_impl<4>(keys, n); return; } }
+  if constexpr (NMAX >= 64) { if (n > 32) { mw_sort_desc_impl<2>(keys, n); return; } }
+  mw_sort_desc_impl<1>(keys, n);
+}
+#else
+template <int NMAX>
+inline void mw_sort_desc(unsigned long long* keys, int n) {
+  std::sort(keys, keys + n, [](unsigned long long a, unsigned long long b) { return a > b; });
+}
+#endif
+
+// -------------------------------------------------------------------------------------------------
+// The per-warp engine.  Scalars are warp-uniform and live in registers.
+// -------------------------------------------------------------------------------------------------
+template <int CHI>
+struct MonoEngine {
+  static constexpr int N2 = 2 * CHI;
+  MonoSmem<CHI>& s;
+  MonoSite<CHI>* sites;     // [n_sites] this warp's MPS (global)
+  int* bd;                  // [n_sites + 1] bond dimensions (global)
+  const double* wtab;
+  const int* wdim;
+  double* trace;
+  DecodeParams P;
+  MonoCounters cnt;
+  int n_traced, status, centre, K, Wq, Mr, mirrored;
+
+  MD_DEV MonoEngine(MonoSmem<CHI>& sm) : s(sm) {}
+
+  MD_DEV int phys(int j) const { return mirrored ? (P.n_sites - 1 - j) : j; }
+  MD_DEV int dim_left(int j) const { int p = phys(j); return mirrored ? bd[p + 1] : bd[p]; }
+  MD_DEV int dim_right(int j) const { int p = phys(j); return mirrored ? bd[p] : bd[p + 1]; }
+  MD_DEV void set_dim_right(int j, int v) { int p = phys(j); MW_LANE0 { if (mirrored) bd[p] = v; else bd[p + 1] = v; } MW_SYNC(); }
+
+  MD_DEV void load_w(int tid) {
+    MW_FOR(i, 16) { s.W[i] = (tid < 0) ? ((i == 0 || i == 3) ? 1.0 : 0.0) : wtab[tid * 16 + i]; }
+    MW_SYNC();
+  }
+  MD_DEV int w_vl(int tid) const { return tid < 0 ? 1 : wdim[tid * 4 + 0]; }
+  MD_DEV int w_vr(int tid) const { return tid < 0 ? 1 : wdim[tid * 4 + 1]; }
+  MD_DEV int w_iso(int tid) const { return tid < 0 ? 1 : wdim[tid * 4 + 2]; }
+  MD_DEV double w_at(int vr, int q, int wo, int pu, int pd) const { return s.W[((q * vr + wo) * 2 + pu) * 2 + pd]; }
+
+  // ---- stage site j in the frame view: rows (a, p) -> (s.st, s.sv), a < dim_left(j) ----
+  MD_DEV void load_site(int j) {
+    const MonoSite<CHI>& src = sites[phys(j)];
+    const int A = dim_left(j), B = dim_right(j);
+    if (!mirrored) {
+      MW_FOR(r, 2 * A) { s.sv[r] = src.val[r]; s.st[r] = src.tgt[r]; }
+    } else {
+      // the stored tensor has dims (B, 2, A): rows (b, p) -> a.  Invert per p (unique writers: p-monomial).
+      MW_FOR(r, 2 * A) { s.st[r] = -1; s.sv[r] = 0.0; }
+      MW_SYNC();
+      MW_FOR(r, 2 * B) {
+        const int t = src.tgt[r];
+        if (t >= 0) { const int o = t * 2 + (r & 1); s.st[o] = (int16_t)(r >> 1); s.sv[o] = src.val[r]; }
+      }
+    }
+    cnt.bytes_hbm += 10.0 * 2 * (mirrored ? B : A);
+    MW_SYNC();
+  }
+
+  // ---- new carried row from entry (q, m) of the coefficient side, output physical index pd, factor f:
+  //      sum over (w', pu) of f * W(q, w', pu, pd) * A[m, pu, .] must live in a single column ----
+  MD_DEV bool gather_row(int vr, int Bn, int q, int m, int pd, double f, int* col_out, double* val_out) const {
+    int col = -1; double val = 0.0; bool ok = true;
+    for (int wo = 0; wo < vr; ++wo)
+      for (int pu = 0; pu < 2; ++pu) {
+        const double w = w_at(vr, q, wo, pu, pd);
+        if (w == 0.0) continue;
+        const int t = s.st[m * 2 + pu];
+        if (t < 0) continue;
+        const int c = wo * Bn + t;
+        if (col >= 0 && c != col) ok = false;
+        col = c;
+        val += (f * w) * s.sv[m * 2 + pu];
+      }
+    *col_out = col; *val_out = val;
+    return ok;
+  }
+
+  // ---- carried <- site j with the first MPO tensor applied (contractor.py:276-291, first half) ----
+  MD_DEV void carried_from_site(int j, int tid) {
+    load_w(tid);
+    const int A = dim_left(j), B = dim_right(j), vr = w_vr(tid);
+    load_site(j);
+    int bad = 0;
+    // rows (k, p') of the carried matrix; columns (q, m) = q*B + m
+    MW_FOR(r, 2 * A) {
+      int col; double val;
+      if (!gather_row(vr, B, 0, r >> 1, r & 1, 1.0, &col, &val)) bad = 1;
+      s.cv[r] = val; s.cc[r] = (int16_t)col;
+    }
+    if (MW_ANY(bad)) status = ST_NOT_MONOMIAL;
+    K = A; Wq = vr; Mr = B;
+    MW_SYNC();
+  }
+
+  // ---- one two-site step: absorb site jn (frame index) with MPO tensor tid ----
+  MD_DEV void step(int jn, int tid, int chi_lim, double cut, int is_move, int renorm_sv) {
+    const int vl = w_vl(tid), vr = w_vr(tid), iso = w_iso(tid);
+    const int Bn = dim_right(jn);
+    const int R = K * 2;
+    int C = Wq * Mr;
+    load_w(tid);
+    if (vl != Wq || dim_left(jn) != Mr) { status = ST_CAPACITY; return; }
+    load_site(jn);
+    int bad = 0;
+    if (!iso) {
+      // theta = Mmat . T formed explicitly (contractor.py:328-342): row (k, r) keeps one entry, now in column
+      // (p', w', m') = (p'*vr + w')*Bn + m'
+      if (2 * vr * Bn > N2) { status = ST_CAPACITY; return; }
+      MW_FOR(r, R) {
+        const int c = s.cc[r];
+        if (c < 0) continue;
+        const int q = c / Mr, m = c - q * Mr;
+        const double v = s.cv[r];
+        int col = -1; double val = 0.0;
+        for (int pd = 0; pd < 2; ++pd) {
+          int c1; double v1;
+          if (!gather_row(vr, Bn, q, m, pd, v, &c1, &v1)) bad = 1;
+          if (c1 < 0) continue;
+          c1 += pd * vr * Bn;
+          if (col >= 0 && c1 != col) bad = 1;
+          col = c1; val += v1;
+        }
+        s.cc[r] = (int16_t)col; s.cv[r] = val;
+      }
+      C = 2 * vr * Bn;
+      MW_SYNC();
+    }
+    // ---- column sums: at most one row per p may hit a column ----
+    MW_FOR(c, C) { s.acc[0][c] = 0.0; s.acc[1][c] = 0.0; s.own[0][c] = -1; s.own[1][c] = -1; }
+    MW_SYNC();
+    MW_FOR(r, R) {
+      const int c = s.cc[r];
+      if (c >= 0) { const double v = s.cv[r]; s.own[r & 1][c] = (int16_t)(r >> 1); s.acc[r & 1][c] = v * v; }
+    }
+    MW_SYNC();
+    MW_FOR(r, R) { const int c = s.cc[r]; if (c >= 0 && s.own[r & 1][c] != (r >> 1)) bad = 1; }
+    if (MW_ANY(bad)) { status = ST_NOT_MONOMIAL; return; }
+    // sigma^2, first supporting row, largest sigma^2; the sort keys go into acc[1] (viewed as 64-bit integers)
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(s.acc[1]);
+    double mx = 0.0;
+    MW_FOR(c, C) {
+      const double n2 = s.acc[0][c] + s.acc[1][c];
+      const int o0 = s.own[0][c], o1 = s.own[1][c];
+      const int first = (o0 >= 0 && (o1 < 0 || 2 * o0 < 2 * o1 + 1)) ? 2 * o0 : ((o1 >= 0) ? 2 * o1 + 1 : (int)MONO_ROW_MASK);
+      s.sig[c] = n2;          // squared for now
+      mx = fmax(mx, n2);
+      unsigned long long kb;
+#ifdef MDOPT_EMU
+      memcpy(&kb, &n2, 8);
+#else
+      kb = (unsigned long long)__double_as_longlong(n2);
+#endif
+      keys[c] = (n2 > 0.0) ? ((kb & ~MONO_ROW_MASK) | (MONO_ROW_MASK - (unsigned long long)first)) : 0ull;
+    }
+    mx = mw_max(mx);
+    const double floor2 = mx * (4.0 * EPS) * (4.0 * EPS);
+    MW_SYNC();
+    // truncation count (utils.py:119): #(sigma > cut) among the numerically non-zero columns
+    int cnt_keep = 0, cnt_nz = 0;
+    MW_FOR(c, C) {
+      const double n2 = s.sig[c];
+      const double v = sqrt(n2);
+      cnt_keep += (v > cut && n2 > floor2) ? 1 : 0;
+      cnt_nz += (n2 > 0.0) ? 1 : 0;
+    }
+    cnt_keep = mw_isum(cnt_keep);
+    const int nnz = mw_isum(cnt_nz);
+    int Knew = cnt_keep < chi_lim ? cnt_keep : chi_lim;
+    // ---- canonical order: sort by (sigma^2, first row), cluster, sort by (cluster, first row) ----
+    mw_sort_desc<N2>(keys, C);
+    // cluster starts: position p opens a cluster when its value drops below the previous one by more than the tie width
+    MW_FOR(p, nnz) {
+      int flag = 1;
+      if (p > 0) {
+        double a, b;
+        const unsigned long long ka = keys[p - 1] & ~MONO_ROW_MASK, kb = keys[p] & ~MONO_ROW_MASK;
+#ifdef MDOPT_EMU
+        memcpy(&a, &ka, 8); memcpy(&b, &kb, 8);
+#else
+        a = __longlong_as_double((long long)ka); b = __longlong_as_double((long long)kb);
+#endif
+        flag = (b < a * (1.0 - MONO_TIE_REL2)) ? 1 : 0;
+      }
+      s.rank[p] = (int16_t)flag;   // scratch: the ranks are written further down
+    }
+    MW_SYNC();
+    unsigned long long* keys2 = reinterpret_cast<unsigned long long*>(s.acc[0]);   // acc[0] is free: sigma^2 sits in s.sig
+    MW_FOR(p, nnz) {
+      int st0 = p;
+      while (!s.rank[st0]) --st0;
+      keys2[p] = ((unsigned long long)(N2 - st0) << MONO_ROW_BITS) | (keys[p] & MONO_ROW_MASK);
+    }
+    mw_sort_desc<N2>(keys2, nnz);
+    // order[pos] = column, rank[column] = pos (kept) or -1
+    MW_FOR(c, C) s.rank[c] = -1;
+    MW_SYNC();
+    double kept2 = 0.0, err2 = 0.0;
+    MW_FOR(p, nnz) {
+      const int first = (int)(MONO_ROW_MASK - (keys2[p] & MONO_ROW_MASK));
+      const int c = s.cc[first];
+      s.order[p] = (int16_t)c;
+      const double n2 = s.sig[c];
+      if (p < Knew) { s.rank[c] = (int16_t)p; kept2 += n2; } else err2 += n2;
+    }
+    kept2 = mw_sum(kept2); err2 = mw_sum(err2);
+    MW_SYNC();
+    MW_FOR(c, C) s.sig[c] = sqrt(s.sig[c]);
+    MW_SYNC();
+    if (trace != nullptr) {
+      if (n_traced < P.trace_max) {
+        double* tr = trace + (size_t)n_traced * P.trace_stride;
+        MW_LANE0 { tr[0] = R; tr[1] = C; tr[2] = Knew; tr[3] = is_move; }
+        MW_FOR(c, N2) { if (4 + c < P.trace_stride) tr[4 + c] = (c < nnz) ? s.sig[s.order[c]] : 0.0; }
+      }
+      n_traced += 1;
+    }
+    if (cnt_keep > chi_lim && err2 > 0.0) cnt.n_trunc += 1.0;
+    if (Knew > CHI) { status = ST_CAPACITY; return; }
+    const double dscale = (renorm_sv && kept2 > 0.0) ? 1.0 / sqrt(kept2) : 1.0;
+    const int zero = (Knew == 0);
+    if (zero) Knew = 1;   // zero matrix: keep a single zero direction (the state has zero norm)
+    // ---- site jn-1 <- U: row (k, p) -> (rank of its column, value / sigma) ----
+    {
+      MonoSite<CHI>& dst = sites[phys(jn - 1)];
+      if (!mirrored) {
+        MW_FOR(r, R) {
+          const int c = s.cc[r];
+          const int t = (c >= 0) ? s.rank[c] : -1;
+          double v = 0.0;
+          if (t >= 0) v = s.cv[r] * (1.0 / s.sig[c]);
+          int tt = t;
+          if (zero) { tt = (r == 0) ? 0 : -1; v = (r == 0) ? 1.0 : 0.0; }
+          dst.tgt[r] = (int16_t)tt; dst.val[r] = v;
+        }
+      } else {   // stored dims (Knew, 2, K): rows (kn, p) -> k
+        MW_FOR(r, 2 * Knew) { s.ut[r] = -1; s.uv[r] = 0.0; }
+        MW_SYNC();
+        MW_FOR(r, R) {
+          const int c = s.cc[r];
+          const int t = (c >= 0) ? s.rank[c] : -1;
+          if (t >= 0 && !zero) { const int o = t * 2 + (r & 1); s.ut[o] = (int16_t)(r >> 1); s.uv[o] = s.cv[r] * (1.0 / s.sig[c]); }
+        }
+        if (zero) { MW_LANE0 { s.ut[0] = 0; s.uv[0] = 1.0; } }
+        MW_SYNC();
+        MW_FOR(r, 2 * Knew) { dst.tgt[r] = s.ut[r]; dst.val[r] = s.uv[r]; }
+      }
+      cnt.bytes_hbm += 10.0 * 2 * (mirrored ? Knew : K);
+    }
+    MW_SYNC();
+    // ---- next carried matrix ----
+    bad = 0;
+    // (the old rows were last read by the U store above; the new ones depend on order / sig / the staged site only)
+    if (iso) {
+      MW_FOR(rn, 2 * Knew) {
+        int col = -1; double val = 0.0;
+        if (!zero) {
+          const int c = s.order[rn >> 1];
+          const int q = c / Mr, m = c - q * Mr;
+          if (!gather_row(vr, Bn, q, m, rn & 1, dscale * s.sig[c], &col, &val)) bad = 1;
+        }
+        s.cv[rn] = val; s.cc[rn] = (int16_t)col;
+      }
+    } else {
+      // coefficients diag(sigma) over columns (p', w', m'): carried(Knew, 2, vr, Bn), row (kn, p') -> (w', m')
+      MW_FOR(rn, 2 * Knew) {
+        int col = -1; double val = 0.0;
+        if (!zero) {
+          const int c = s.order[rn >> 1];
+          const int pd = c / (vr * Bn);
+          if (pd == (rn & 1)) { col = c - pd * vr * Bn; val = dscale * s.sig[c]; }
+        }
+        s.cv[rn] = val; s.cc[rn] = (int16_t)col;
+      }
+    }
+    MW_SYNC();
+    if (MW_ANY(bad)) { status = ST_NOT_MONOMIAL; return; }
+    set_dim_right(jn - 1, Knew);
+    K = Knew; Wq = vr; Mr = Bn;
+    cnt.n_steps += 1.0;
+    MW_SYNC();
+  }
+
+  // ---- carried (K, 2, 1, Mr) -> site j, optionally divided by its Frobenius norm (optimiser/utils.py:340-345) ----
+  MD_DEV void carried_to_site(int j, int renorm) {
+    const int n = K * 2;
+    double scale = 1.0;
+    if (renorm) {
+      double acc = 0.0;
+      MW_FOR(r, n) { if (s.cc[r] >= 0) { const double v = s.cv[r]; acc += v * v; } }
+      acc = mw_sum(acc);
+      const double nrm = sqrt(acc);
+      scale = (nrm > 0.0) ? 1.0 / nrm : 1.0;
+    }
+    MonoSite<CHI>& dst = sites[phys(j)];
+    if (!mirrored) {
+      MW_FOR(r, n) { const int c = s.cc[r]; dst.tgt[r] = (int16_t)c; dst.val[r] = (c >= 0) ? s.cv[r] * scale : 0.0; }
+    } else {   // stored dims (Mr, 2, K): rows (m, p) -> k
+      MW_FOR(r, 2 * Mr) { s.ut[r] = -1; s.uv[r] = 0.0; }
+      MW_SYNC();
+      MW_FOR(r, n) {
+        const int c = s.cc[r];
+        if (c >= 0) { const int o = c * 2 + (r & 1); s.ut[o] = (int16_t)(r >> 1); s.uv[o] = s.cv[r] * scale; }
+      }
+      MW_SYNC();
+      MW_FOR(r, 2 * Mr) { dst.tgt[r] = s.ut[r]; dst.val[r] = s.uv[r]; }
+    }
+    cnt.bytes_hbm += 10.0 * 2 * (mirrored ? Mr : K);
+    MW_SYNC();
+  }
+
+  MD_DEV void sweep(int start, int len, const int* tids, int chi_lim, double cut, int renorm_after, int is_move,
+                    int renorm_sv) {
+    carried_from_site(start, tids ? tids[0] : -1);
+    if (status == ST_NOT_MONOMIAL) return;
+    for (int t = 1; t < len; ++t) {
+      step(start + t, tids ? tids[t] : -1, chi_lim, cut, is_move, renorm_sv);
+      if (status == ST_CAPACITY || status == ST_NOT_MONOMIAL) return;
+    }
+    if (Wq != 1) { status = ST_CAPACITY; return; }
+    carried_to_site(start + len - 1, renorm_after);
+  }
+
+  MD_DEV void move_centre(int target) {
+    const int from = centre;
+    if (target == from) return;
+    if (target > from) {
+      mirrored = 0;
+      sweep(from, target - from + 1, nullptr, CHI, P.cut_move, 0, 1, 0);
+    } else {
+      mirrored = 1;
+      sweep(P.n_sites - 1 - from, from - target + 1, nullptr, CHI, P.cut_move, 0, 1, 0);
+      mirrored = 0;
+    }
+    centre = target;
+  }
+
+  // ---- product state + bit-flip bias (mps/utils.py:439-512, decoding.py:140-190) ----
+  MD_DEV void init_product(const uint8_t* sym) {
+    const int N = P.n_sites;
+    const double d = (P.bias_p >= 0.0) ? sqrt(1.0 - P.bias_p) : 1.0;
+    const double o = (P.bias_p >= 0.0) ? sqrt(P.bias_p) : 0.0;
+    MW_FOR(j, N) {
+      double a0, a1;
+      const int c = sym[j];
+      if (c == 0) { a0 = 1.0; a1 = 0.0; }
+      else if (c == 1) { a0 = 0.0; a1 = 1.0; }
+      else { a0 = 1.0 / sqrt(2.0); a1 = a0; }
+      if (j >= P.n_logical && P.bias_p >= 0.0) {
+        const double b0 = a0 * d + a1 * o, b1 = a0 * o + a1 * d;
+        a0 = b0; a1 = b1;
+      }
+      sites[j].val[0] = a0; sites[j].val[1] = a1;
+      sites[j].tgt[0] = 0; sites[j].tgt[1] = 0;
+    }
+    MW_FOR(j, N + 1) bd[j] = 1;
+    centre = 0; mirrored = 0; status = ST_OK; n_traced = 0;
+    MW_SYNC();
+  }
+
+  // ---- marginal over sites kL..N-1, reverse, dense, |.|, L2 renorm, tolerant arg-max ----
+  //   canonical.py:956-989, :150-161, :241-272; decoding.py:1362-1379
+  MD_DEV void marginal_readout(double* out, int* success) {
+    const int N = P.n_sites, kL = P.n_head, ren = P.renormalise;
+    if (P.kept_mask != ((kL >= 32) ? 0xffffffffu : ((1u << kL) - 1u))) { status = ST_NOT_MONOMIAL; return; }
+    double* T = s.cv;     // current last tensor (L x 2)
+    double* w = s.sig;    // traced vector
+    int L = bd[N - 1];
+    MW_FOR(t, L * 2) T[t] = (sites[N - 1].tgt[t] >= 0) ? sites[N - 1].val[t] : 0.0;
+    MW_SYNC();
+    for (int site = N - 1; site >= kL; --site) {
+      MW_FOR(l, L) w[l] = (T[l * 2] + T[l * 2 + 1]) * (1.0 / sqrt(2.0));
+      MW_SYNC();
+      const int L2 = bd[site - 1];
+      const MonoSite<CHI>& A = sites[site - 1];   // (L2, 2, L)
+      double acc = 0.0;
+      MW_FOR(t, L2 * 2) {
+        const int b = A.tgt[t];
+        const double v = (b >= 0) ? A.val[t] * w[b] : 0.0;
+        T[t] = v; acc += v * v;
+      }
+      cnt.bytes_hbm += 10.0 * 2 * L2;
+      if (ren) {
+        acc = mw_sum(acc);
+        const double nrm = sqrt(acc);
+        MW_SYNC();
+        MW_FOR(t, L2 * 2) T[t] = T[t] / nrm;   // unguarded like the reference: 0/0 -> NaN
+      }
+      MW_SYNC();
+      L = L2;
+    }
+    // the merged last logical tensor goes back into the MPS (what CanonicalMPS.marginal returns)
+    MW_FOR(t, L * 2) { sites[kL - 1].val[t] = T[t]; sites[kL - 1].tgt[t] = 0; }
+    MW_LANE0 { bd[kL] = 1; }
+    MW_SYNC();
+    // dense stage over the kL logical sites: every class follows one path through the monomial tensors
+    const int ncls = 1 << kL;
+    double nrm2 = 0.0, top = 0.0; int badv = 0;
+    MW_FOR(i, ncls) {
+      int b = 0; double amp = 1.0;
+      for (int j = 0; j < kL; ++j) {
+        const int r = b * 2 + ((i >> j) & 1);
+        if (j == kL - 1) { amp *= T[r]; break; }
+        const int t = sites[j].tgt[r];
+        if (t < 0) { amp = 0.0; break; }
+        amp *= sites[j].val[r]; b = t;
+      }
+      const double v = fabs(amp);
+      out[i] = v; nrm2 += v * v; top = fmax(top, v); badv |= (v != v);
+    }
+    nrm2 = mw_sum(nrm2); top = mw_max(top); badv = MW_ANY(badv);
+    const double nrm = sqrt(nrm2);
+    const double inv = (ren && nrm > 1e-17) ? 1.0 / nrm : 1.0;
+    const int bad = (badv || nrm != nrm) ? 1 : 0;
+    MW_SYNC();
+    MW_FOR(i, ncls) out[i] = out[i] * inv;
+    MW_SYNC();
+    MW_LANE0 {
+      if (bad) *success = 0;
+      else {
+        const double t2 = top * inv;
+        const double eps = fmax(P.readout_rel * t2, P.readout_abs);
+        *success = (out[0] >= t2 - eps) ? 1 : 0;
+      }
+    }
+    if (bad && status == ST_OK) status = ST_ZERO_NORM;
+    MW_SYNC();
+  }
+
+  MD_DEV void run(const int* prog, const uint8_t* sym, double* out, int* success) {
+    init_product(sym);
+    int pc = 0;
+    while (pc < P.n_ops) {
+      const int op = prog[pc];
+      if (op == OP_END) break;
+      if (op == OP_SWEEP) {
+        const int start = prog[pc + 1], len = prog[pc + 2], ren = prog[pc + 3], rsv = prog[pc + 4];
+        move_centre(start);
+        if (status != ST_CAPACITY && status != ST_NOT_MONOMIAL) {
+          mirrored = 0;
+          sweep(start, len, prog + pc + 5, P.chi_max, P.cut_sweep, ren, 0, rsv);
+          centre = start + len - 1;
+        }
+        pc += 5 + len;
+      } else if (op == OP_MOVE) {
+        move_centre(prog[pc + 1]);
+        pc += 2;
+      } else if (op == OP_MARGINAL) {
+        marginal_readout(out, success);
+        pc += 1;
+      } else {
+        status = ST_NOT_MONOMIAL;   // two-site gates / compression: dense engine
+      }
+      if (status == ST_CAPACITY || status == ST_NOT_MONOMIAL) break;
+    }
+  }
+};
+
+}  // namespace mdopt

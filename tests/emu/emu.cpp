@@ -1,12 +1,14 @@
 // Host emulation of the block-level engine (mdopt_b200/csrc/*.cuh compiled with -DMDOPT_EMU).
 // TEST INFRASTRUCTURE ONLY: lets the CPU-only test tier exercise the exact index logic, pivoting,
 // truncation rules and program interpreter the CUDA kernels run.  Never linked into libmdopt_b200.so.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
 
 #include "../../include/mdopt_b200.h"
 #include "../../mdopt_b200/csrc/mps_core.cuh"
+#include "../../mdopt_b200/csrc/mono_core.cuh"
 
 using namespace mdopt;
 
@@ -52,6 +54,42 @@ int decode_impl(const mdopt_decode_desc* d, const int32_t* program, const double
     counters[3] = sm->cnt.bytes_hbm; counters[4] = sm->cnt.n_steps; counters[5] = sm->cnt.n_trunc;
     counters[6] = sm->cnt.n_jacobi_sweeps; counters[7] = 0;
   }
+  delete sm;
+  return 0;
+}
+
+// the monomial (one warp per syndrome) engine, lane loops run sequentially
+template <int CHI>
+int mono_impl(const mdopt_decode_desc* d, const int32_t* program, const double* wtab, const int32_t* wdim,
+              const uint8_t* symbols, int batch, double* dist, int32_t* success, int32_t* status, double* trace,
+              double* counters) {
+  MonoSmem<CHI>* sm = new MonoSmem<CHI>();
+  std::vector<MonoSite<CHI>> sites(d->n_sites);
+  std::vector<int> bd(d->n_sites + 1);
+  MonoEngine<CHI> E(*sm);
+  E.sites = sites.data(); E.bd = bd.data(); E.wtab = wtab; E.wdim = wdim;
+  DecodeParams P;
+  P.n_sites = d->n_sites; P.n_logical = d->n_logical; P.chi_max = d->chi_max; P.mode = d->mode;
+  P.renormalise = d->renormalise; P.trace_stride = d->trace_stride; P.trace_max = d->trace_max;
+  P.n_ops = d->n_ops; P.cut_sweep = d->cut_sweep; P.cut_move = d->cut_move; P.rank_tol = d->rank_tol;
+  P.bias_p = d->bias_p;
+  P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
+  P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
+  P.readout_rel = d->readout_rel; P.readout_abs = d->readout_abs;
+  P.n_tensors = 0;
+  E.P = P;
+  E.cnt = MonoCounters{};
+  const int ncls = 1 << d->n_logical;
+  for (int b = 0; b < batch; ++b) {
+    E.trace = (trace && d->trace_stride > 0) ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
+    E.run(program, symbols + (size_t)b * d->n_sites, dist + (size_t)b * ncls, success + b);
+    status[b] = E.status;
+    if (E.status == ST_CAPACITY || E.status == ST_NOT_MONOMIAL) {
+      for (int i = 0; i < ncls; ++i) dist[(size_t)b * ncls + i] = NAN;
+      success[b] = 0;
+    }
+  }
+  if (counters) { counters[3] = E.cnt.bytes_hbm; counters[4] = E.cnt.n_steps; counters[5] = E.cnt.n_trunc; }
   delete sm;
   return 0;
 }
@@ -143,6 +181,20 @@ int emu_decode_batch(const mdopt_decode_desc* d, int chi_cap, const int32_t* pro
     case 64: return decode_impl<64>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
     case 128: return decode_impl<128>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
     case 256: return decode_impl<256>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+  }
+  return -2;
+}
+int emu_mono_decode_batch(const mdopt_decode_desc* d, int chi_cap, const int32_t* program, const double* wtab,
+                          const int32_t* wdim, const uint8_t* symbols, int batch, double* dist, int32_t* success,
+                          int32_t* status, double* trace, double* counters) {
+  switch (chi_cap) {
+    case 8: return mono_impl<8>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+    case 16: return mono_impl<16>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+    case 32: return mono_impl<32>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+    case 64: return mono_impl<64>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+    case 128: return mono_impl<128>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+    case 256: return mono_impl<256>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+    case 512: return mono_impl<512>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
   }
   return -2;
 }

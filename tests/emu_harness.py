@@ -16,7 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "emu", "libmdopt_emu.so")
 SRC = [os.path.join(HERE, "emu", "emu.cpp"), os.path.join(ROOT, "mdopt_b200", "csrc", "block_ops.cuh"),
-       os.path.join(ROOT, "mdopt_b200", "csrc", "mps_core.cuh"), os.path.join(ROOT, "include", "mdopt_b200.h")]
+       os.path.join(ROOT, "mdopt_b200", "csrc", "mps_core.cuh"), os.path.join(ROOT, "mdopt_b200", "csrc", "mono_core.cuh"),
+       os.path.join(ROOT, "include", "mdopt_b200.h")]
 
 
 def build(force=False):
@@ -42,8 +43,10 @@ def _ptr(a):
 
 
 def decode(program: schedule.Program, symbols, chi_max, cut, bias_p, renormalise=True, mode=schedule.MODE_FAST,
-           trace_max=0, rank_tol=_abi.DEFAULT_RANK_TOL, kept_mask=0, readout=(1e-9, 1e-12)):
-    cap = _abi.chi_capacity(max(chi_max, 1, _abi.readout_min_capacity(program.n_logical)))
+           trace_max=0, rank_tol=_abi.DEFAULT_RANK_TOL, kept_mask=0, readout=(1e-9, 1e-12), mono=False, cap=None):
+    """``mono=True`` runs the monomial (warp-per-syndrome) engine of mono_core.cuh instead of the dense one."""
+    if cap is None:
+        cap = _abi.chi_capacity(max(chi_max, 1, 1 if mono else _abi.readout_min_capacity(program.n_logical)))
     B = symbols.shape[0]
     ncls = 1 << program.n_logical
     stride = (4 + 2 * cap) if trace_max else 0
@@ -56,8 +59,9 @@ def decode(program: schedule.Program, symbols, chi_max, cut, bias_p, renormalise
     trace = np.zeros((B, max(trace_max, 1), max(stride, 1)))
     counters = np.zeros(8)
     syms = np.ascontiguousarray(symbols, dtype=np.uint8)
-    rc = lib().emu_decode_batch(C.byref(desc), cap, _ptr(program.ops), _ptr(program.wtab), _ptr(program.wdim),
-                                _ptr(syms), B, _ptr(dist), _ptr(success), _ptr(status), _ptr(trace), _ptr(counters))
+    fn = lib().emu_mono_decode_batch if mono else lib().emu_decode_batch
+    rc = fn(C.byref(desc), cap, _ptr(program.ops), _ptr(program.wtab), _ptr(program.wdim),
+            _ptr(syms), B, _ptr(dist), _ptr(success), _ptr(status), _ptr(trace), _ptr(counters))
     assert rc == 0
     return dist, success, status, trace, counters
 
