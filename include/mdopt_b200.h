@@ -34,6 +34,8 @@ extern "C" {
 #define MDOPT_ST_NOT_CONVERGED 1 /* a Jacobi SVD hit its sweep limit (result still returned) */
 #define MDOPT_ST_CAPACITY 2      /* a tensor exceeded the compiled capacity; result invalid */
 #define MDOPT_ST_ZERO_NORM 3     /* the state lost all weight; result is NaN like the reference's */
+#define MDOPT_ST_NOT_MONOMIAL 4  /* monomial engine only: a tensor left the sparse structure it verifies at every step
+                                    (or the program has a two-site gate); result invalid, re-run on the dense engine */
 
 #define MDOPT_E_BADARG (-1)
 #define MDOPT_E_CAPACITY (-2)
@@ -123,6 +125,28 @@ int mdopt_decode_batch_host(const mdopt_decode_desc* desc, int chi_cap, int n_ct
                             int batch, double* h_dist, int32_t* h_success, int32_t* h_status, uint8_t* d_symbols,
                             double* d_dist, int32_t* d_success, int32_t* d_status, double* d_counters,
                             void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The monomial ("trellis") engine for the same decode (mdopt_b200/csrc/mono_core.cuh): one warp per syndrome, every
+ * site tensor held as 2*chi (value, target) pairs.  It covers programs made of MDOPT_OP_SWEEP / _MOVE / _MARGINAL on
+ * product-state inputs (the bit-flip-bias decode, decoding.py:1267-1274, 1285-1339) and verifies the structure it
+ * relies on at every step; a syndrome that leaves it gets MDOPT_ST_NOT_MONOMIAL and must be re-run through
+ * mdopt_decode_batch_*.  Arguments as for mdopt_decode_batch_device / _host, with warps in place of CTAs;
+ * desc->mode is ignored; counters = {0, 0, 0, bytes, steps, truncating steps, 0, fallbacks, 0...}.
+ * Capacities: 8, 16, ..., 512.
+ */
+int mdopt_mono_chi_capacity(int chi);
+int mdopt_mono_num_warps(int chi_cap);
+size_t mdopt_mono_workspace_bytes(int chi_cap, int n_sites, int n_warps);
+int mdopt_mono_decode_batch_device(const mdopt_decode_desc* desc, int chi_cap, int n_warps, const int32_t* program,
+                                   const double* wtab, const int32_t* wdim, int n_tensors, const uint8_t* symbols,
+                                   int batch, double* dist, int32_t* success, int32_t* status, double* trace,
+                                   double* counters, void* workspace, size_t workspace_bytes, void* stream);
+int mdopt_mono_decode_batch_host(const mdopt_decode_desc* desc, int chi_cap, int n_warps, const int32_t* d_program,
+                                 const double* d_wtab, const int32_t* d_wdim, int n_tensors, const uint8_t* h_symbols,
+                                 int batch, double* h_dist, int32_t* h_success, int32_t* h_status, uint8_t* d_symbols,
+                                 double* d_dist, int32_t* d_success, int32_t* d_status, double* d_counters,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Run a program on caller-owned MPS buffers, in place (single-state API: mps_mpo_contract

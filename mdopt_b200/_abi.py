@@ -14,7 +14,7 @@ class DecodeDesc(C.Structure):
     ]
 
 
-ST_OK, ST_NOT_CONVERGED, ST_CAPACITY, ST_ZERO_NORM = 0, 1, 2, 3
+ST_OK, ST_NOT_CONVERGED, ST_CAPACITY, ST_ZERO_NORM, ST_NOT_MONOMIAL = 0, 1, 2, 3, 4
 E_BADARG, E_CAPACITY, E_NOGPU = -1, -2, -3
 DEFAULT_RANK_TOL = 1e-14
 CUT_MOVE = 1e-12  # default cut of split_two_site_tensor, used by move_orth_centre (mdopt/utils/utils.py:293)
@@ -35,6 +35,12 @@ PROTOTYPES = {
     "mdopt_decode_batch_device": (_i, [_desc, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mdopt_decode_batch_host": (_i, [_desc, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                      _sz, _p]),
+    "mdopt_mono_chi_capacity": (_i, [_i]),
+    "mdopt_mono_num_warps": (_i, [_i]),
+    "mdopt_mono_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mdopt_mono_decode_batch_device": (_i, [_desc, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mdopt_mono_decode_batch_host": (_i, [_desc, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                          _sz, _p]),
     "mdopt_site_stride": (_sz, [_i]),
     "mdopt_mps_program_workspace_bytes": (_sz, [_i, _i]),
     "mdopt_mps_program_device": (_i, [_desc, _i, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
@@ -70,6 +76,16 @@ def readout_min_capacity(n_logical: int) -> int:
     """Smallest capacity whose read-out pages hold the dense stage for ``n_logical`` kept sites."""
     k = int(n_logical)
     return (1 << (k - 1)) if k <= 6 else (1 << ((k + 1) // 2))
+
+
+MONO_CAPACITIES = (8, 16, 32, 64, 128, 256, 512)  # the monomial warp engine
+
+
+def mono_chi_capacity(chi: int) -> int:
+    for cap in MONO_CAPACITIES:
+        if chi <= cap:
+            return cap
+    return 0
 
 
 def chi_capacity(chi: int) -> int:

@@ -20,6 +20,19 @@ const ChiOps* ops_for(int chi_cap) {
   }
 }
 
+const mdopt::MonoOps* mono_ops_for(int chi_cap) {
+  switch (chi_cap) {
+    case 8: return mdopt::mono_ops_8();
+    case 16: return mdopt::mono_ops_16();
+    case 32: return mdopt::mono_ops_32();
+    case 64: return mdopt::mono_ops_64();
+    case 128: return mdopt::mono_ops_128();
+    case 256: return mdopt::mono_ops_256();
+    case 512: return mdopt::mono_ops_512();
+    default: return nullptr;
+  }
+}
+
 // Fused read-out of a batch of dense logical vectors (decoding.py:1362-1379).
 __global__ void readout_kernel(int batch, int ncls, const double* __restrict__ v, int renormalise, double* dist,
                                int* success) {
@@ -108,6 +121,65 @@ int mdopt_decode_batch_host(const mdopt_decode_desc* desc, int chi_cap, int n_ct
   int rc = mdopt_decode_batch_device(&d2, chi_cap, n_ctas, d_program, d_wtab, d_wdim, n_tensors, d_symbols, batch,
                                      d_dist, d_success, d_status, nullptr, d_counters, workspace, workspace_bytes,
                                      stream);
+  if (rc != 0) return rc;
+  e = cudaMemcpyAsync(h_dist, d_dist, (size_t)batch * ncls * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyAsync(h_success, d_success, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpyAsync(h_status, d_status, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaStreamSynchronize(st);
+}
+
+int mdopt_mono_chi_capacity(int chi) {
+  if (chi <= 0) return 0;
+  for (int cap = 8; cap <= 512; cap *= 2)
+    if (chi <= cap) return cap;
+  return 0;
+}
+
+int mdopt_mono_num_warps(int chi_cap) {
+  const mdopt::MonoOps* ops = mono_ops_for(chi_cap);
+  return ops ? ops->num_warps() : 0;
+}
+
+size_t mdopt_mono_workspace_bytes(int chi_cap, int n_sites, int n_warps) {
+  const mdopt::MonoOps* ops = mono_ops_for(chi_cap);
+  if (!ops || n_sites <= 0 || n_warps <= 0) return 0;
+  return ops->ws_bytes_per_warp(n_sites) * (size_t)n_warps + 256;
+}
+
+int mdopt_mono_decode_batch_device(const mdopt_decode_desc* desc, int chi_cap, int n_warps, const int32_t* program,
+                                   const double* wtab, const int32_t* wdim, int n_tensors, const uint8_t* symbols,
+                                   int batch, double* dist, int32_t* success, int32_t* status, double* trace,
+                                   double* counters, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!desc || !program || !wtab || !wdim || !symbols || !dist || !success || !status || !workspace)
+    return MDOPT_E_BADARG;
+  if (batch <= 0 || n_warps <= 0 || n_tensors <= 0) return MDOPT_E_BADARG;
+  if (desc->n_logical < 1 || desc->n_logical > 12 || desc->n_sites <= desc->n_logical) return MDOPT_E_BADARG;
+  const mdopt::MonoOps* ops = mono_ops_for(chi_cap);
+  if (!ops || desc->chi_max < 1 || desc->chi_max > chi_cap) return MDOPT_E_CAPACITY;
+  return ops->decode(desc, n_warps, program, wtab, wdim, n_tensors, symbols, batch, dist, success, status, trace,
+                     counters, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mdopt_mono_decode_batch_host(const mdopt_decode_desc* desc, int chi_cap, int n_warps, const int32_t* d_program,
+                                 const double* d_wtab, const int32_t* d_wdim, int n_tensors, const uint8_t* h_symbols,
+                                 int batch, double* h_dist, int32_t* h_success, int32_t* h_status, uint8_t* d_symbols,
+                                 double* d_dist, int32_t* d_success, int32_t* d_status, double* d_counters,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!desc || !h_symbols || !h_dist || !h_success || !h_status || !d_symbols || !d_dist || !d_success || !d_status)
+    return MDOPT_E_BADARG;
+  if (batch <= 0) return MDOPT_E_BADARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t ncls = (size_t)1 << desc->n_logical;
+  cudaError_t e = cudaMemcpyAsync(d_symbols, h_symbols, (size_t)batch * desc->n_sites, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return (int)e;
+  mdopt_decode_desc d2 = *desc;
+  d2.trace_stride = 0;
+  int rc = mdopt_mono_decode_batch_device(&d2, chi_cap, n_warps, d_program, d_wtab, d_wdim, n_tensors, d_symbols,
+                                          batch, d_dist, d_success, d_status, nullptr, d_counters, workspace,
+                                          workspace_bytes, stream);
   if (rc != 0) return rc;
   e = cudaMemcpyAsync(h_dist, d_dist, (size_t)batch * ncls * sizeof(double), cudaMemcpyDeviceToHost, st);
   if (e != cudaSuccess) return (int)e;

@@ -26,6 +26,24 @@ struct ChiOps {
                      cudaStream_t st);
 };
 
+// the monomial warp engine (mono_core.cuh): compiled capacities 8 ... 512
+struct MonoOps {
+  int chi;
+  int (*num_warps)();
+  size_t (*ws_bytes_per_warp)(int n_sites);
+  int (*decode)(const mdopt_decode_desc* d, int n_warps, const int32_t* program, const double* wtab,
+                const int32_t* wdim, int n_tensors, const uint8_t* symbols, int batch, double* dist, int32_t* success,
+                int32_t* status, double* trace, double* counters, void* workspace, size_t workspace_bytes,
+                cudaStream_t st);
+};
+const MonoOps* mono_ops_8();
+const MonoOps* mono_ops_16();
+const MonoOps* mono_ops_32();
+const MonoOps* mono_ops_64();
+const MonoOps* mono_ops_128();
+const MonoOps* mono_ops_256();
+const MonoOps* mono_ops_512();
+
 const ChiOps* chi_ops_8();
 const ChiOps* chi_ops_16();
 const ChiOps* chi_ops_32();

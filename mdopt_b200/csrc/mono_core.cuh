@@ -42,8 +42,6 @@
 
 namespace mdopt {
 
-enum { ST_NOT_MONOMIAL = 4 };
-enum { MODE_MONO = 3 };
 constexpr double MONO_TIE_REL2 = 2e-10;   // cluster width on sigma^2 (= 1e-10 relative on sigma)
 constexpr int MONO_ROW_BITS = 10;         // low key bits that carry the first supporting row (2*chi <= 1024)
 constexpr unsigned long long MONO_ROW_MASK = (1ull << MONO_ROW_BITS) - 1ull;
@@ -104,8 +102,10 @@ inline int mw_isum(int v) { return v; }
 // stay inside a lane and the others are one 64-bit shuffle each).  Host: std::sort.  Keys are unique or zero.
 // -------------------------------------------------------------------------------------------------
 #ifndef MDOPT_EMU
+// (not inlined: inside the function the warp is known to be converged, so every shuffle is a plain SHFL; inlined
+// into the engine's data-dependent control flow each one would carry a WARPSYNC.COLLECTIVE)
 template <int EPL>
-__device__ __forceinline__ void mw_sort_desc_impl(unsigned long long* keys, int n) {
+__device__ __noinline__ void mw_sort_desc_impl(unsigned long long* keys, int n) {
   const int lane = threadIdx.x & 31;
   unsigned long long k[EPL];
 #pragma unroll
@@ -477,20 +477,6 @@ struct MonoEngine {
     carried_to_site(start + len - 1, renorm_after);
   }
 
-  MD_DEV void move_centre(int target) {
-    const int from = centre;
-    if (target == from) return;
-    if (target > from) {
-      mirrored = 0;
-      sweep(from, target - from + 1, nullptr, CHI, P.cut_move, 0, 1, 0);
-    } else {
-      mirrored = 1;
-      sweep(P.n_sites - 1 - from, from - target + 1, nullptr, CHI, P.cut_move, 0, 1, 0);
-      mirrored = 0;
-    }
-    centre = target;
-  }
-
   // ---- product state + bit-flip bias (mps/utils.py:439-512, decoding.py:140-190) ----
   MD_DEV void init_product(const uint8_t* sym) {
     const int N = P.n_sites;
@@ -583,27 +569,41 @@ struct MonoEngine {
     MW_SYNC();
   }
 
+  // ---- run the program.  Every sweep -- the centre move in front of an op (canonical.py:345-420; moving left runs in
+  //      the mirrored frame like the reference's reverse()) and the MPO sweep itself -- goes through ONE call site,
+  //      so the step code exists once in the kernel ----
   MD_DEV void run(const int* prog, const uint8_t* sym, double* out, int* success) {
     init_product(sym);
     int pc = 0;
     while (pc < P.n_ops) {
       const int op = prog[pc];
       if (op == OP_END) break;
-      if (op == OP_SWEEP) {
-        const int start = prog[pc + 1], len = prog[pc + 2], ren = prog[pc + 3], rsv = prog[pc + 4];
-        move_centre(start);
-        if (status != ST_CAPACITY && status != ST_NOT_MONOMIAL) {
-          mirrored = 0;
-          sweep(start, len, prog + pc + 5, P.chi_max, P.cut_sweep, ren, 0, rsv);
-          centre = start + len - 1;
-        }
-        pc += 5 + len;
-      } else if (op == OP_MOVE) {
-        move_centre(prog[pc + 1]);
-        pc += 2;
-      } else if (op == OP_MARGINAL) {
+      if (op == OP_MARGINAL) {
         marginal_readout(out, success);
         pc += 1;
+      } else if (op == OP_SWEEP || op == OP_MOVE) {
+        const int target = prog[pc + 1];
+        for (int phase = (target == centre) ? 1 : 0; phase < 2; ++phase) {
+          if (phase == 1 && op == OP_MOVE) break;
+          int start, len, chi_lim, ren = 0, rsv = 0;
+          double cut;
+          const int* tids = nullptr;
+          if (phase == 0) {   // move the centre to `target`
+            mirrored = (target < centre) ? 1 : 0;
+            start = mirrored ? (P.n_sites - 1 - centre) : centre;
+            len = (mirrored ? (centre - target) : (target - centre)) + 1;
+            chi_lim = CHI; cut = P.cut_move;
+          } else {
+            mirrored = 0;
+            start = target; len = prog[pc + 2]; ren = prog[pc + 3]; rsv = prog[pc + 4];
+            tids = prog + pc + 5; chi_lim = P.chi_max; cut = P.cut_sweep;
+          }
+          sweep(start, len, tids, chi_lim, cut, ren, phase == 0, rsv);
+          mirrored = 0;
+          if (status == ST_CAPACITY || status == ST_NOT_MONOMIAL) break;
+          centre = (phase == 0) ? target : (target + len - 1);
+        }
+        pc += (op == OP_MOVE) ? 2 : (5 + prog[pc + 2]);
       } else {
         status = ST_NOT_MONOMIAL;   // two-site gates / compression: dense engine
       }

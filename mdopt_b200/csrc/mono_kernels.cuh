@@ -1,0 +1,113 @@
+// Kernel and launcher of the monomial warp engine (mono_core.cuh); included by mono_inst.cu once per capacity.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/mdopt_b200.h"
+#include "mono_core.cuh"
+
+namespace mdopt {
+namespace {
+
+// bytes of global workspace one warp needs: its MPS in monomial form + the bond dimensions
+__host__ __device__ inline size_t mono_ws_bytes_per_warp(int chi, int n_sites) {
+  size_t b = (size_t)n_sites * ((size_t)2 * chi * 10) + ((size_t)n_sites + 1) * sizeof(int);
+  return (b + 255) & ~(size_t)255;
+}
+
+// -------------------------------------------------------------------------------------------------
+// One warp per CTA, one syndrome per warp at a time; persistent warps pull syndromes from a global counter.
+// A warp's whole state is its ~8 KB of shared memory (chi = 64) plus its MPS slice in the workspace, so an SM
+// keeps 24 syndromes in flight and the site records stream through L2 / HBM.
+// -------------------------------------------------------------------------------------------------
+// resident one-warp CTAs per SM the register budget is tuned for (shared memory allows 24 at chi <= 64)
+constexpr int mono_min_ctas(int chi) { return chi <= 64 ? 24 : (chi <= 128 ? 12 : (chi <= 256 ? 6 : 3)); }
+template <int CHI>
+__global__ void __launch_bounds__(32, mono_min_ctas(CHI))
+mono_decode_kernel(DecodeParams P, const int* __restrict__ prog, const double* __restrict__ wtab,
+                   const int* __restrict__ wdim, const uint8_t* __restrict__ syms, int batch, double* dist,
+                   int* success, int* status, double* trace, double* counters, unsigned char* ws,
+                   int* work_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MonoSmem<CHI>& s = *reinterpret_cast<MonoSmem<CHI>*>(smem_raw);
+  static_assert(sizeof(MonoSite<CHI>) == (size_t)2 * CHI * 10, "site record layout");
+  MonoEngine<CHI> E(s);
+  unsigned char* base = ws + (size_t)blockIdx.x * mono_ws_bytes_per_warp(CHI, P.n_sites);
+  E.sites = reinterpret_cast<MonoSite<CHI>*>(base);
+  E.bd = reinterpret_cast<int*>(base + (size_t)P.n_sites * sizeof(MonoSite<CHI>));
+  E.wtab = wtab; E.wdim = wdim; E.P = P;
+  E.cnt = MonoCounters{};
+  const int ncls = 1 << P.n_logical;
+  const int lane = threadIdx.x;
+  while (true) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(work_counter, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= batch) break;
+    E.trace = trace ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
+    E.run(prog, syms + (size_t)b * P.n_sites, dist + (size_t)b * ncls, success + b);
+    __syncwarp();
+    if (E.status == ST_CAPACITY || E.status == ST_NOT_MONOMIAL) {
+      for (int i = lane; i < ncls; i += 32) dist[(size_t)b * ncls + i] = nan("");
+      if (lane == 0) success[b] = 0;
+      E.cnt.n_fallback += 1.0;
+    }
+    if (lane == 0) status[b] = E.status;
+    __syncwarp();
+  }
+  if (lane == 0 && counters) {
+    atomicAdd(counters + 3, E.cnt.bytes_hbm);
+    atomicAdd(counters + 4, E.cnt.n_steps);
+    atomicAdd(counters + 5, E.cnt.n_trunc);
+    atomicAdd(counters + 7, E.cnt.n_fallback);
+  }
+}
+
+template <int CHI>
+int mono_num_warps_impl() {
+  int dev = 0, sms = 0, per = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (cudaFuncSetAttribute((const void*)mono_decode_kernel<CHI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(MonoSmem<CHI>)) != cudaSuccess)
+    return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, mono_decode_kernel<CHI>, 32, sizeof(MonoSmem<CHI>)) !=
+      cudaSuccess)
+    return 0;
+  return sms * per;
+}
+
+template <int CHI>
+int launch_mono_decode(const mdopt_decode_desc* d, int n_warps, const int32_t* program, const double* wtab,
+                       const int32_t* wdim, int n_tensors, const uint8_t* symbols, int batch, double* dist,
+                       int32_t* success, int32_t* status, double* trace, double* counters, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
+  const size_t per = mono_ws_bytes_per_warp(CHI, d->n_sites);
+  if (workspace_bytes < per * (size_t)n_warps + 256) return MDOPT_E_BADARG;
+  cudaError_t e = cudaFuncSetAttribute((const void*)mono_decode_kernel<CHI>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MonoSmem<CHI>));
+  if (e != cudaSuccess) return (int)e;
+  DecodeParams P;
+  P.n_sites = d->n_sites; P.n_logical = d->n_logical; P.chi_max = d->chi_max; P.mode = d->mode;
+  P.renormalise = d->renormalise; P.trace_stride = d->trace_stride; P.trace_max = d->trace_max;
+  P.n_ops = d->n_ops; P.cut_sweep = d->cut_sweep; P.cut_move = d->cut_move; P.rank_tol = d->rank_tol;
+  P.bias_p = d->bias_p;
+  P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
+  P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
+  P.readout_rel = d->readout_rel; P.readout_abs = d->readout_abs;
+  P.n_tensors = n_tensors;
+  int* work_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + per * (size_t)n_warps);
+  e = cudaMemsetAsync(work_counter, 0, 256, st);
+  if (e != cudaSuccess) return (int)e;
+  if (counters) {
+    e = cudaMemsetAsync(counters, 0, 16 * sizeof(double), st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int grid = batch < n_warps ? batch : n_warps;
+  mono_decode_kernel<CHI><<<grid, 32, sizeof(MonoSmem<CHI>), st>>>(
+      P, program, wtab, wdim, symbols, batch, dist, success, status, d->trace_stride > 0 ? trace : nullptr, counters,
+      reinterpret_cast<unsigned char*>(workspace), work_counter);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+}  // namespace mdopt

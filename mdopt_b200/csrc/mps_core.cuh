@@ -31,9 +31,6 @@
 
 namespace mdopt {
 
-enum { OP_END = 0, OP_SWEEP = 1, OP_MOVE = 2, OP_MARGINAL = 3, OP_GATE2 = 4, OP_COMPRESS = 5 };
-enum { MODE_FAST = 0, MODE_SVD = 1, MODE_SVD_GRAM = 2 };  // 2: SVD mode with the deterministic Gram check only
-enum { ST_OK = 0, ST_NOT_CONVERGED = 1, ST_CAPACITY = 2, ST_ZERO_NORM = 3 };
 
 // Per-CTA engine.  All persistent state lives in shared memory (s.st) so that it costs no registers in
 // the register-resident QR loops; the Engine object itself is just the reference to the CTA's Smem.
@@ -600,7 +597,15 @@ struct Engine {
     MD_SYNC();
     const int Knew = factor(theta, R, C, CHI, st.P.cut_move, 1);
     if (st.status == ST_CAPACITY) return;
-    const int lay = s.iscr[7];
+    int lay = s.iscr[7];
+    if (lay == 3) {
+      // orthogonal-columns fast path of the SVD modes: the coefficient matrix diag(sigma) is not materialised by
+      // factor(); this op reads it as a matrix, so write it out (layout 1: coefficients in s.P2)
+      MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; s.P2[k * LD + c] = (c == s.order[k]) ? s.sig[c] : 0.0; }
+      MD_LEADER { s.iscr[7] = 1; }
+      MD_SYNC();
+      lay = 1;
+    }
     const double* coef = (lay == 2) ? s.X : s.P2;
     double scale = 1.0;
     if (renorm) {

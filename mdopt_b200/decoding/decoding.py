@@ -85,12 +85,14 @@ def css_code_logicals_sites(code):
     return schedule.code_site_lists(code)[1]
 
 
-def _resolve_mode(mode: str, depolarising: bool, cut: float, chi: int = 64) -> str:
-    """"auto" -> the SVD mode (the reference algorithm with the orthogonality checks in front of every split).  With
-    the bit-flip bias no split needs a rotation; with the depolarising bias about half of them do and the mode is
-    still ahead of the QR steps (d=5, chi_max=64: 416 vs 309 syndromes/s; d=7, chi_max=128: 1.25 vs 0.82).  An
-    explicit "fast" with a cut that discards singular values is run as "svd"."""
+def _resolve_mode(mode: str, depolarising: bool, cut: float) -> str:
+    """``"auto"``: the monomial warp engine for the bit-flip bias (product-state inputs and 0/1 constraint tensors keep
+    every site tensor p-monomial, which the engine verifies; anything it hands back is re-run on the dense engine),
+    the dense SVD mode for the depolarising bias (the two-site bias gates mix the basis).  An explicit ``"fast"`` with
+    a cut that discards singular values is run as ``"svd"``: the QR steps do not apply ``cut``."""
     if mode == "auto":
+        mode = "svd" if depolarising else "mono"
+    if mode == "mono" and depolarising:
         mode = "svd"
     if mode == "fast" and cut > 1e-14:
         mode = "svd"
@@ -131,12 +133,12 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
     what ``decode_css(code, errors[b], ...)`` returns.  All-identity errors take the reference's early exit
     (``[1, 0, 0, 0], 1``, decoding.py:1225-1228).
 
-    ``mode``: ``"svd"`` runs the reference algorithm split by split (SVD with ``k = min(chi_max, #(s > cut))``); with
-    the bit-flip bias every bond stays in its Schmidt basis under the XOR / SWAP constraint tensors, so every split
-    finds its columns already orthogonal (checked on the GPU) and needs no rotation; with the depolarising bias about
-    half of the splits fall through to the Jacobi rotations.  ``"fast"`` replaces non-truncating splits by
-    rank-revealing QR steps (needs ``cut <= 1e-14``).  ``"auto"`` (default) is ``"svd"``.  ``"svd-gram"`` is
-    ``"svd"`` with the deterministic Gram check only.
+    ``mode``: ``"mono"`` is the monomial warp engine (one warp per syndrome, site tensors as 2*chi (value, target)
+    pairs; the structure is verified at every step and a syndrome that leaves it is re-run on the dense engine).
+    ``"svd"`` runs the reference algorithm split by split on dense tensors (SVD with ``k = min(chi_max, #(s > cut))``,
+    orthogonality checks in front of the Jacobi rotations); ``"svd-gram"`` is ``"svd"`` with the deterministic Gram
+    check only; ``"fast"`` replaces non-truncating splits by rank-revealing QR steps (needs ``cut <= 1e-14``).
+    ``"auto"`` (default) is ``"mono"`` for the bit-flip bias and ``"svd"`` for the depolarising bias.
     """
     from mdopt_b200 import engine
 
@@ -146,7 +148,7 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
     k = code.num_x_logicals() + code.num_z_logicals()
     n = len(code)
     n_sites = 2 * n + k
-    mode = _resolve_mode(mode, depol, cut, _effective_chi(chi_max, n_sites))
+    mode = _resolve_mode(mode, depol, cut)
     errors = list(errors)
     B = len(errors)
     if B == 0:
@@ -235,7 +237,7 @@ def decode_custom_batch(stabilizers: Sequence[str], x_logicals: Sequence[str], z
     n_sites = 2 * n + k
     if not 1 <= k <= 12:
         raise NotImplementedError("the dense read-out supports 1..12 logical sites")
-    mode = _resolve_mode(mode, depol, cut, _effective_chi(chi_max, n_sites))
+    mode = _resolve_mode(mode, depol, cut)
     errors = list(errors)
     B = len(errors)
     dist = np.zeros((B, 1 << k))

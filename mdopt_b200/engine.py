@@ -12,15 +12,35 @@ import numpy as np
 
 from mdopt_b200 import _abi, _lib, schedule
 
-_MODES = {"fast": schedule.MODE_FAST, "svd": schedule.MODE_SVD, "svd-gram": schedule.MODE_SVD_GRAM}
+_MODES = {"fast": schedule.MODE_FAST, "svd": schedule.MODE_SVD, "svd-gram": schedule.MODE_SVD_GRAM,
+          "mono": schedule.MODE_MONO}
+MONO_FALLBACK_MODE = "svd-gram"   # dense mode that re-runs syndromes the monomial engine hands back
 
 
 def mode_id(mode) -> int:
     if isinstance(mode, str):
         if mode not in _MODES:
-            raise ValueError(f"mode must be 'fast', 'svd' or 'svd-gram', given {mode!r}")
+            raise ValueError(f"mode must be 'mono', 'fast', 'svd' or 'svd-gram', given {mode!r}")
         return _MODES[mode]
     return int(mode)
+
+
+def program_is_monomial_candidate(program: schedule.Program) -> bool:
+    """The monomial engine interprets sweeps, moves and the read-out; two-site gates and compression are dense."""
+    ops, pc = program.ops, 0
+    while pc < len(ops):
+        op = int(ops[pc])
+        if op == schedule.OP_END:
+            return True
+        if op == schedule.OP_SWEEP:
+            pc += 5 + int(ops[pc + 2])
+        elif op == schedule.OP_MOVE:
+            pc += 2
+        elif op == schedule.OP_MARGINAL:
+            pc += 1
+        else:
+            return False
+    return True
 
 
 def _vp(t) -> C.c_void_p:
@@ -40,7 +60,13 @@ class DeviceProgram:
 
 
 class DecodeEngine:
-    """Owns the per-device workspace and staging buffers; decodes batches that share a program."""
+    """Owns the per-device workspace and staging buffers; decodes batches that share a program.
+
+    One engine serves every ``chi_max`` up to its compiled capacity (``chi_max`` travels in the descriptor of each
+    call).  The workspaces of the two kernels -- the dense CTA-per-syndrome engine and the monomial warp-per-syndrome
+    engine -- are allocated on first use and freed by ``release()``.  An engine owns ONE workspace, work counter and
+    counter block per kernel: launches on it must be serialised on one stream (do not share an engine between
+    concurrently running streams)."""
 
     def __init__(self, n_sites: int, n_logical: int, chi_max: int, device=None, max_batch: int = 1 << 16) -> None:
         self.lib, self.torch = _lib.require_gpu()
@@ -48,12 +74,28 @@ class DecodeEngine:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.n_sites, self.n_logical, self.chi_max = int(n_sites), int(n_logical), int(chi_max)
         self.cap = _abi.chi_capacity(max(self.chi_max, _abi.readout_min_capacity(n_logical)))
-        if self.cap == 0:
+        self.mono_cap = _abi.mono_chi_capacity(self.chi_max)
+        if self.cap == 0 and self.mono_cap == 0:
             raise _lib.MdoptCudaError(
-                f"chi_max={chi_max} exceeds the largest compiled capacity ({_abi.MAX_CAPACITY})"
+                f"chi_max={chi_max} exceeds the largest compiled capacity ({_abi.MONO_CAPACITIES[-1]})"
             )
         if not 1 <= self.n_logical <= 12:
-            raise NotImplementedError("the dense read-out supports 1..12 logical sites (Dephasing DMRG is out of scope)")
+            raise NotImplementedError("the dense read-out supports 1..12 logical sites")
+        self.counters = torch.zeros(16, dtype=torch.float64, device=self.device)
+        self.workspace = None
+        self.mono_workspace = None
+        self.n_ctas = self.n_warps = 0
+        self.max_batch = 0
+        self._alloc(max_batch)
+        self._programs: Dict[int, DeviceProgram] = {}
+
+    def _ensure_dense(self) -> None:
+        if self.workspace is not None:
+            return
+        if self.cap == 0:
+            raise _lib.MdoptCudaError(
+                f"chi_max={self.chi_max} exceeds the largest capacity of the dense engine ({_abi.MAX_CAPACITY})")
+        torch = self.torch
         with torch.cuda.device(self.device):
             self.n_ctas = int(self.lib.mdopt_decode_num_ctas(self.cap))
             if self.n_ctas <= 0:
@@ -64,10 +106,27 @@ class DecodeEngine:
             self.n_ctas = max(1, min(self.n_ctas, int(0.8 * free_bytes) // max(per_cta, 1)))
             self.ws_bytes = int(self.lib.mdopt_decode_workspace_bytes(self.cap, self.n_sites, self.n_ctas))
             self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
-            self.counters = torch.zeros(16, dtype=torch.float64, device=self.device)
-        self.max_batch = 0
-        self._alloc(max_batch)
-        self._programs: Dict[int, DeviceProgram] = {}
+
+    def _ensure_mono(self) -> None:
+        if self.mono_workspace is not None:
+            return
+        if self.mono_cap == 0:
+            raise _lib.MdoptCudaError(f"chi_max={self.chi_max} exceeds the monomial engine's largest capacity")
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            self.n_warps = int(self.lib.mdopt_mono_num_warps(self.mono_cap))
+            if self.n_warps <= 0:
+                raise _lib.MdoptCudaError("monomial decode kernel cannot be made resident on this device")
+            free_bytes, _total = torch.cuda.mem_get_info()
+            per_warp = int(self.lib.mdopt_mono_workspace_bytes(self.mono_cap, self.n_sites, 1))
+            self.n_warps = max(1, min(self.n_warps, int(0.8 * free_bytes) // max(per_warp, 1)))
+            self.mono_ws_bytes = int(self.lib.mdopt_mono_workspace_bytes(self.mono_cap, self.n_sites, self.n_warps))
+            self.mono_workspace = torch.empty(self.mono_ws_bytes, dtype=torch.uint8, device=self.device)
+
+    def release(self) -> None:
+        """Free the device workspaces (they come back on the next launch)."""
+        self.workspace = None
+        self.mono_workspace = None
 
     def _alloc(self, batch: int) -> None:
         torch = self.torch
@@ -114,38 +173,75 @@ class DecodeEngine:
             d_success = torch.empty(batch, dtype=torch.int32, device=self.device)
         if d_status is None:
             d_status = torch.empty(batch, dtype=torch.int32, device=self.device)
-        stride = 4 + 2 * self.cap if trace_max else 0
+        mono = mode_id(mode) == schedule.MODE_MONO
+        cap = self.mono_cap if mono else self.cap
+        stride = 4 + 2 * cap if trace_max else 0
         d_trace = torch.zeros((batch, trace_max, stride), dtype=torch.float64, device=self.device) if trace_max else None
         desc = self._desc(program, cut, bias_p, renormalise, mode, stride, trace_max, rank_tol)
         with torch.cuda.device(self.device):
-            rc = self.lib.mdopt_decode_batch_device(
-                C.byref(desc), self.cap, self.n_ctas, _vp(dp.ops), _vp(dp.wtab), _vp(dp.wdim), dp.wtab.shape[0],
-                _vp(d_symbols), batch, _vp(d_dist), _vp(d_success), _vp(d_status), _vp(d_trace),
-                _vp(self.counters), _vp(self.workspace), self.ws_bytes, _stream(torch))
-        _lib.check(rc, "mdopt_decode_batch_device")
+            if mono:
+                # no automatic dense re-run here: the caller sees MDOPT_ST_NOT_MONOMIAL in d_status (decode_host
+                # and decode_css_batch do the re-run)
+                self._ensure_mono()
+                rc = self.lib.mdopt_mono_decode_batch_device(
+                    C.byref(desc), self.mono_cap, self.n_warps, _vp(dp.ops), _vp(dp.wtab), _vp(dp.wdim),
+                    dp.wtab.shape[0], _vp(d_symbols), batch, _vp(d_dist), _vp(d_success), _vp(d_status), _vp(d_trace),
+                    _vp(self.counters), _vp(self.mono_workspace), self.mono_ws_bytes, _stream(torch))
+            else:
+                self._ensure_dense()
+                rc = self.lib.mdopt_decode_batch_device(
+                    C.byref(desc), self.cap, self.n_ctas, _vp(dp.ops), _vp(dp.wtab), _vp(dp.wdim), dp.wtab.shape[0],
+                    _vp(d_symbols), batch, _vp(d_dist), _vp(d_success), _vp(d_status), _vp(d_trace),
+                    _vp(self.counters), _vp(self.workspace), self.ws_bytes, _stream(torch))
+        _lib.check(rc, "mdopt_mono_decode_batch_device" if mono else "mdopt_decode_batch_device")
         return d_dist, d_success, d_status, d_trace
 
     # ---- host buffers in, host buffers out (the drop-in call) --------------------------------------
     def decode_host(self, program, symbols: np.ndarray, cut=1e-17, bias_p=0.1, renormalise=True, mode="fast",
                     rank_tol=_abi.DEFAULT_RANK_TOL, kept_mask=0, readout=(1e-9, 1e-12)):
-        """H2D copy of the symbols, fused decode kernel, D2H of (dist, success, status); synchronous."""
+        """H2D copy of the symbols, fused decode kernel, D2H of (dist, success, status); synchronous.
+
+        ``mode="mono"`` runs the monomial warp engine and re-runs, on the dense engine, every syndrome it hands back
+        with MDOPT_ST_NOT_MONOMIAL (none for a bit-flip-bias decode); both stages are GPU kernels."""
         torch = self.torch
         dp = self.upload(program)
         batch = int(symbols.shape[0])
         if batch > self.max_batch:
             self._alloc(batch)
         self.h_sym[:batch].numpy()[...] = symbols
+        mono = mode_id(mode) == schedule.MODE_MONO
+        if mono and (kept_mask or not program_is_monomial_candidate(program)):
+            mono, mode = False, MONO_FALLBACK_MODE   # erased logical-index qubits / two-site gates: dense engine
         desc = self._desc(program, cut, bias_p, renormalise, mode, rank_tol=rank_tol, kept_mask=kept_mask,
                           readout=readout)
         with torch.cuda.device(self.device):
-            rc = self.lib.mdopt_decode_batch_host(
-                C.byref(desc), self.cap, self.n_ctas, _vp(dp.ops), _vp(dp.wtab), _vp(dp.wdim), dp.wtab.shape[0],
-                _vp(self.h_sym), batch, _vp(self.h_dist), _vp(self.h_success), _vp(self.h_status),
-                _vp(self.d_sym), _vp(self.d_dist), _vp(self.d_success), _vp(self.d_status), _vp(self.counters),
-                _vp(self.workspace), self.ws_bytes, _stream(torch))
-        _lib.check(rc, "mdopt_decode_batch_host")
-        return (self.h_dist[:batch].numpy().copy(), self.h_success[:batch].numpy().copy(),
-                self.h_status[:batch].numpy().copy())
+            if mono:
+                self._ensure_mono()
+                rc = self.lib.mdopt_mono_decode_batch_host(
+                    C.byref(desc), self.mono_cap, self.n_warps, _vp(dp.ops), _vp(dp.wtab), _vp(dp.wdim),
+                    dp.wtab.shape[0], _vp(self.h_sym), batch, _vp(self.h_dist), _vp(self.h_success),
+                    _vp(self.h_status), _vp(self.d_sym), _vp(self.d_dist), _vp(self.d_success), _vp(self.d_status),
+                    _vp(self.counters), _vp(self.mono_workspace), self.mono_ws_bytes, _stream(torch))
+            else:
+                self._ensure_dense()
+                rc = self.lib.mdopt_decode_batch_host(
+                    C.byref(desc), self.cap, self.n_ctas, _vp(dp.ops), _vp(dp.wtab), _vp(dp.wdim), dp.wtab.shape[0],
+                    _vp(self.h_sym), batch, _vp(self.h_dist), _vp(self.h_success), _vp(self.h_status),
+                    _vp(self.d_sym), _vp(self.d_dist), _vp(self.d_success), _vp(self.d_status), _vp(self.counters),
+                    _vp(self.workspace), self.ws_bytes, _stream(torch))
+        _lib.check(rc, "mdopt_mono_decode_batch_host" if mono else "mdopt_decode_batch_host")
+        dist = self.h_dist[:batch].numpy().copy()
+        success = self.h_success[:batch].numpy().copy()
+        status = self.h_status[:batch].numpy().copy()
+        if mono:
+            redo = np.nonzero(status == _abi.ST_NOT_MONOMIAL)[0]
+            self.last_mono_fallbacks = int(redo.size)
+            if redo.size:
+                d2, s2, st2 = self.decode_host(program, np.ascontiguousarray(symbols[redo]), cut=cut, bias_p=bias_p,
+                                               renormalise=renormalise, mode=MONO_FALLBACK_MODE, rank_tol=rank_tol,
+                                               kept_mask=kept_mask, readout=readout)
+                dist[redo], success[redo], status[redo] = d2, s2, st2
+        return dist, success, status
 
     def read_counters(self) -> Dict[str, float]:
         c = self.counters.cpu().numpy()
@@ -158,11 +254,23 @@ _ENGINES: Dict[Tuple, DecodeEngine] = {}
 
 
 def get_engine(n_sites: int, n_logical: int, chi_max: int) -> DecodeEngine:
+    """Cached engine, keyed on the COMPILED capacities (a sweep over chi_max = 20, 30, 40, 64 shares one engine and one
+    workspace; ``chi_max`` itself travels in the descriptor of every call)."""
     lib, torch = _lib.require_gpu()
-    key = (torch.cuda.current_device(), n_sites, n_logical, chi_max)
+    cap = _abi.chi_capacity(max(int(chi_max), _abi.readout_min_capacity(n_logical)))
+    key = (torch.cuda.current_device(), n_sites, n_logical, cap, _abi.mono_chi_capacity(int(chi_max)))
     if key not in _ENGINES:
-        _ENGINES[key] = DecodeEngine(n_sites, n_logical, chi_max, max_batch=4096)
-    return _ENGINES[key]
+        _ENGINES[key] = DecodeEngine(n_sites, n_logical, int(chi_max), max_batch=4096)
+    eng = _ENGINES[key]
+    eng.chi_max = int(chi_max)
+    return eng
+
+
+def clear_engines() -> None:
+    """Drop every cached engine and its device workspaces."""
+    for eng in _ENGINES.values():
+        eng.release()
+    _ENGINES.clear()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -205,6 +313,8 @@ def run_program_on_mps(tensors, centre: int, ops: np.ndarray, wtab: np.ndarray, 
     Without an explicit ``cap`` the compiled capacity is chosen from the input bonds and ``chi_max`` and raised
     (64 -> 128 -> 256) when an intermediate bond outgrows it, so an untruncated contraction behaves like the
     reference's up to bond dimension 256."""
+    if mode == "fast" and cut > 1e-14:
+        mode = "svd"   # the QR steps of "fast" never apply the user's cut (rule k = min(chi_max, #(s > cut)))
     max_bond = max(max(t.shape[0], t.shape[2]) for t in tensors)
     if cap is not None:
         caps = [int(cap)]
@@ -264,7 +374,7 @@ def _run_program_at_capacity(tensors, centre, ops, wtab, wdim, chi_max, cut, ren
     return res
 
 
-def run_constraints(mps, strings, logical_tensors, chi_max, cut, renormalise, strategy, order=None, mode="fast"):
+def run_constraints(mps, strings, logical_tensors, chi_max, cut, renormalise, strategy, order=None, mode="svd"):
     from mdopt_b200.mps.canonical import CanonicalMPS
 
     table, ops, spans = schedule.TensorTable(), [], []

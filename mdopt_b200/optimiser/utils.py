@@ -99,7 +99,7 @@ class ConstraintString:
 
 def apply_constraints(mps, strings, logical_tensors, chi_max=int(1e4), cut=float(1e-17), renormalise=True,
                       strategy="Naive", silent=False, dense=False, return_entropies_and_bond_dims=False,
-                      order=None, mode="fast"):
+                      order=None, mode="svd"):
     """Apply constraint strings to an MPS on the GPU (reference :216-359).
 
     Returns a new ``CanonicalMPS``; the input is not modified.  ``dense`` and

@@ -16,7 +16,7 @@ import numpy as np
 from mdopt_b200.optimiser.utils import (COPY_LEFT, SWAP, XOR_BULK, XOR_LEFT, XOR_RIGHT, ConstraintString, msro)
 
 OP_END, OP_SWEEP, OP_MOVE, OP_MARGINAL, OP_GATE2, OP_COMPRESS = 0, 1, 2, 3, 4, 5
-MODE_FAST, MODE_SVD, MODE_SVD_GRAM = 0, 1, 2
+MODE_FAST, MODE_SVD, MODE_SVD_GRAM, MODE_MONO = 0, 1, 2, 3
 SYM_ZERO, SYM_ONE, SYM_PLUS = 0, 1, 2
 
 # decoding.py:283-320; "E" (erasure) becomes "++"
