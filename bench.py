@@ -5,9 +5,12 @@
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
 
 One *step* decodes one batch of seeded bit-flip error strings (p = 0.05, decoder bias 0.1, cut 1e-17,
-"Optimised" order) per GPU.  `value` is whole-job syndromes/s with the product-state symbols already
-resident in HBM; `e2e` is the same batch through the public `decode_css_batch` call with host strings in
-and host arrays out (symbol packing, H2D, kernel, D2H inside the timed region).
+"Optimised" order) per GPU: by default the 100 000-syndrome batch BASELINE.json configs[1] names, one such shard per
+GPU (weak scaling); `--scaling strong` shards ONE 100 000-syndrome batch over the GPUs instead.  `value` is whole-job
+syndromes/s with the product-state symbols already resident in HBM; `e2e` is the same batch through the public
+`decode_css_batch` call with host strings in and host arrays out (string packing, H2D, kernel, D2H inside the timed
+region).  The CPU arm times the UNMODIFIED reference (oracle/_ref, copied by oracle/make_ref.py) on the host cores;
+the same run compares the GPU results of the CPU-sample syndromes with it (`parity`).
 """
 from __future__ import annotations
 
@@ -27,28 +30,29 @@ import numpy as np  # noqa: E402
 LATTICE, CHI_MAX, ERROR_RATE, BIAS, CUT, SEED = 5, 64, 0.05, 0.1, 1e-17, 123
 WORKLOAD = f"surface_d{LATTICE}_bitflip_p{ERROR_RATE}_bias{BIAS}_chi{CHI_MAX}_cut{CUT}_optimised"
 REF_FLOP_PER_NONTRIVIAL = 47.98e9 + 1.70e9  # LAPACK-count of the reference's call sequence
-# dram__bytes_read.sum + dram__bytes_write.sum of decode_kernel<64> from the `ncu --set full` capture summarised
-# in profiles/r01_decode_kernel_ncu_summary.md: 12.23 GB for a launch of 143 non-trivial syndromes (default mode)
-DRAM_BYTES_PER_NONTRIVIAL = 12.23e9 / 143
+CONFIG2_BATCH = 100_000
 
 
 def seeded_errors(n_qubits, rate, count, seed, offset=0):
     """One child generator per syndrome (examples/decoding/quantum_surface.py:130-137), bit-flip model."""
-    ss = np.random.SeedSequence(seed)
+    ss = np.random.SeedSequence(seed, n_children_spawned=offset)
+    table = np.array(["I", "X"])
     out = []
-    for child in ss.spawn(offset + count)[offset:]:
-        rng = np.random.default_rng(child)
-        out.append("".join("X" if rng.random() < rate else "I" for _ in range(n_qubits)))
+    for child in ss.spawn(count):
+        # rng.random(n) draws the same doubles as n successive rng.random() calls (decoding.py:1018-1022)
+        out.append("".join(table[(np.random.default_rng(child).random(n_qubits) < rate).astype(np.intp)]))
     return out
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm on the host cores (the reference itself is Python and
-# does not travel to the GPU box; oracle/mps_oracle.py is pinned bit-for-bit against it, see DESIGN.md).
+# CPU arm: the UNMODIFIED reference (oracle/_ref, see oracle/make_ref.py) on the host cores, one process per core with
+# one BLAS thread each (the reference's own cluster convention, quantum_surface_cc.sh:58).  If oracle/_ref did not
+# travel, the numpy port of the same algorithm (oracle/mps_oracle.py, pinned against the reference) is timed instead
+# and the line says kind = "port".
 # ------------------------------------------------------------------------------------------------------
 def _cpu_init():
-    """One BLAS thread per worker (the reference's cluster convention, quantum_surface_cc.sh:58).  The env
-    var alone is not enough: the parent has usually initialised its BLAS pool before the fork."""
+    """One BLAS thread per worker.  The env var alone is not enough: the parent has usually initialised its BLAS
+    pool before the fork."""
     os.environ["OMP_NUM_THREADS"] = "1"
     try:
         from threadpoolctl import threadpool_limits
@@ -58,43 +62,79 @@ def _cpu_init():
         pass
 
 
-def _cpu_worker(err):
+def _cpu_decoder():
+    """(kind, decode(err, canonical) -> (dist, ok)) bound to the reference if present, else to the port."""
+    if hasattr(_cpu_decoder, "cached"):
+        return _cpu_decoder.cached
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import mps_oracle as O
+    import make_ref
+    import structured_svd as S
 
-    code = _cpu_worker.code if hasattr(_cpu_worker, "code") else O.surface_code(LATTICE)
-    _cpu_worker.code = code
-    dist, ok = O.decode_css(code, err, chi_max=CHI_MAX, cut=CUT, bias_type="Bitflip", bias_prob=BIAS,
-                            contraction_strategy="Optimised", tolerance=1e-12)
-    return int(ok)
+    kw = dict(chi_max=CHI_MAX, cut=CUT, bias_type="Bitflip", bias_prob=BIAS, contraction_strategy="Optimised",
+              tolerance=1e-12)
+    ref = make_ref.import_reference()
+    if ref is not None:
+        decode_css, qec = ref
+        code = qec.hypergraph_product(qec.repetition_code(LATTICE), qec.repetition_code(LATTICE))
+        kind, fn = "reference", (lambda e: decode_css(code, e, silent=True, **kw))
+    else:
+        import mps_oracle as O
+
+        code = O.surface_code(LATTICE)
+        kind, fn = "port", (lambda e: O.decode_css(code, e, **kw))
+
+    def decode(err, canonical=False):
+        if canonical:   # the same decode with the canonical tie-break at the SVD hook (parity leg, never timed)
+            with S.installed():
+                d, ok = fn(err)
+        else:
+            d, ok = fn(err)
+        return [float(x) for x in d], int(ok)
+
+    _cpu_decoder.cached = (kind, decode)
+    return _cpu_decoder.cached
 
 
-def cpu_rate(errors, cores, budget_s=25.0):
+def _cpu_worker(err):
+    return (err,) + _cpu_decoder()[1](err)
+
+
+def _cpu_worker_canonical(err):
+    return (err,) + _cpu_decoder()[1](err, canonical=True)
+
+
+def cpu_rate(errors, cores, budget_s=25.0, parity=False):
     """Decode `errors` on `cores` worker processes for at most ~budget_s seconds of measured time; returns
-    (syndromes/s, seconds, n_done, n_success).  Bounded so the default bench always ends within minutes."""
+    (syndromes/s, seconds, n_done, rows) with rows = [(error, dist, ok)].  Bounded so the default bench always ends
+    within minutes.  With `parity`, the finished syndromes are decoded once more (untimed) with the canonical
+    tie-break installed, for the in-run parity check."""
     import multiprocessing as mp
 
-    os.environ["OMP_NUM_THREADS"] = "1"  # the reference's own cluster convention (quantum_surface_cc.sh:58)
+    os.environ["OMP_NUM_THREADS"] = "1"
     ctx = mp.get_context("fork")
     pool = ctx.Pool(cores, initializer=_cpu_init)
+    rows, canon = [], []
     try:
         warm = pool.map_async(_cpu_worker, errors[:cores])  # imports, BLAS init, first decode
-        warm.get(timeout=180)
+        warm.get(timeout=300)
         t0 = time.perf_counter()
-        done, oks = 0, 0
         it = pool.imap_unordered(_cpu_worker, errors, chunksize=1)
-        while done < len(errors):
+        while len(rows) < len(errors):
             remaining = budget_s - (time.perf_counter() - t0)
             try:
-                oks += it.next(timeout=max(remaining, 0.01))
-                done += 1
+                rows.append(it.next(timeout=max(remaining, 0.01)))
             except mp.TimeoutError:
                 break
         dt = time.perf_counter() - t0
+        if parity and rows:
+            try:
+                canon = pool.map_async(_cpu_worker_canonical, [r[0] for r in rows]).get(timeout=120)
+            except Exception:  # noqa: BLE001
+                canon = []
     finally:
         pool.terminate()
         pool.join()
-    return done / dt, dt, done, oks
+    return len(rows) / dt, dt, len(rows), rows, canon
 
 
 def cpu_sample_main():
@@ -103,20 +143,36 @@ def cpu_sample_main():
     cores = min(len(os.sched_getaffinity(0)), 64)
     n = LATTICE * LATTICE + (LATTICE - 1) ** 2
     sample = seeded_errors(n, ERROR_RATE, 2 * cores, SEED)
-    r, dt, done, _ = cpu_rate(sample, cores)
-    print(json.dumps({"value": r, "unit": "syndromes/s", "cores": cores, "kind": "port",
+    kind = _cpu_decoder()[0]
+    r, dt, done, rows, canon = cpu_rate(sample, cores, parity=True)
+    print(json.dumps({"value": r, "unit": "syndromes/s", "cores": cores, "kind": kind,
                       "sample": f"{done} of the first {len(sample)} seeded syndromes of the workload in {dt:.1f}s, "
-                                f"oracle port of the reference algorithm, multiprocessing.Pool({cores}), "
-                                "one BLAS thread per worker"}), flush=True)
+                                + ("the unmodified reference (oracle/_ref)" if kind == "reference" else
+                                   "numpy port of the reference algorithm")
+                                + f", multiprocessing.Pool({cores}), one BLAS thread per worker",
+                      "rows": rows, "rows_canonical": canon}), flush=True)
 
 
 def cpu_baseline_subprocess():
     try:
         out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-sample"], capture_output=True,
-                             text=True, timeout=300)
+                             text=True, timeout=600)
         return json.loads(out.stdout.strip().splitlines()[-1])
     except Exception as exc:  # noqa: BLE001
         return {"value": None, "unit": "syndromes/s", "cores": 0, "kind": "port", "sample": f"failed: {exc!r}"}
+
+
+def parity_report(rows, gpu_lookup):
+    """Compare CPU rows [(error, dist, ok)] with the GPU results of the same error strings."""
+    if not rows:
+        return None
+    mism, worst = 0, 0.0
+    for err, dist, ok in rows:
+        g_dist, g_ok = gpu_lookup(err)
+        mism += int(int(ok) != int(g_ok))
+        d = np.asarray(dist, dtype=float)
+        worst = max(worst, float(np.max(np.abs(d - g_dist)) / max(np.max(d), 1e-300)))
+    return {"n": len(rows), "flag_mismatch": mism, "max_rel": worst}
 
 
 def run_reference(args):
@@ -127,10 +183,11 @@ def run_reference(args):
     n = LATTICE * LATTICE + (LATTICE - 1) ** 2
     per_step = 2 * cores
     errors = seeded_errors(n, ERROR_RATE, per_step * (args.steps + args.warmup), SEED)
+    kind = _cpu_decoder()[0]
     rates, times = [], []
     for step in range(args.warmup + args.steps):
         chunk = errors[step * per_step:(step + 1) * per_step]
-        r, dt, done, _ = cpu_rate(chunk, cores)
+        r, dt, done, _, _ = cpu_rate(chunk, cores)
         if step >= args.warmup:
             rates.append(done)
             times.append(dt)
@@ -140,9 +197,11 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_step": per_step, "seed": SEED, "done_per_step": rates},
-        "cpu_baseline": {"value": total, "unit": "syndromes/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": total, "unit": "syndromes/s", "cores": cores, "kind": kind,
                          "sample": f"up to {per_step} seeded syndromes per step x {args.steps} steps (25 s cap "
-                                   f"per step), multiprocessing.Pool({cores}), one BLAS thread per worker"},
+                                   f"per step), " + ("the unmodified reference from oracle/_ref" if kind == "reference"
+                                                     else "numpy port of the reference algorithm")
+                                   + f", multiprocessing.Pool({cores}), one BLAS thread per worker"},
         "e2e": {"value": total, "unit": "syndromes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -230,6 +289,21 @@ def measure_fp64_peak(torch, device):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+def traffic_per_launch(kernel, n_nontrivial):
+    """DRAM bytes per launch of the dominant kernel from the `ncu --set full` capture of this round, if one has been
+    summarised under profiles/ (bytes per non-trivial syndrome x the syndromes of a launch); None otherwise -- the
+    bench never invents the number."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as fh:
+            doc = json.load(fh)
+        ent = doc.get(kernel)
+        if ent:
+            return ent["dram_bytes_per_nontrivial_syndrome"] * n_nontrivial, ent.get("source")
+    except (OSError, ValueError, KeyError):
+        pass
+    return None, None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -251,9 +325,17 @@ def run_ours(args):
     n = len(code)
     k = code.num_x_logicals() + code.num_z_logicals()
     n_sites = 2 * n + k
-    B = args.batch
     # contiguous shard of the seeded error list per rank (quantum_surface.py's generator, rank-offset)
-    errors = seeded_errors(n, ERROR_RATE, B, SEED, offset=rank * B)
+    if args.scaling == "strong":
+        from mdopt_b200.distributed import shard_bounds
+        lo, hi = shard_bounds(args.batch, rank, world)
+        B, total = hi - lo, args.batch
+        errors = seeded_errors(n, ERROR_RATE, B, SEED, offset=lo)
+    else:
+        B, total = args.batch, args.batch * world
+        errors = seeded_errors(n, ERROR_RATE, B, SEED, offset=rank * B)
+    mode = args.mode
+    mono = mode == "mono"
     nontriv = [e for e in errors if e != "I" * n]
     assert all("Z" not in e and "Y" not in e for e in nontriv)
     prog = schedule.build_decode_program(code, True, False, True, "Optimised")
@@ -266,7 +348,7 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     def step_device():
-        eng.decode_device(prog, d_syms, cut=CUT, bias_p=BIAS, renormalise=True, mode=args.mode, d_dist=d_dist,
+        eng.decode_device(prog, d_syms, cut=CUT, bias_p=BIAS, renormalise=True, mode=mode, d_dist=d_dist,
                           d_success=d_succ, d_status=d_stat)
 
     def barrier():
@@ -274,7 +356,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    fp64_peak = measure_fp64_peak(torch, device) if rank == 0 else 0.0
+    fp64_peak = measure_fp64_peak(torch, device) if (rank == 0 and not mono) else 0.0
 
     for _ in range(args.warmup):
         step_device()
@@ -297,20 +379,23 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     total_ms = float(t_dev.item())
+    status_dev = d_stat.cpu().numpy()
+    gpu_dist_dev = d_dist.cpu().numpy()
+    gpu_succ_dev = d_succ.cpu().numpy()
 
     # end-to-end through the public API: host strings in, host arrays out (pack + H2D + kernel + D2H)
+    kw = dict(chi_max=CHI_MAX, cut=CUT, bias_type="Bitflip", bias_prob=BIAS, contraction_strategy="Optimised",
+              mode=mode)
     for _ in range(max(1, min(args.warmup, 2))):
-        decode_css_batch(code, errors, chi_max=CHI_MAX, cut=CUT, bias_type="Bitflip", bias_prob=BIAS,
-                         contraction_strategy="Optimised", mode=args.mode)
+        decode_css_batch(code, errors, **kw)
     barrier()
     e2e_s = []
-    succ_host = None
+    succ_host = dist_host = None
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        dist_host, succ_host = decode_css_batch(code, errors, chi_max=CHI_MAX, cut=CUT, bias_type="Bitflip",
-                                                bias_prob=BIAS, contraction_strategy="Optimised", mode=args.mode)
+        dist_host, succ_host, stat_host = decode_css_batch(code, errors, return_status=True, **kw)
         torch.cuda.synchronize()
         e2e_s.append(time.perf_counter() - t0)
     barrier()
@@ -324,48 +409,76 @@ def run_ours(args):
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
-    status_bad = int((d_stat != 0).sum().item())
+    status_bad = int((status_dev != 0).sum()) + int((stat_host != 0).sum())
+    # the device-resident run and the host-API run decode the same strings: they must agree bit for bit
+    nt_idx = np.array([i for i, e in enumerate(errors) if e != "I" * n])
+    same_paths = bool(np.array_equal(gpu_dist_dev, dist_host[nt_idx]) and np.array_equal(gpu_succ_dev, succ_host[nt_idx]))
 
     if rank == 0:
-        value = world * B * args.steps / (total_ms * 1e-3)
-        e2e_value = world * B * args.steps / float(t_e2e.item())
-        flops = counters["flops_qr"] + counters["flops_jacobi"] + counters["flops_apply"]
+        value = total * args.steps / (total_ms * 1e-3)
+        e2e_value = total * args.steps / float(t_e2e.item())
         kernel_s = (sum(step_ms) / args.steps) * 1e-3
-        achieved = flops / kernel_s / 1e12
-        cpu = None
+        kernel = "mono_decode_kernel<64>" if mono else "decode_kernel<64>"
+        hbm_peak, hbm_src = hbm_peak_gbs()
+        if mono:
+            achieved_gbs = counters["bytes"] / kernel_s / 1e9
+            roof = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
+                    "note": "achieved = site records read + written per launch (10 bytes per (value, target) pair, "
+                            "counted by the kernel itself) / CUDA-event duration of the launch"}
+        else:
+            flops = counters["flops_qr"] + counters["flops_jacobi"] + counters["flops_apply"]
+            roof = roofline_head(flops / kernel_s / 1e12, fp64_peak, counters["bytes"] / kernel_s / 1e9)
+            roof["flops_per_launch"] = flops
+        traffic, traffic_src = traffic_per_launch(kernel, len(nontriv))
+        roof.update({"traffic": traffic, "traffic_source": traffic_src, "kernel": kernel,
+                     "algorithmic_bytes_per_launch": counters["bytes"],
+                     "algorithmic_bytes_per_nontrivial_syndrome": counters["bytes"] / max(len(nontriv), 1),
+                     "steps_per_launch": counters["steps"], "truncating_steps_per_launch": counters["truncating_steps"],
+                     "two_site_steps_per_s": counters["steps"] / kernel_s,
+                     "reference_algorithm_equiv_tflops": REF_FLOP_PER_NONTRIVIAL * len(nontriv) / kernel_s / 1e12})
+        cpu = parity = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline_subprocess()
+            lookup_idx = {e: i for i, e in reversed(list(enumerate(errors)))}
+
+            def gpu_lookup(err):
+                i = lookup_idx[err]
+                return dist_host[i], succ_host[i]
+
+            rows, canon = cpu.pop("rows", []), cpu.pop("rows_canonical", [])
+            parity = {"vs_cpu_arm": parity_report(rows, gpu_lookup),
+                      "vs_cpu_arm_with_canonical_tie_break": parity_report(canon, gpu_lookup),
+                      "device_resident_equals_host_api": same_paths,
+                      "note": "vs_cpu_arm: the timed CPU decodes (LAPACK tie-breaks; marginals differ inside the "
+                              "degenerate-truncation spread, DESIGN.md section 6); with the canonical tie-break at the "
+                              "SVD hook (oracle/structured_svd.py) the comparison is well-posed: 1e-10 is the bar"}
+        n_warps = getattr(eng, "n_warps", 0)
         line = {
             "metric": "decoded syndromes/sec", "value": value, "unit": "syndromes/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "nontrivial_per_gpu": len(nontriv), "seed": SEED,
-                       "mode": args.mode, "l2": "256 MB flush write between timed steps; per-step working set "
-                       f"{eng.ws_bytes / 1e6:.0f} MB > 126 MB L2", "n_ctas": eng.n_ctas},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "batch_total": total,
+                       "nontrivial_per_gpu": len(nontriv), "seed": SEED, "mode": mode,
+                       "l2": "256 MB flush write between timed steps; the resident MPS records ("
+                             + (f"{eng.mono_ws_bytes / 1e6:.0f}" if mono else f"{eng.ws_bytes / 1e6:.0f}")
+                             + " MB) exceed the 126 MB L2",
+                       "resident": {"warps": n_warps} if mono else {"ctas": eng.n_ctas}},
+            "nontrivial_rate": value * len(nontriv) / max(B, 1),
             "e2e": {"value": e2e_value, "unit": "syndromes/s", "h2d_bytes_per_step": int(syms.nbytes),
                     "d2h_bytes_per_step": int(len(nontriv) * ((1 << k) * 8 + 8))},
             "gpu_launches": args.steps,
-            "roofline": roofline_head(achieved, fp64_peak, counters["bytes"] / kernel_s / 1e9) | {
-                         "traffic": DRAM_BYTES_PER_NONTRIVIAL * len(nontriv),
-                         "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/ (85 MB per "
-                                         "non-trivial syndrome; the algorithmic site-tensor bytes are a little higher, "
-                                         "L2 absorbs the rest)",
-                         "kernel": "decode_kernel<64>", "note": "achieved = the kernel's own counters per launch "
-                         "(site-tensor bytes read + written, or FLOPs) / CUDA-event duration; FP64 peak = cuBLAS "
-                         "DGEMM 8192^3 measured in this run", "flops_per_launch": flops,
-                         "flops_split": {k2: counters[k2] for k2 in ("flops_qr", "flops_jacobi", "flops_apply")},
-                         "algorithmic_bytes_per_launch": counters["bytes"],
-                         "achieved_gbs": counters["bytes"] / kernel_s / 1e9,
-                         "steps_per_launch": counters["steps"], "truncating_steps": counters["truncating_steps"],
-                         "cycle_split": {k2: counters[k2] for k2 in counters if k2.startswith("cyc_")},
-                         "qr_reflectors": counters["qr_reflectors"], "jacobi_sweeps": counters["jacobi_sweeps"],
-                         "reference_algorithm_equiv_tflops": REF_FLOP_PER_NONTRIVIAL * len(nontriv) / kernel_s / 1e12},
+            "roofline": roof,
             "clocks": sampler.summary(),
             "counts": {"decoded": int(counts[0]), "success": int(counts[1]), "nan": int(counts[2]),
-                       "status_not_ok_rank0": status_bad},
+                       "status_not_ok_rank0": status_bad,
+                       "dense_fallbacks_rank0": int(getattr(eng, "last_mono_fallbacks", 0))},
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if parity:
+            line["parity"] = parity
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -377,9 +490,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="syndromes per GPU per step")
-    ap.add_argument("--mode", default="svd", choices=["fast", "svd", "svd-gram"],
-                    help="svd (default): the reference algorithm with the orthogonality fast path; fast: QR steps")
+    ap.add_argument("--batch", type=int, default=CONFIG2_BATCH,
+                    help="syndromes per step: per GPU (weak scaling) or in total (--scaling strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every GPU decodes its own --batch shard; strong: ONE --batch sharded over the GPUs")
+    ap.add_argument("--mode", default="mono", choices=["mono", "fast", "svd", "svd-gram"],
+                    help="mono (default): the monomial warp engine; svd / svd-gram / fast: the dense CTA engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

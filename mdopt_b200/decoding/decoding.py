@@ -157,35 +157,45 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
     dist = np.zeros((B, 1 << k))
     success = np.zeros(B, dtype=np.int32)
     status = np.zeros(B, dtype=np.int32)
-    groups: Dict[Tuple[bool, bool, int], List[int]] = {}
+    # whole-batch character tests (decoding.py:1225-1231: trivial / "X" in error / "Z" in error), no per-string Python
+    raw = schedule.pack_errors(errors, n)
+    trivial = (raw == ord("I")).all(axis=1)
+    has_x = (raw == ord("X")).any(axis=1)
+    has_z = (raw == ord("Z")).any(axis=1)
+    erased = (raw == ord("E")).any(axis=1)
+    dist[trivial, 0], success[trivial] = 1.0, 1
     default_mask = (1 << k) - 1
-    for b, err in enumerate(errors):
-        if len(err) != n:
-            raise ValueError(f"The error length is {2 * len(err)}, expected {2 * n}.")
-        trivial, has_x, has_z = schedule.error_flags(err)
-        if trivial:
-            dist[b, 0], success[b] = 1.0, 1
-        else:
-            mask = schedule.readout_kept_mask(err, k) if "E" in err else default_mask
-            groups.setdefault((has_x, has_z, mask), []).append(b)
+    groups: Dict[Tuple[bool, bool, int], np.ndarray] = {}
+    plain = ~trivial & ~erased
+    for hx in (False, True):
+        for hz in (False, True):
+            idx = np.nonzero(plain & (has_x == hx) & (has_z == hz))[0]
+            if idx.size:
+                groups[(hx, hz, default_mask)] = idx
+    by_mask: Dict[Tuple[bool, bool, int], List[int]] = {}
+    for b in np.nonzero(~trivial & erased)[0]:
+        by_mask.setdefault((bool(has_x[b]), bool(has_z[b]), schedule.readout_kept_mask(errors[b], k)), []).append(int(b))
+    for key, rows in by_mask.items():
+        rows = np.asarray(rows)
+        groups[key] = np.sort(np.concatenate([groups[key], rows])) if key in groups else rows
     if not groups:
         return (dist, success, status) if return_status else (dist, success)
     # the constraint groups stay gated by the characters of the ORIGINAL error (decoding.py:1230-1231 run before
     # the multiplication at :1237-1240); only the product state sees the multiplied string
-    state_errors = errors
+    state_raw = raw
     if multiply_by_stabiliser:
         stabs_x, stabs_z = css_code_stabilisers(code)
-        state_errors = _state_errors(errors, stabs_x + stabs_z, rng)
+        state_raw = schedule.pack_errors(_state_errors(errors, stabs_x + stabs_z, rng), n)
     eng = engine.get_engine(n_sites, k, _effective_chi(chi_max, n_sites))
-    for (has_x, has_z, mask), idx in groups.items():
-        prog = _program_for(code, has_x, has_z, renormalise, contraction_strategy, orders, bias_type, bias_prob)
-        syms = schedule.symbols_from_errors([state_errors[b] for b in idx], k)
+    for (hx, hz, mask), idx in groups.items():
+        prog = _program_for(code, hx, hz, renormalise, contraction_strategy, orders, bias_type, bias_prob)
+        syms = schedule.symbols_from_raw(state_raw[idx], k)
         d, s, st = eng.decode_host(prog, syms, cut=cut, bias_p=(-1.0 if depol else bias_prob),
                                    renormalise=renormalise, mode=mode,
                                    kept_mask=(0 if mask == default_mask else mask))
         dist[idx], success[idx], status[idx] = d, s, st
         if not silent:
-            logging.info("decoded %d syndromes with flags X=%s Z=%s", len(idx), has_x, has_z)
+            logging.info("decoded %d syndromes with flags X=%s Z=%s", len(idx), hx, hz)
     return (dist, success, status) if return_status else (dist, success)
 
 

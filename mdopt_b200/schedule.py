@@ -268,33 +268,43 @@ def readout_kept_mask(error: str, n_logical: int) -> int:
     return mask
 
 
+_LUT = np.zeros((256, 2), dtype=np.uint8)
+_VALID = np.zeros(256, dtype=bool)
+for _ch, _bits in _PAULI_BITS.items():
+    _LUT[ord(_ch)] = _bits
+    _VALID[ord(_ch)] = True
+
+
+def pack_errors(errors: Sequence[str], n: int) -> np.ndarray:
+    """uint8 [B, n] array of the Pauli characters of a batch of error strings, validated like the reference does
+    (length: decoding.py:1249-1252, characters: :318).  One buffer for the whole batch: the per-string work of a
+    100k-syndrome batch must stay out of Python loops."""
+    B = len(errors)
+    lengths = set(map(len, errors))
+    if lengths - {n}:
+        bad = next(e for e in errors if len(e) != n)
+        raise ValueError(f"The error length is {2 * len(bad)}, expected {2 * n}.")
+    try:
+        raw = np.frombuffer("".join(errors).encode("ascii"), dtype=np.uint8).reshape(B, n)
+    except UnicodeEncodeError:
+        bad = next(ch for e in errors for ch in e if ord(ch) > 127)
+        raise ValueError(f"Invalid Pauli encountered -- {bad}.") from None
+    ok = _VALID[raw]
+    if not ok.all():
+        b, q = np.argwhere(~ok)[0]
+        raise ValueError(f"Invalid Pauli encountered -- {errors[b][q]}.")
+    return raw
+
+
+def symbols_from_raw(raw: np.ndarray, n_logical: int) -> np.ndarray:
+    """uint8 [B, k + 2n] product-state symbols from packed Pauli characters: '+' on the logical sites, then the bits."""
+    B, n = raw.shape
+    out = np.empty((B, n_logical + 2 * n), dtype=np.uint8)
+    out[:, :n_logical] = SYM_PLUS
+    out[:, n_logical:] = _LUT[raw].reshape(B, 2 * n)
+    return out
+
+
 def symbols_from_errors(errors: Sequence[str], n_logical: int) -> np.ndarray:
     """uint8 [B, k + 2n] product-state symbols: '+' on the logical sites, then the Pauli bits."""
-    n = len(errors[0])
-    B = len(errors)
-    out = np.full((B, n_logical + 2 * n), SYM_PLUS, dtype=np.uint8)
-    lut = np.zeros((256, 2), dtype=np.uint8)
-    valid = np.zeros(256, dtype=bool)
-    for ch, bits in _PAULI_BITS.items():
-        lut[ord(ch)] = bits
-        valid[ord(ch)] = True
-    for err in errors:
-        if len(err) != n:
-            raise ValueError(f"The error length is {2 * len(err)}, expected {2 * n}.")
-    try:  # one buffer for the whole batch (the per-string path below reports the offending character)
-        raw = np.frombuffer("".join(errors).encode("ascii"), dtype=np.uint8).reshape(B, n)
-    except (UnicodeEncodeError, ValueError):
-        raw = None
-    if raw is not None and valid[raw].all():
-        out[:, n_logical:] = lut[raw].reshape(B, 2 * n)
-        return out
-    for b, err in enumerate(errors):
-        try:
-            row = np.frombuffer(err.encode("ascii"), dtype=np.uint8)
-        except UnicodeEncodeError:
-            raise ValueError(f"Invalid Pauli encountered -- {err}.") from None
-        if not valid[row].all():
-            bad = err[int(np.argmin(valid[row]))]
-            raise ValueError(f"Invalid Pauli encountered -- {bad}.")
-        out[b, n_logical:] = lut[row].reshape(-1)
-    return out
+    return symbols_from_raw(pack_errors(errors, len(errors[0])), n_logical)

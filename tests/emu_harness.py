@@ -46,7 +46,8 @@ def decode(program: schedule.Program, symbols, chi_max, cut, bias_p, renormalise
            trace_max=0, rank_tol=_abi.DEFAULT_RANK_TOL, kept_mask=0, readout=(1e-9, 1e-12), mono=False, cap=None):
     """``mono=True`` runs the monomial (warp-per-syndrome) engine of mono_core.cuh instead of the dense one."""
     if cap is None:
-        cap = _abi.chi_capacity(max(chi_max, 1, 1 if mono else _abi.readout_min_capacity(program.n_logical)))
+        cap = (_abi.mono_chi_capacity(max(chi_max, 1)) if mono else
+               _abi.chi_capacity(max(chi_max, 1, _abi.readout_min_capacity(program.n_logical))))
     B = symbols.shape[0]
     ncls = 1 << program.n_logical
     stride = (4 + 2 * cap) if trace_max else 0
