@@ -146,7 +146,7 @@ int mdopt_mono_num_warps(int chi_cap) {
 size_t mdopt_mono_workspace_bytes(int chi_cap, int n_sites, int n_warps) {
   const mdopt::MonoOps* ops = mono_ops_for(chi_cap);
   if (!ops || n_sites <= 0 || n_warps <= 0) return 0;
-  return ops->ws_bytes_per_warp(n_sites) * (size_t)n_warps + 256;
+  return ops->ws_bytes_per_warp(n_sites) * (size_t)n_warps + 256 + 64 * 160;   // + work counter + tensor tables
 }
 
 int mdopt_mono_decode_batch_device(const mdopt_decode_desc* desc, int chi_cap, int n_warps, const int32_t* program,

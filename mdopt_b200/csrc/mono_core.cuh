@@ -33,8 +33,15 @@
 #define MW_SYNC() ((void)0)
 #define MW_ANY(x) (x)
 #define MW_LANE0 if (true)
+#define MW_PHASE inline
 #else
-#define MW_FOR(i, n) for (int i = (int)(threadIdx.x & 31u); i < (n); i += 32)
+// Engine phases are NOT inlined: inside a function the compiler knows the warp entered converged, so the shuffles
+// of the reductions are plain SHFLs; inlined into the program interpreter's data-dependent control flow every one
+// of them carried a WARPSYNC.COLLECTIVE / ENDCOLLECTIVE pair.
+#define MW_PHASE __device__ __noinline__
+// lane loops are NOT unrolled: trip counts are <= 2*chi/32, and the unrolled copies (4x + remainder per loop) made the
+// hot code of a step larger than the 32 KB L1.5 instruction cache
+#define MW_FOR(i, n) _Pragma("unroll 1") for (int i = (int)(threadIdx.x & 31u); i < (n); i += 32)
 #define MW_SYNC() __syncwarp()
 #define MW_ANY(x) __any_sync(0xffffffffu, (x))
 #define MW_LANE0 if ((threadIdx.x & 31u) == 0)
@@ -53,38 +60,89 @@ struct MonoSite {
   int16_t tgt[2 * CHI];
 };
 
+// One MPO site tensor (vL, vR, pU, pD), vL, vR <= 2, as the engine reads it: its non-zeros per (incoming bond q,
+// outgoing physical pd), idx = q*2 + pd -- at most two (w', pU, value) entries (one for XOR / SWAP / IDENTITY, two
+// for COPY_LEFT); en = 3 marks a tensor the monomial form cannot take.  Built once per launch (mono_build_tables).
+struct MonoTensor {
+  double ew[4][2];
+  int en[4];
+  int ewo[4][2], epu[4][2];
+  int vl, vr, iso, pad;
+};
+
+MD_HD void mono_build_tensor(const double* w16, const int* dim4, MonoTensor* out) {
+  const int vl = dim4[0], vr = dim4[1];
+  out->vl = vl; out->vr = vr; out->iso = dim4[2]; out->pad = 0;
+  for (int idx = 0; idx < 4; ++idx) {
+    const int q = idx >> 1, pd = idx & 1;
+    int n = 0;
+    for (int e = 0; e < 2; ++e) { out->ew[idx][e] = 0.0; out->ewo[idx][e] = 0; out->epu[idx][e] = 0; }
+    if (q < vl && vl <= 2 && vr <= 2 && dim4[3] == 0) {
+      for (int wo = 0; wo < vr; ++wo)
+        for (int pu = 0; pu < 2; ++pu) {
+          const double w = w16[((q * vr + wo) * 2 + pu) * 2 + pd];
+          if (w == 0.0) continue;
+          if (n < 2) { out->ew[idx][n] = w; out->ewo[idx][n] = wo; out->epu[idx][n] = pu; }
+          ++n;
+        }
+    } else if (q < vl) {
+      n = 3;   // two-site gate entries (dim4[3] != 0) or oversized bonds: not a monomial MPO tensor
+    }
+    out->en[idx] = n > 2 ? 3 : n;
+  }
+}
+// slot 0 = the identity MPO tensor of a centre move, slot 1 + t = tensor t of the program's table
+MD_HD void mono_build_identity(MonoTensor* out) {
+  const double w[16] = {1.0, 0.0, 0.0, 1.0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const int dim[4] = {1, 1, 1, 0};
+  mono_build_tensor(w, dim, out);
+}
+
+struct MonoCounters {
+  double bytes_hbm, n_steps, n_trunc, n_fallback;
+};
+
+// Warp-uniform engine state.  It lives in shared memory (like the dense engine's EngineState) so that the phases can
+// be separate functions without a per-thread stack object.
+template <int CHI>
+struct MonoState {
+  MonoSite<CHI>* sites;     // [n_sites] this warp's MPS (global)
+  int* bd;                  // [n_sites + 1] bond dimensions (global)
+  const MonoTensor* tabs;   // [1 + n_tensors]
+  double* trace;
+  DecodeParams P;
+  MonoCounters cnt;
+  int n_traced, status, centre, K, Wq, Mr, mirrored;
+};
+
 // Per-warp shared memory.
 template <int CHI>
 struct MonoSmem {
   static constexpr int N2 = 2 * CHI;
   // carried matrix, row-singleton form: row r = (k, p') has its only entry cv[r] in column cc[r] (-1: empty row)
   double cv[N2];
-  // per column: squared entry of the row with p = 0 / p = 1 that hits it; reused as 64-bit sort keys
+  // per column: squared entry of the row with p = 0 / p = 1 that hits it; acc[1] is reused for the 64-bit sort keys,
+  // acc[0] for sigma^2 and then 1 / sigma of the kept columns
   double acc[2][N2];
   double sig[N2];        // sigma per column
   double sv[N2];         // staged next site, frame view: rows (m, p) -> (st, sv)
-  double uv[N2];         // outgoing U record (values), also the marginal chain's vector
+  double uv[N2];         // outgoing record in the mirrored frame (values)
   int16_t cc[N2];
-  int16_t own[2][N2];    // k of the row with p = 0 / 1 that hits the column, -1 none
+  int16_t own[2][N2];    // k of the row with p = 0 / 1 that hits the column, -1 none; then the cluster flags
   int16_t rank[N2];      // new bond index of a column, -1 dropped
   int16_t order[N2];     // column at sorted position
   int16_t st[N2];
   int16_t ut[N2];
-  double W[16];          // current MPO tensor (vL, vR, pU, pD)
-  double red[4];
-};
-
-struct MonoCounters {
-  double bytes_hbm, n_steps, n_trunc, n_fallback;
+  MonoState<CHI> state;
 };
 
 #ifndef MDOPT_EMU
-__device__ __forceinline__ double mw_sum(double v) {
+static __device__ __noinline__ double mw_sum(double v) {
 #pragma unroll
   for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
   return v;
 }
-__device__ __forceinline__ double mw_max(double v) {
+static __device__ __noinline__ double mw_max(double v) {
 #pragma unroll
   for (int off = 16; off; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
   return v;
@@ -98,48 +156,76 @@ inline int mw_isum(int v) { return v; }
 
 // -------------------------------------------------------------------------------------------------
 // Sort n 64-bit keys (shared memory, n <= NMAX = 32*EPL) in DESCENDING order, in place.
-// Device: bitonic network, EPL keys per lane in registers (element e = lane*EPL + j, so the two smallest strides
-// stay inside a lane and the others are one 64-bit shuffle each).  Host: std::sort.  Keys are unique or zero.
+// Device: bitonic network with EPL keys per lane in registers (element e = lane*EPL + j), written as LOOPS over the
+// merge sizes and strides: the merge of size S first pairs e with its mirror e ^ (S-1), then with e ^ t for
+// t = S/4 ... 1, so every comparator points the same way (the lower element keeps the larger key).  Strides below
+// EPL stay inside a lane, the others are one 64-bit shuffle per key.  The code of one variant is ~2 KB: with 24
+// independent warps per SM the instruction caches (6 KB L0 per scheduler, 32 KB L1.5) decide the speed of this
+// kernel, and the fully unrolled network (16 KB per variant) made `no_instruction` the top stall.
+// Not inlined: inside the function the warp is known to be converged, so every shuffle is a plain SHFL.
+// Host: std::sort.  Keys are unique or zero.
 // -------------------------------------------------------------------------------------------------
 #ifndef MDOPT_EMU
-// (not inlined: inside the function the warp is known to be converged, so every shuffle is a plain SHFL; inlined
-// into the engine's data-dependent control flow each one would carry a WARPSYNC.COLLECTIVE)
+template <int EPL>
+__device__ __forceinline__ void mw_sort_inlane(unsigned long long (&k)[EPL], int tmax) {
+  // comparators e ^ t for t = tmax, tmax/2, ..., 1 (all < EPL): pairs (j, j | t), the lower index keeps the maximum
+#pragma unroll
+  for (int t = EPL >> 1; t > 0; t >>= 1) {
+    if (t <= tmax) {
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {
+        if ((j & t) == 0) {
+          const unsigned long long a = k[j], b = k[j | t];
+          const bool sw = a < b;
+          k[j] = sw ? b : a; k[j | t] = sw ? a : b;
+        }
+      }
+    }
+  }
+}
+
 template <int EPL>
 __device__ __noinline__ void mw_sort_desc_impl(unsigned long long* keys, int n) {
   const int lane = threadIdx.x & 31;
   unsigned long long k[EPL];
 #pragma unroll
   for (int j = 0; j < EPL; ++j) { const int e = lane * EPL + j; k[j] = (e < n) ? keys[e] : 0ull; }
-  constexpr int N = 32 * EPL;
+  // merges that stay inside a lane (S <= EPL): mirror stage j ^ (S-1), then strides S/4 ... 1
 #pragma unroll
-  for (int size = 2; size <= N; size <<= 1) {
+  for (int S = 2; S <= EPL; S <<= 1) {
 #pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (stride < EPL) {
-#pragma unroll
-        for (int j = 0; j < EPL; ++j) {
-          if ((j & stride) == 0) {
-            const int e = lane * EPL + j;
-            const bool desc = ((e & size) == 0);   // descending blocks first -> whole array descending at size == N
-            const unsigned long long a = k[j], b = k[j | stride];
-            const bool sw = desc ? (a < b) : (a > b);
-            k[j] = sw ? b : a; k[j | stride] = sw ? a : b;
-          }
-        }
-      } else {
-        const int lm = stride / EPL;
-#pragma unroll
-        for (int j = 0; j < EPL; ++j) {
-          const int e = lane * EPL + j;
-          const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[j], lm);
-          const bool lower = ((lane & lm) == 0);
-          const bool desc = ((e & size) == 0);
-          // the lower element of the pair keeps the larger key in a descending block
-          const bool take_max = (lower == desc);
-          k[j] = take_max ? (k[j] > o ? k[j] : o) : (k[j] < o ? k[j] : o);
-        }
+    for (int j = 0; j < EPL; ++j) {
+      const int o = j ^ (S - 1);
+      if (j < o) {
+        const unsigned long long a = k[j], b = k[o];
+        const bool sw = a < b;
+        k[j] = sw ? b : a; k[o] = sw ? a : b;
       }
     }
+    mw_sort_inlane<EPL>(k, S >> 2);
+  }
+  // merges across lanes: S = 2*EPL ... 32*EPL
+#pragma unroll 1
+  for (int sl = 2; sl <= 32; sl <<= 1) {       // sl = S / EPL
+    {  // mirror stage: partner lane = lane ^ (sl - 1), partner key index = EPL-1-j
+      const bool keep_max = (lane & (sl >> 1)) == 0;
+      unsigned long long o[EPL];
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) o[j] = __shfl_xor_sync(0xffffffffu, k[EPL - 1 - j], sl - 1);
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) { const bool gt = k[j] > o[j]; k[j] = (gt == keep_max) ? k[j] : o[j]; }
+    }
+#pragma unroll 1
+    for (int lm = sl >> 2; lm > 0; lm >>= 1) {   // strides t = lm * EPL >= EPL
+      const bool keep_max = (lane & lm) == 0;
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[j], lm);
+        const bool gt = k[j] > o;
+        k[j] = (gt == keep_max) ? k[j] : o;
+      }
+    }
+    mw_sort_inlane<EPL>(k, EPL >> 1);
   }
 #pragma unroll
   for (int j = 0; j < EPL; ++j) { const int e = lane * EPL + j; if (e < n) keys[e] = k[j]; }
@@ -163,42 +249,23 @@ inline void mw_sort_desc(unsigned long long* keys, int n) {
 #endif
 
 // -------------------------------------------------------------------------------------------------
-// The per-warp engine.  Scalars are warp-uniform and live in registers.
+// The per-warp engine: free functions over the warp's shared memory.
 // -------------------------------------------------------------------------------------------------
 template <int CHI>
-struct MonoEngine {
+struct Mono {
   static constexpr int N2 = 2 * CHI;
-  MonoSmem<CHI>& s;
-  MonoSite<CHI>* sites;     // [n_sites] this warp's MPS (global)
-  int* bd;                  // [n_sites + 1] bond dimensions (global)
-  const double* wtab;
-  const int* wdim;
-  double* trace;
-  DecodeParams P;
-  MonoCounters cnt;
-  int n_traced, status, centre, K, Wq, Mr, mirrored;
+  using SM = MonoSmem<CHI>;
 
-  MD_DEV MonoEngine(MonoSmem<CHI>& sm) : s(sm) {}
-
-  MD_DEV int phys(int j) const { return mirrored ? (P.n_sites - 1 - j) : j; }
-  MD_DEV int dim_left(int j) const { int p = phys(j); return mirrored ? bd[p + 1] : bd[p]; }
-  MD_DEV int dim_right(int j) const { int p = phys(j); return mirrored ? bd[p] : bd[p + 1]; }
-  MD_DEV void set_dim_right(int j, int v) { int p = phys(j); MW_LANE0 { if (mirrored) bd[p] = v; else bd[p + 1] = v; } MW_SYNC(); }
-
-  MD_DEV void load_w(int tid) {
-    MW_FOR(i, 16) { s.W[i] = (tid < 0) ? ((i == 0 || i == 3) ? 1.0 : 0.0) : wtab[tid * 16 + i]; }
-    MW_SYNC();
-  }
-  MD_DEV int w_vl(int tid) const { return tid < 0 ? 1 : wdim[tid * 4 + 0]; }
-  MD_DEV int w_vr(int tid) const { return tid < 0 ? 1 : wdim[tid * 4 + 1]; }
-  MD_DEV int w_iso(int tid) const { return tid < 0 ? 1 : wdim[tid * 4 + 2]; }
-  MD_DEV double w_at(int vr, int q, int wo, int pu, int pd) const { return s.W[((q * vr + wo) * 2 + pu) * 2 + pd]; }
+  // ---- frame helpers: logical site j of the current frame ----
+  static MD_DEV int phys(const SM& s, int j) { return s.state.mirrored ? (s.state.P.n_sites - 1 - j) : j; }
+  static MD_DEV int dim_left(const SM& s, int j) { const int p = phys(s, j); return s.state.mirrored ? s.state.bd[p + 1] : s.state.bd[p]; }
+  static MD_DEV int dim_right(const SM& s, int j) { const int p = phys(s, j); return s.state.mirrored ? s.state.bd[p] : s.state.bd[p + 1]; }
 
   // ---- stage site j in the frame view: rows (a, p) -> (s.st, s.sv), a < dim_left(j) ----
-  MD_DEV void load_site(int j) {
-    const MonoSite<CHI>& src = sites[phys(j)];
-    const int A = dim_left(j), B = dim_right(j);
-    if (!mirrored) {
+  static MD_DEV void load_site(SM& s, int j) {
+    const MonoSite<CHI>& src = s.state.sites[phys(s, j)];
+    const int A = dim_left(s, j), B = dim_right(s, j), mir = s.state.mirrored;
+    if (!mir) {
       MW_FOR(r, 2 * A) { s.sv[r] = src.val[r]; s.st[r] = src.tgt[r]; }
     } else {
       // the stored tensor has dims (B, 2, A): rows (b, p) -> a.  Invert per p (unique writers: p-monomial).
@@ -209,69 +276,72 @@ struct MonoEngine {
         if (t >= 0) { const int o = t * 2 + (r & 1); s.st[o] = (int16_t)(r >> 1); s.sv[o] = src.val[r]; }
       }
     }
-    cnt.bytes_hbm += 10.0 * 2 * (mirrored ? B : A);
+    MW_LANE0 { s.state.cnt.bytes_hbm += 10.0 * 2 * (mir ? B : A); }
     MW_SYNC();
   }
 
   // ---- new carried row from entry (q, m) of the coefficient side, output physical index pd, factor f:
   //      sum over (w', pu) of f * W(q, w', pu, pd) * A[m, pu, .] must live in a single column ----
-  MD_DEV bool gather_row(int vr, int Bn, int q, int m, int pd, double f, int* col_out, double* val_out) const {
-    int col = -1; double val = 0.0; bool ok = true;
-    for (int wo = 0; wo < vr; ++wo)
-      for (int pu = 0; pu < 2; ++pu) {
-        const double w = w_at(vr, q, wo, pu, pd);
-        if (w == 0.0) continue;
-        const int t = s.st[m * 2 + pu];
-        if (t < 0) continue;
-        const int c = wo * Bn + t;
-        if (col >= 0 && c != col) ok = false;
-        col = c;
-        val += (f * w) * s.sv[m * 2 + pu];
-      }
+  static MD_DEV bool gather_row(const SM& s, const MonoTensor& T, int Bn, int q, int m, int pd, double f,
+                                int* col_out, double* val_out) {
+    const int idx = q * 2 + pd;
+    const int n = T.en[idx];
+    int col = -1; double val = 0.0; bool ok = (n <= 2);
+    for (int e = 0; e < n && e < 2; ++e) {
+      const int r = m * 2 + T.epu[idx][e];
+      const int t = s.st[r];
+      if (t < 0) continue;
+      const int c = T.ewo[idx][e] * Bn + t;
+      if (col >= 0 && c != col) ok = false;
+      col = c;
+      val += (f * T.ew[idx][e]) * s.sv[r];
+    }
     *col_out = col; *val_out = val;
     return ok;
   }
 
   // ---- carried <- site j with the first MPO tensor applied (contractor.py:276-291, first half) ----
-  MD_DEV void carried_from_site(int j, int tid) {
-    load_w(tid);
-    const int A = dim_left(j), B = dim_right(j), vr = w_vr(tid);
-    load_site(j);
-    int bad = 0;
+  static MW_PHASE void carried_from_site(SM& s, int j, int tid) {
+    const MonoTensor& T = s.state.tabs[tid + 1];
+    const int A = dim_left(s, j), B = dim_right(s, j), vr = T.vr;
+    load_site(s, j);
+    int bad = (T.vl != 1);
     // rows (k, p') of the carried matrix; columns (q, m) = q*B + m
     MW_FOR(r, 2 * A) {
       int col; double val;
-      if (!gather_row(vr, B, 0, r >> 1, r & 1, 1.0, &col, &val)) bad = 1;
+      if (!gather_row(s, T, B, 0, r >> 1, r & 1, 1.0, &col, &val)) bad = 1;
       s.cv[r] = val; s.cc[r] = (int16_t)col;
     }
-    if (MW_ANY(bad)) status = ST_NOT_MONOMIAL;
-    K = A; Wq = vr; Mr = B;
+    bad = MW_ANY(bad);
+    s.state.K = A; s.state.Wq = vr; s.state.Mr = B;
+    if (bad) s.state.status = ST_NOT_MONOMIAL;
     MW_SYNC();
   }
 
   // ---- one two-site step: absorb site jn (frame index) with MPO tensor tid ----
-  MD_DEV void step(int jn, int tid, int chi_lim, double cut, int is_move, int renorm_sv) {
-    const int vl = w_vl(tid), vr = w_vr(tid), iso = w_iso(tid);
-    const int Bn = dim_right(jn);
+  static MW_PHASE void step(SM& s, int jn, int tid, int chi_lim, double cut, int is_move, int renorm_sv) {
+    const MonoTensor& T = s.state.tabs[tid + 1];
+    const int vl = T.vl, vr = T.vr, iso = T.iso;
+    const int K = s.state.K, Wq = s.state.Wq, Mr = s.state.Mr, mir = s.state.mirrored;
+    const int Bn = dim_right(s, jn);
     const int R = K * 2;
     int C = Wq * Mr;
-    load_w(tid);
-    if (vl != Wq || dim_left(jn) != Mr) { status = ST_CAPACITY; return; }
-    load_site(jn);
+    if (vl != Wq || dim_left(s, jn) != Mr) { s.state.status = ST_CAPACITY; MW_SYNC(); return; }
+    load_site(s, jn);
     int bad = 0;
     if (!iso) {
       // theta = Mmat . T formed explicitly (contractor.py:328-342): row (k, r) keeps one entry, now in column
       // (p', w', m') = (p'*vr + w')*Bn + m'
-      if (2 * vr * Bn > N2) { status = ST_CAPACITY; return; }
+      if (2 * vr * Bn > N2) { s.state.status = ST_CAPACITY; MW_SYNC(); return; }
       MW_FOR(r, R) {
         const int c = s.cc[r];
         if (c < 0) continue;
-        const int q = c / Mr, m = c - q * Mr;
+        const int q = (c >= Mr) ? 1 : 0, m = c - q * Mr;   // MPO bonds are <= 2
         const double v = s.cv[r];
         int col = -1; double val = 0.0;
         for (int pd = 0; pd < 2; ++pd) {
           int c1; double v1;
-          if (!gather_row(vr, Bn, q, m, pd, v, &c1, &v1)) bad = 1;
+          if (!gather_row(s, T, Bn, q, m, pd, v, &c1, &v1)) bad = 1;
           if (c1 < 0) continue;
           c1 += pd * vr * Bn;
           if (col >= 0 && c1 != col) bad = 1;
@@ -291,15 +361,16 @@ struct MonoEngine {
     }
     MW_SYNC();
     MW_FOR(r, R) { const int c = s.cc[r]; if (c >= 0 && s.own[r & 1][c] != (r >> 1)) bad = 1; }
-    if (MW_ANY(bad)) { status = ST_NOT_MONOMIAL; return; }
-    // sigma^2, first supporting row, largest sigma^2; the sort keys go into acc[1] (viewed as 64-bit integers)
+    if (MW_ANY(bad)) { s.state.status = ST_NOT_MONOMIAL; MW_SYNC(); return; }
+    // sigma^2, sigma, first supporting row, largest sigma^2; the sort keys go into acc[1] (viewed as 64-bit integers)
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(s.acc[1]);
     double mx = 0.0;
     MW_FOR(c, C) {
       const double n2 = s.acc[0][c] + s.acc[1][c];
       const int o0 = s.own[0][c], o1 = s.own[1][c];
       const int first = (o0 >= 0 && (o1 < 0 || 2 * o0 < 2 * o1 + 1)) ? 2 * o0 : ((o1 >= 0) ? 2 * o1 + 1 : (int)MONO_ROW_MASK);
-      s.sig[c] = n2;          // squared for now
+      s.acc[0][c] = n2;       // sigma^2 (each column is handled by one lane: no hazard with the read above)
+      s.sig[c] = sqrt(n2);
       mx = fmax(mx, n2);
       unsigned long long kb;
 #ifdef MDOPT_EMU
@@ -315,19 +386,19 @@ struct MonoEngine {
     // truncation count (utils.py:119): #(sigma > cut) among the numerically non-zero columns
     int cnt_keep = 0, cnt_nz = 0;
     MW_FOR(c, C) {
-      const double n2 = s.sig[c];
-      const double v = sqrt(n2);
-      cnt_keep += (v > cut && n2 > floor2) ? 1 : 0;
+      const double n2 = s.acc[0][c];
+      cnt_keep += (s.sig[c] > cut && n2 > floor2) ? 1 : 0;
       cnt_nz += (n2 > 0.0) ? 1 : 0;
     }
     cnt_keep = mw_isum(cnt_keep);
     const int nnz = mw_isum(cnt_nz);
     int Knew = cnt_keep < chi_lim ? cnt_keep : chi_lim;
-    // ---- canonical order: sort by (sigma^2, first row), cluster, sort by (cluster, first row) ----
+    // ---- canonical order: sort by (sigma^2, first row); values within the tie width of their predecessor (chained)
+    //      form one cluster; inside a cluster the order is by first supporting row ----
     mw_sort_desc<N2>(keys, C);
-    // cluster starts: position p opens a cluster when its value drops below the previous one by more than the tie width
+    int multi = 0;
     MW_FOR(p, nnz) {
-      int flag = 1;
+      int flag = 1;   // position p opens a cluster
       if (p > 0) {
         double a, b;
         const unsigned long long ka = keys[p - 1] & ~MONO_ROW_MASK, kb = keys[p] & ~MONO_ROW_MASK;
@@ -338,53 +409,58 @@ struct MonoEngine {
 #endif
         flag = (b < a * (1.0 - MONO_TIE_REL2)) ? 1 : 0;
       }
-      s.rank[p] = (int16_t)flag;   // scratch: the ranks are written further down
+      s.own[0][p] = (int16_t)flag;   // own[] is free after the structure check
+      multi |= !flag;
     }
-    MW_SYNC();
-    unsigned long long* keys2 = reinterpret_cast<unsigned long long*>(s.acc[0]);   // acc[0] is free: sigma^2 sits in s.sig
-    MW_FOR(p, nnz) {
-      int st0 = p;
-      while (!s.rank[st0]) --st0;
-      keys2[p] = ((unsigned long long)(N2 - st0) << MONO_ROW_BITS) | (keys[p] & MONO_ROW_MASK);
-    }
-    mw_sort_desc<N2>(keys2, nnz);
-    // order[pos] = column, rank[column] = pos (kept) or -1
+    multi = MW_ANY(multi);
     MW_FOR(c, C) s.rank[c] = -1;
     MW_SYNC();
     double kept2 = 0.0, err2 = 0.0;
     MW_FOR(p, nnz) {
-      const int first = (int)(MONO_ROW_MASK - (keys2[p] & MONO_ROW_MASK));
-      const int c = s.cc[first];
-      s.order[p] = (int16_t)c;
-      const double n2 = s.sig[c];
-      if (p < Knew) { s.rank[c] = (int16_t)p; kept2 += n2; } else err2 += n2;
-    }
-    kept2 = mw_sum(kept2); err2 = mw_sum(err2);
-    MW_SYNC();
-    MW_FOR(c, C) s.sig[c] = sqrt(s.sig[c]);
-    MW_SYNC();
-    if (trace != nullptr) {
-      if (n_traced < P.trace_max) {
-        double* tr = trace + (size_t)n_traced * P.trace_stride;
-        MW_LANE0 { tr[0] = R; tr[1] = C; tr[2] = Knew; tr[3] = is_move; }
-        MW_FOR(c, N2) { if (4 + c < P.trace_stride) tr[4 + c] = (c < nnz) ? s.sig[s.order[c]] : 0.0; }
+      const int first = (int)(MONO_ROW_MASK - (keys[p] & MONO_ROW_MASK));
+      int pos = p;
+      if (multi) {   // rank inside the cluster = members with an earlier first row (clusters are short)
+        int lo = p, hi = p + 1;
+        while (!s.own[0][lo]) --lo;
+        while (hi < nnz && !s.own[0][hi]) ++hi;
+        if (hi - lo > 1) {
+          pos = lo;
+          for (int q = lo; q < hi; ++q) pos += ((int)(MONO_ROW_MASK - (keys[q] & MONO_ROW_MASK)) < first) ? 1 : 0;
+        }
       }
-      n_traced += 1;
+      const int c = s.cc[first];
+      s.order[pos] = (int16_t)c;
+      const double n2 = s.acc[0][c];
+      // a kept column leaves 1 / sigma in acc[0] for the U store below (one division per kept column, not per row)
+      if (pos < Knew) { s.rank[c] = (int16_t)pos; kept2 += n2; s.acc[0][c] = 1.0 / s.sig[c]; } else err2 += n2;
     }
-    if (cnt_keep > chi_lim && err2 > 0.0) cnt.n_trunc += 1.0;
-    if (Knew > CHI) { status = ST_CAPACITY; return; }
+    if (renorm_sv) kept2 = mw_sum(kept2);
+    err2 = mw_sum(err2);
+    MW_SYNC();
+    if (s.state.trace != nullptr) {
+      const int nt = s.state.n_traced;
+      if (nt < s.state.P.trace_max) {
+        const int stride = s.state.P.trace_stride;
+        double* tr = s.state.trace + (size_t)nt * stride;
+        MW_LANE0 { tr[0] = R; tr[1] = C; tr[2] = Knew; tr[3] = is_move; }
+        MW_FOR(c, N2) { if (4 + c < stride) tr[4 + c] = (c < nnz) ? s.sig[s.order[c]] : 0.0; }
+      }
+      MW_SYNC();
+      MW_LANE0 { s.state.n_traced = nt + 1; }
+    }
+    if (Knew > CHI) { s.state.status = ST_CAPACITY; MW_SYNC(); return; }
     const double dscale = (renorm_sv && kept2 > 0.0) ? 1.0 / sqrt(kept2) : 1.0;
     const int zero = (Knew == 0);
     if (zero) Knew = 1;   // zero matrix: keep a single zero direction (the state has zero norm)
     // ---- site jn-1 <- U: row (k, p) -> (rank of its column, value / sigma) ----
     {
-      MonoSite<CHI>& dst = sites[phys(jn - 1)];
-      if (!mirrored) {
+      MonoSite<CHI>& dst = s.state.sites[phys(s, jn - 1)];
+      if (!mir) {
         MW_FOR(r, R) {
           const int c = s.cc[r];
           const int t = (c >= 0) ? s.rank[c] : -1;
           double v = 0.0;
-          if (t >= 0) v = s.cv[r] * (1.0 / s.sig[c]);
+          if (t >= 0) v = s.cv[r] * s.acc[0][c];
           int tt = t;
           if (zero) { tt = (r == 0) ? 0 : -1; v = (r == 0) ? 1.0 : 0.0; }
           dst.tgt[r] = (int16_t)tt; dst.val[r] = v;
@@ -395,25 +471,24 @@ struct MonoEngine {
         MW_FOR(r, R) {
           const int c = s.cc[r];
           const int t = (c >= 0) ? s.rank[c] : -1;
-          if (t >= 0 && !zero) { const int o = t * 2 + (r & 1); s.ut[o] = (int16_t)(r >> 1); s.uv[o] = s.cv[r] * (1.0 / s.sig[c]); }
+          if (t >= 0 && !zero) { const int o = t * 2 + (r & 1); s.ut[o] = (int16_t)(r >> 1); s.uv[o] = s.cv[r] * s.acc[0][c]; }
         }
         if (zero) { MW_LANE0 { s.ut[0] = 0; s.uv[0] = 1.0; } }
         MW_SYNC();
         MW_FOR(r, 2 * Knew) { dst.tgt[r] = s.ut[r]; dst.val[r] = s.uv[r]; }
       }
-      cnt.bytes_hbm += 10.0 * 2 * (mirrored ? Knew : K);
     }
     MW_SYNC();
-    // ---- next carried matrix ----
+    // ---- next carried matrix (the old rows were last read by the U store above; the new ones depend on order / sig /
+    //      the staged site only) ----
     bad = 0;
-    // (the old rows were last read by the U store above; the new ones depend on order / sig / the staged site only)
     if (iso) {
       MW_FOR(rn, 2 * Knew) {
         int col = -1; double val = 0.0;
         if (!zero) {
           const int c = s.order[rn >> 1];
-          const int q = c / Mr, m = c - q * Mr;
-          if (!gather_row(vr, Bn, q, m, rn & 1, dscale * s.sig[c], &col, &val)) bad = 1;
+          const int q = (c >= Mr) ? 1 : 0, m = c - q * Mr;
+          if (!gather_row(s, T, Bn, q, m, rn & 1, dscale * s.sig[c], &col, &val)) bad = 1;
         }
         s.cv[rn] = val; s.cc[rn] = (int16_t)col;
       }
@@ -423,22 +498,29 @@ struct MonoEngine {
         int col = -1; double val = 0.0;
         if (!zero) {
           const int c = s.order[rn >> 1];
-          const int pd = c / (vr * Bn);
+          const int pd = (c >= vr * Bn) ? 1 : 0;
           if (pd == (rn & 1)) { col = c - pd * vr * Bn; val = dscale * s.sig[c]; }
         }
         s.cv[rn] = val; s.cc[rn] = (int16_t)col;
       }
     }
-    MW_SYNC();
-    if (MW_ANY(bad)) { status = ST_NOT_MONOMIAL; return; }
-    set_dim_right(jn - 1, Knew);
-    K = Knew; Wq = vr; Mr = Bn;
-    cnt.n_steps += 1.0;
+    bad = MW_ANY(bad);
+    MW_LANE0 {
+      MonoState<CHI>& st = s.state;
+      if (bad) st.status = ST_NOT_MONOMIAL;
+      const int p = phys(s, jn - 1);
+      if (mir) st.bd[p] = Knew; else st.bd[p + 1] = Knew;   // set_dim_right(jn - 1)
+      st.K = Knew; st.Wq = vr; st.Mr = Bn;
+      st.cnt.n_steps += 1.0;
+      st.cnt.bytes_hbm += 10.0 * 2 * (mir ? Knew : K);
+      if (cnt_keep > chi_lim && err2 > 0.0) st.cnt.n_trunc += 1.0;
+    }
     MW_SYNC();
   }
 
   // ---- carried (K, 2, 1, Mr) -> site j, optionally divided by its Frobenius norm (optimiser/utils.py:340-345) ----
-  MD_DEV void carried_to_site(int j, int renorm) {
+  static MW_PHASE void carried_to_site(SM& s, int j, int renorm) {
+    const int K = s.state.K, Mr = s.state.Mr, mir = s.state.mirrored;
     const int n = K * 2;
     double scale = 1.0;
     if (renorm) {
@@ -448,8 +530,8 @@ struct MonoEngine {
       const double nrm = sqrt(acc);
       scale = (nrm > 0.0) ? 1.0 / nrm : 1.0;
     }
-    MonoSite<CHI>& dst = sites[phys(j)];
-    if (!mirrored) {
+    MonoSite<CHI>& dst = s.state.sites[phys(s, j)];
+    if (!mir) {
       MW_FOR(r, n) { const int c = s.cc[r]; dst.tgt[r] = (int16_t)c; dst.val[r] = (c >= 0) ? s.cv[r] * scale : 0.0; }
     } else {   // stored dims (Mr, 2, K): rows (m, p) -> k
       MW_FOR(r, 2 * Mr) { s.ut[r] = -1; s.uv[r] = 0.0; }
@@ -461,34 +543,40 @@ struct MonoEngine {
       MW_SYNC();
       MW_FOR(r, 2 * Mr) { dst.tgt[r] = s.ut[r]; dst.val[r] = s.uv[r]; }
     }
-    cnt.bytes_hbm += 10.0 * 2 * (mirrored ? Mr : K);
+    MW_LANE0 { s.state.cnt.bytes_hbm += 10.0 * 2 * (mir ? Mr : K); }
     MW_SYNC();
   }
 
-  MD_DEV void sweep(int start, int len, const int* tids, int chi_lim, double cut, int renorm_after, int is_move,
-                    int renorm_sv) {
-    carried_from_site(start, tids ? tids[0] : -1);
-    if (status == ST_NOT_MONOMIAL) return;
+  // ---- sweep of an MPO over frame sites start..start+len-1 (tids == nullptr: identity MPO = centre move) ----
+  static MD_DEV void sweep(SM& s, int start, int len, const int* tids, int chi_lim, double cut, int renorm_after,
+                           int is_move, int renorm_sv) {
+    carried_from_site(s, start, tids ? tids[0] : -1);
+    if (s.state.status == ST_NOT_MONOMIAL) return;
     for (int t = 1; t < len; ++t) {
-      step(start + t, tids ? tids[t] : -1, chi_lim, cut, is_move, renorm_sv);
-      if (status == ST_CAPACITY || status == ST_NOT_MONOMIAL) return;
+      step(s, start + t, tids ? tids[t] : -1, chi_lim, cut, is_move, renorm_sv);
+      const int st = s.state.status;
+      if (st == ST_CAPACITY || st == ST_NOT_MONOMIAL) return;
     }
-    if (Wq != 1) { status = ST_CAPACITY; return; }
-    carried_to_site(start + len - 1, renorm_after);
+    if (s.state.Wq != 1) { s.state.status = ST_CAPACITY; MW_SYNC(); return; }
+    carried_to_site(s, start + len - 1, renorm_after);
   }
 
   // ---- product state + bit-flip bias (mps/utils.py:439-512, decoding.py:140-190) ----
-  MD_DEV void init_product(const uint8_t* sym) {
-    const int N = P.n_sites;
-    const double d = (P.bias_p >= 0.0) ? sqrt(1.0 - P.bias_p) : 1.0;
-    const double o = (P.bias_p >= 0.0) ? sqrt(P.bias_p) : 0.0;
+  static MW_PHASE void init_product(SM& s, const uint8_t* sym) {
+    const DecodeParams& P = s.state.P;
+    const int N = P.n_sites, kL = P.n_logical;
+    const double bp = P.bias_p;
+    const double d = (bp >= 0.0) ? sqrt(1.0 - bp) : 1.0;
+    const double o = (bp >= 0.0) ? sqrt(bp) : 0.0;
+    MonoSite<CHI>* sites = s.state.sites;
+    int* bd = s.state.bd;
     MW_FOR(j, N) {
       double a0, a1;
       const int c = sym[j];
       if (c == 0) { a0 = 1.0; a1 = 0.0; }
       else if (c == 1) { a0 = 0.0; a1 = 1.0; }
       else { a0 = 1.0 / sqrt(2.0); a1 = a0; }
-      if (j >= P.n_logical && P.bias_p >= 0.0) {
+      if (j >= kL && bp >= 0.0) {
         const double b0 = a0 * d + a1 * o, b1 = a0 * o + a1 * d;
         a0 = b0; a1 = b1;
       }
@@ -496,20 +584,24 @@ struct MonoEngine {
       sites[j].tgt[0] = 0; sites[j].tgt[1] = 0;
     }
     MW_FOR(j, N + 1) bd[j] = 1;
-    centre = 0; mirrored = 0; status = ST_OK; n_traced = 0;
+    MW_LANE0 { s.state.centre = 0; s.state.mirrored = 0; s.state.status = ST_OK; s.state.n_traced = 0; }
     MW_SYNC();
   }
 
   // ---- marginal over sites kL..N-1, reverse, dense, |.|, L2 renorm, tolerant arg-max ----
   //   canonical.py:956-989, :150-161, :241-272; decoding.py:1362-1379
-  MD_DEV void marginal_readout(double* out, int* success) {
+  static MW_PHASE void marginal_readout(SM& s, double* out, int* success) {
+    const DecodeParams& P = s.state.P;
     const int N = P.n_sites, kL = P.n_head, ren = P.renormalise;
-    if (P.kept_mask != ((kL >= 32) ? 0xffffffffu : ((1u << kL) - 1u))) { status = ST_NOT_MONOMIAL; return; }
+    if (P.kept_mask != ((kL >= 32) ? 0xffffffffu : ((1u << kL) - 1u))) { s.state.status = ST_NOT_MONOMIAL; MW_SYNC(); return; }
+    MonoSite<CHI>* sites = s.state.sites;
+    int* bd = s.state.bd;
     double* T = s.cv;     // current last tensor (L x 2)
     double* w = s.sig;    // traced vector
     int L = bd[N - 1];
     MW_FOR(t, L * 2) T[t] = (sites[N - 1].tgt[t] >= 0) ? sites[N - 1].val[t] : 0.0;
     MW_SYNC();
+    double bytes = 0.0;
     for (int site = N - 1; site >= kL; --site) {
       MW_FOR(l, L) w[l] = (T[l * 2] + T[l * 2 + 1]) * (1.0 / sqrt(2.0));
       MW_SYNC();
@@ -521,7 +613,7 @@ struct MonoEngine {
         const double v = (b >= 0) ? A.val[t] * w[b] : 0.0;
         T[t] = v; acc += v * v;
       }
-      cnt.bytes_hbm += 10.0 * 2 * L2;
+      bytes += 10.0 * 2 * L2;
       if (ren) {
         acc = mw_sum(acc);
         const double nrm = sqrt(acc);
@@ -533,7 +625,7 @@ struct MonoEngine {
     }
     // the merged last logical tensor goes back into the MPS (what CanonicalMPS.marginal returns)
     MW_FOR(t, L * 2) { sites[kL - 1].val[t] = T[t]; sites[kL - 1].tgt[t] = 0; }
-    MW_LANE0 { bd[kL] = 1; }
+    MW_LANE0 { bd[kL] = 1; s.state.cnt.bytes_hbm += bytes; }
     MW_SYNC();
     // dense stage over the kL logical sites: every class follows one path through the monomial tensors
     const int ncls = 1 << kL;
@@ -564,50 +656,58 @@ struct MonoEngine {
         const double eps = fmax(P.readout_rel * t2, P.readout_abs);
         *success = (out[0] >= t2 - eps) ? 1 : 0;
       }
+      if (bad && s.state.status == ST_OK) s.state.status = ST_ZERO_NORM;
     }
-    if (bad && status == ST_OK) status = ST_ZERO_NORM;
     MW_SYNC();
   }
 
   // ---- run the program.  Every sweep -- the centre move in front of an op (canonical.py:345-420; moving left runs in
-  //      the mirrored frame like the reference's reverse()) and the MPO sweep itself -- goes through ONE call site,
-  //      so the step code exists once in the kernel ----
-  MD_DEV void run(const int* prog, const uint8_t* sym, double* out, int* success) {
-    init_product(sym);
+  //      the mirrored frame like the reference's reverse()) and the MPO sweep itself -- goes through ONE call site ----
+  static MD_DEV void run(SM& s, const int* prog, const uint8_t* sym, double* out, int* success) {
+    init_product(s, sym);
+    const int n_ops = s.state.P.n_ops, n_sites = s.state.P.n_sites;
     int pc = 0;
-    while (pc < P.n_ops) {
+    while (pc < n_ops) {
       const int op = prog[pc];
       if (op == OP_END) break;
       if (op == OP_MARGINAL) {
-        marginal_readout(out, success);
+        marginal_readout(s, out, success);
         pc += 1;
       } else if (op == OP_SWEEP || op == OP_MOVE) {
         const int target = prog[pc + 1];
-        for (int phase = (target == centre) ? 1 : 0; phase < 2; ++phase) {
+        for (int phase = (target == s.state.centre) ? 1 : 0; phase < 2; ++phase) {
           if (phase == 1 && op == OP_MOVE) break;
-          int start, len, chi_lim, ren = 0, rsv = 0;
+          int start, len, chi_lim, ren = 0, rsv = 0, mir = 0;
           double cut;
           const int* tids = nullptr;
+          const int centre = s.state.centre;
           if (phase == 0) {   // move the centre to `target`
-            mirrored = (target < centre) ? 1 : 0;
-            start = mirrored ? (P.n_sites - 1 - centre) : centre;
-            len = (mirrored ? (centre - target) : (target - centre)) + 1;
-            chi_lim = CHI; cut = P.cut_move;
+            mir = (target < centre) ? 1 : 0;
+            start = mir ? (n_sites - 1 - centre) : centre;
+            len = (mir ? (centre - target) : (target - centre)) + 1;
+            chi_lim = CHI; cut = s.state.P.cut_move;
           } else {
-            mirrored = 0;
             start = target; len = prog[pc + 2]; ren = prog[pc + 3]; rsv = prog[pc + 4];
-            tids = prog + pc + 5; chi_lim = P.chi_max; cut = P.cut_sweep;
+            tids = prog + pc + 5; chi_lim = s.state.P.chi_max; cut = s.state.P.cut_sweep;
           }
-          sweep(start, len, tids, chi_lim, cut, ren, phase == 0, rsv);
-          mirrored = 0;
-          if (status == ST_CAPACITY || status == ST_NOT_MONOMIAL) break;
-          centre = (phase == 0) ? target : (target + len - 1);
+          MW_SYNC();
+          MW_LANE0 { s.state.mirrored = mir; }
+          MW_SYNC();
+          sweep(s, start, len, tids, chi_lim, cut, ren, phase == 0, rsv);
+          MW_SYNC();
+          MW_LANE0 { s.state.mirrored = 0; }
+          const int st = s.state.status;
+          if (st == ST_CAPACITY || st == ST_NOT_MONOMIAL) break;
+          MW_LANE0 { s.state.centre = (phase == 0) ? target : (target + len - 1); }
+          MW_SYNC();
         }
         pc += (op == OP_MOVE) ? 2 : (5 + prog[pc + 2]);
       } else {
-        status = ST_NOT_MONOMIAL;   // two-site gates / compression: dense engine
+        MW_LANE0 { s.state.status = ST_NOT_MONOMIAL; }   // two-site gates / compression: dense engine
+        MW_SYNC();
       }
-      if (status == ST_CAPACITY || status == ST_NOT_MONOMIAL) break;
+      const int st = s.state.status;
+      if (st == ST_CAPACITY || st == ST_NOT_MONOMIAL) break;
     }
   }
 };

@@ -14,6 +14,20 @@ __host__ __device__ inline size_t mono_ws_bytes_per_warp(int chi, int n_sites) {
   return (b + 255) & ~(size_t)255;
 }
 
+// bytes at the end of the workspace: the work counter (256 B) and the per-launch tensor tables
+__host__ __device__ inline size_t mono_ws_tail_bytes(int n_tensors) {
+  return 256 + (((size_t)n_tensors + 1) * sizeof(MonoTensor) + 255) / 256 * 256;
+}
+constexpr int MONO_MAX_TENSORS = 62;   // tail reserved by mdopt_mono_workspace_bytes: 256 + 63 * 160 bytes, rounded
+
+// Per-launch set-up: the MPO tensor table in the form the engine reads (one thread per tensor; slot 0 = identity).
+__global__ void mono_prepare_kernel(const double* __restrict__ wtab, const int* __restrict__ wdim, int n_tensors,
+                                    MonoTensor* tabs, int* work_counter) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) { mono_build_identity(tabs); *work_counter = 0; }
+  if (t < n_tensors) mono_build_tensor(wtab + (size_t)t * 16, wdim + (size_t)t * 4, tabs + 1 + t);
+}
+
 // -------------------------------------------------------------------------------------------------
 // One warp per CTA, one syndrome per warp at a time; persistent warps pull syndromes from a global counter.
 // A warp's whole state is its ~8 KB of shared memory (chi = 64) plus its MPS slice in the workspace, so an SM
@@ -23,42 +37,45 @@ __host__ __device__ inline size_t mono_ws_bytes_per_warp(int chi, int n_sites) {
 constexpr int mono_min_ctas(int chi) { return chi <= 64 ? 24 : (chi <= 128 ? 12 : (chi <= 256 ? 6 : 3)); }
 template <int CHI>
 __global__ void __launch_bounds__(32, mono_min_ctas(CHI))
-mono_decode_kernel(DecodeParams P, const int* __restrict__ prog, const double* __restrict__ wtab,
-                   const int* __restrict__ wdim, const uint8_t* __restrict__ syms, int batch, double* dist,
-                   int* success, int* status, double* trace, double* counters, unsigned char* ws,
-                   int* work_counter) {
+mono_decode_kernel(DecodeParams P, const int* __restrict__ prog, const MonoTensor* __restrict__ tabs,
+                   const uint8_t* __restrict__ syms, int batch, double* dist, int* success, int* status,
+                   double* trace, double* counters, unsigned char* ws, int* work_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MonoSmem<CHI>& s = *reinterpret_cast<MonoSmem<CHI>*>(smem_raw);
   static_assert(sizeof(MonoSite<CHI>) == (size_t)2 * CHI * 10, "site record layout");
-  MonoEngine<CHI> E(s);
-  unsigned char* base = ws + (size_t)blockIdx.x * mono_ws_bytes_per_warp(CHI, P.n_sites);
-  E.sites = reinterpret_cast<MonoSite<CHI>*>(base);
-  E.bd = reinterpret_cast<int*>(base + (size_t)P.n_sites * sizeof(MonoSite<CHI>));
-  E.wtab = wtab; E.wdim = wdim; E.P = P;
-  E.cnt = MonoCounters{};
-  const int ncls = 1 << P.n_logical;
   const int lane = threadIdx.x;
+  if (lane == 0) {
+    unsigned char* base = ws + (size_t)blockIdx.x * mono_ws_bytes_per_warp(CHI, P.n_sites);
+    MonoState<CHI>& st = s.state;
+    st.sites = reinterpret_cast<MonoSite<CHI>*>(base);
+    st.bd = reinterpret_cast<int*>(base + (size_t)P.n_sites * sizeof(MonoSite<CHI>));
+    st.tabs = tabs; st.P = P; st.trace = nullptr;
+    st.cnt = MonoCounters{};
+  }
+  __syncwarp();
+  const int ncls = 1 << P.n_logical;
   while (true) {
     int b = 0;
     if (lane == 0) b = atomicAdd(work_counter, 1);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= batch) break;
-    E.trace = trace ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
-    E.run(prog, syms + (size_t)b * P.n_sites, dist + (size_t)b * ncls, success + b);
+    if (lane == 0) s.state.trace = trace ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
     __syncwarp();
-    if (E.status == ST_CAPACITY || E.status == ST_NOT_MONOMIAL) {
+    Mono<CHI>::run(s, prog, syms + (size_t)b * P.n_sites, dist + (size_t)b * ncls, success + b);
+    __syncwarp();
+    const int st = s.state.status;
+    if (st == ST_CAPACITY || st == ST_NOT_MONOMIAL) {
       for (int i = lane; i < ncls; i += 32) dist[(size_t)b * ncls + i] = nan("");
-      if (lane == 0) success[b] = 0;
-      E.cnt.n_fallback += 1.0;
+      if (lane == 0) { success[b] = 0; s.state.cnt.n_fallback += 1.0; }
     }
-    if (lane == 0) status[b] = E.status;
+    if (lane == 0) status[b] = st;
     __syncwarp();
   }
   if (lane == 0 && counters) {
-    atomicAdd(counters + 3, E.cnt.bytes_hbm);
-    atomicAdd(counters + 4, E.cnt.n_steps);
-    atomicAdd(counters + 5, E.cnt.n_trunc);
-    atomicAdd(counters + 7, E.cnt.n_fallback);
+    atomicAdd(counters + 3, s.state.cnt.bytes_hbm);
+    atomicAdd(counters + 4, s.state.cnt.n_steps);
+    atomicAdd(counters + 5, s.state.cnt.n_trunc);
+    atomicAdd(counters + 7, s.state.cnt.n_fallback);
   }
 }
 
@@ -82,7 +99,8 @@ int launch_mono_decode(const mdopt_decode_desc* d, int n_warps, const int32_t* p
                        int32_t* success, int32_t* status, double* trace, double* counters, void* workspace,
                        size_t workspace_bytes, cudaStream_t st) {
   const size_t per = mono_ws_bytes_per_warp(CHI, d->n_sites);
-  if (workspace_bytes < per * (size_t)n_warps + 256) return MDOPT_E_BADARG;
+  if (n_tensors > MONO_MAX_TENSORS) return MDOPT_E_CAPACITY;
+  if (workspace_bytes < per * (size_t)n_warps + mono_ws_tail_bytes(MONO_MAX_TENSORS)) return MDOPT_E_BADARG;
   cudaError_t e = cudaFuncSetAttribute((const void*)mono_decode_kernel<CHI>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MonoSmem<CHI>));
   if (e != cudaSuccess) return (int)e;
@@ -96,7 +114,9 @@ int launch_mono_decode(const mdopt_decode_desc* d, int n_warps, const int32_t* p
   P.readout_rel = d->readout_rel; P.readout_abs = d->readout_abs;
   P.n_tensors = n_tensors;
   int* work_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + per * (size_t)n_warps);
-  e = cudaMemsetAsync(work_counter, 0, 256, st);
+  MonoTensor* tabs = reinterpret_cast<MonoTensor*>(reinterpret_cast<char*>(work_counter) + 256);
+  mono_prepare_kernel<<<(n_tensors + 63) / 64, 64, 0, st>>>(wtab, wdim, n_tensors, tabs, work_counter);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (counters) {
     e = cudaMemsetAsync(counters, 0, 16 * sizeof(double), st);
@@ -104,7 +124,7 @@ int launch_mono_decode(const mdopt_decode_desc* d, int n_warps, const int32_t* p
   }
   const int grid = batch < n_warps ? batch : n_warps;
   mono_decode_kernel<CHI><<<grid, 32, sizeof(MonoSmem<CHI>), st>>>(
-      P, program, wtab, wdim, symbols, batch, dist, success, status, d->trace_stride > 0 ? trace : nullptr, counters,
+      P, program, tabs, symbols, batch, dist, success, status, d->trace_stride > 0 ? trace : nullptr, counters,
       reinterpret_cast<unsigned char*>(workspace), work_counter);
   return (int)cudaGetLastError();
 }

@@ -61,13 +61,16 @@ int decode_impl(const mdopt_decode_desc* d, const int32_t* program, const double
 // the monomial (one warp per syndrome) engine, lane loops run sequentially
 template <int CHI>
 int mono_impl(const mdopt_decode_desc* d, const int32_t* program, const double* wtab, const int32_t* wdim,
-              const uint8_t* symbols, int batch, double* dist, int32_t* success, int32_t* status, double* trace,
-              double* counters) {
+              int n_tensors, const uint8_t* symbols, int batch, double* dist, int32_t* success, int32_t* status,
+              double* trace, double* counters) {
   MonoSmem<CHI>* sm = new MonoSmem<CHI>();
   std::vector<MonoSite<CHI>> sites(d->n_sites);
   std::vector<int> bd(d->n_sites + 1);
-  MonoEngine<CHI> E(*sm);
-  E.sites = sites.data(); E.bd = bd.data(); E.wtab = wtab; E.wdim = wdim;
+  std::vector<MonoTensor> tabs(n_tensors + 1);
+  mono_build_identity(&tabs[0]);
+  for (int t = 0; t < n_tensors; ++t) mono_build_tensor(wtab + (size_t)t * 16, wdim + (size_t)t * 4, &tabs[1 + t]);
+  MonoState<CHI>& st = sm->state;
+  st.sites = sites.data(); st.bd = bd.data(); st.tabs = tabs.data();
   DecodeParams P;
   P.n_sites = d->n_sites; P.n_logical = d->n_logical; P.chi_max = d->chi_max; P.mode = d->mode;
   P.renormalise = d->renormalise; P.trace_stride = d->trace_stride; P.trace_max = d->trace_max;
@@ -76,20 +79,20 @@ int mono_impl(const mdopt_decode_desc* d, const int32_t* program, const double* 
   P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
   P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
   P.readout_rel = d->readout_rel; P.readout_abs = d->readout_abs;
-  P.n_tensors = 0;
-  E.P = P;
-  E.cnt = MonoCounters{};
+  P.n_tensors = n_tensors;
+  st.P = P;
+  st.cnt = MonoCounters{};
   const int ncls = 1 << d->n_logical;
   for (int b = 0; b < batch; ++b) {
-    E.trace = (trace && d->trace_stride > 0) ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
-    E.run(program, symbols + (size_t)b * d->n_sites, dist + (size_t)b * ncls, success + b);
-    status[b] = E.status;
-    if (E.status == ST_CAPACITY || E.status == ST_NOT_MONOMIAL) {
+    st.trace = (trace && d->trace_stride > 0) ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
+    Mono<CHI>::run(*sm, program, symbols + (size_t)b * d->n_sites, dist + (size_t)b * ncls, success + b);
+    status[b] = st.status;
+    if (st.status == ST_CAPACITY || st.status == ST_NOT_MONOMIAL) {
       for (int i = 0; i < ncls; ++i) dist[(size_t)b * ncls + i] = NAN;
       success[b] = 0;
     }
   }
-  if (counters) { counters[3] = E.cnt.bytes_hbm; counters[4] = E.cnt.n_steps; counters[5] = E.cnt.n_trunc; }
+  if (counters) { counters[3] = st.cnt.bytes_hbm; counters[4] = st.cnt.n_steps; counters[5] = st.cnt.n_trunc; }
   delete sm;
   return 0;
 }
@@ -185,16 +188,16 @@ int emu_decode_batch(const mdopt_decode_desc* d, int chi_cap, const int32_t* pro
   return -2;
 }
 int emu_mono_decode_batch(const mdopt_decode_desc* d, int chi_cap, const int32_t* program, const double* wtab,
-                          const int32_t* wdim, const uint8_t* symbols, int batch, double* dist, int32_t* success,
-                          int32_t* status, double* trace, double* counters) {
+                          const int32_t* wdim, int n_tensors, const uint8_t* symbols, int batch, double* dist,
+                          int32_t* success, int32_t* status, double* trace, double* counters) {
   switch (chi_cap) {
-    case 8: return mono_impl<8>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
-    case 16: return mono_impl<16>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
-    case 32: return mono_impl<32>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
-    case 64: return mono_impl<64>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
-    case 128: return mono_impl<128>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
-    case 256: return mono_impl<256>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
-    case 512: return mono_impl<512>(d, program, wtab, wdim, symbols, batch, dist, success, status, trace, counters);
+    case 8: return mono_impl<8>(d, program, wtab, wdim, n_tensors, symbols, batch, dist, success, status, trace, counters);
+    case 16: return mono_impl<16>(d, program, wtab, wdim, n_tensors, symbols, batch, dist, success, status, trace, counters);
+    case 32: return mono_impl<32>(d, program, wtab, wdim, n_tensors, symbols, batch, dist, success, status, trace, counters);
+    case 64: return mono_impl<64>(d, program, wtab, wdim, n_tensors, symbols, batch, dist, success, status, trace, counters);
+    case 128: return mono_impl<128>(d, program, wtab, wdim, n_tensors, symbols, batch, dist, success, status, trace, counters);
+    case 256: return mono_impl<256>(d, program, wtab, wdim, n_tensors, symbols, batch, dist, success, status, trace, counters);
+    case 512: return mono_impl<512>(d, program, wtab, wdim, n_tensors, symbols, batch, dist, success, status, trace, counters);
   }
   return -2;
 }

@@ -60,9 +60,14 @@ def decode(program: schedule.Program, symbols, chi_max, cut, bias_p, renormalise
     trace = np.zeros((B, max(trace_max, 1), max(stride, 1)))
     counters = np.zeros(8)
     syms = np.ascontiguousarray(symbols, dtype=np.uint8)
-    fn = lib().emu_mono_decode_batch if mono else lib().emu_decode_batch
-    rc = fn(C.byref(desc), cap, _ptr(program.ops), _ptr(program.wtab), _ptr(program.wdim),
-            _ptr(syms), B, _ptr(dist), _ptr(success), _ptr(status), _ptr(trace), _ptr(counters))
+    if mono:
+        rc = lib().emu_mono_decode_batch(C.byref(desc), cap, _ptr(program.ops), _ptr(program.wtab),
+                                         _ptr(program.wdim), int(program.wtab.shape[0]), _ptr(syms), B, _ptr(dist),
+                                         _ptr(success), _ptr(status), _ptr(trace), _ptr(counters))
+    else:
+        rc = lib().emu_decode_batch(C.byref(desc), cap, _ptr(program.ops), _ptr(program.wtab), _ptr(program.wdim),
+                                    _ptr(syms), B, _ptr(dist), _ptr(success), _ptr(status), _ptr(trace),
+                                    _ptr(counters))
     assert rc == 0
     return dist, success, status, trace, counters
 
