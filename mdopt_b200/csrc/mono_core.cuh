@@ -133,9 +133,17 @@ struct MonoSmem {
   int16_t order[N2];     // column at sorted position
   int16_t st[N2];
   int16_t ut[N2];
+  MonoTensor tw;         // the MPO tensor of the current step (copied from the per-launch table)
   MonoState<CHI> state;
 };
 
+#ifndef MDOPT_EMU
+__device__ __forceinline__ int mw_clz(unsigned w) { return __clz((int)w); }
+__device__ __forceinline__ int mw_ctz(unsigned w) { return __ffs((int)w) - 1; }
+#else
+inline int mw_clz(unsigned w) { return __builtin_clz(w); }
+inline int mw_ctz(unsigned w) { return __builtin_ctz(w); }
+#endif
 #ifndef MDOPT_EMU
 static __device__ __noinline__ double mw_sum(double v) {
 #pragma unroll
@@ -261,6 +269,28 @@ struct Mono {
   static MD_DEV int dim_left(const SM& s, int j) { const int p = phys(s, j); return s.state.mirrored ? s.state.bd[p + 1] : s.state.bd[p]; }
   static MD_DEV int dim_right(const SM& s, int j) { const int p = phys(s, j); return s.state.mirrored ? s.state.bd[p] : s.state.bd[p + 1]; }
 
+  // ---- copy the step's tensor entry (160 bytes) from the per-launch table into shared memory ----
+  static MD_DEV void load_tensor(SM& s, int tid) {
+    static_assert(sizeof(MonoTensor) == 160, "MonoTensor layout");
+    const int* src = reinterpret_cast<const int*>(s.state.tabs + (tid + 1));
+    int* dst = reinterpret_cast<int*>(&s.tw);
+    MW_FOR(i, (int)(sizeof(MonoTensor) / sizeof(int))) dst[i] = src[i];
+    MW_SYNC();
+  }
+
+  // ---- ask for site j's record ahead of its use: one 128-byte line per lane into L1 (no registers, no staging
+  //      buffer; load_site() a step later hits the cache instead of waiting for L2 / HBM) ----
+  static MD_DEV void prefetch_site(const SM& s, int j) {
+#if !defined(MDOPT_EMU) && !defined(MONO_NO_PREFETCH)
+    const char* base = reinterpret_cast<const char*>(&s.state.sites[phys(s, j)]);
+    const int A = s.state.mirrored ? dim_right(s, j) : dim_left(s, j);   // stored left dimension
+    const int lane = threadIdx.x & 31;
+    const int nv = (2 * A * 8 + 127) >> 7, nt = (2 * A * 2 + 127) >> 7;   // lines of the value / target arrays
+    if (lane < nv) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + lane * 128));
+    else if (lane < nv + nt) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + 2 * CHI * 8 + (lane - nv) * 128));
+#endif
+  }
+
   // ---- stage site j in the frame view: rows (a, p) -> (s.st, s.sv), a < dim_left(j) ----
   static MD_DEV void load_site(SM& s, int j) {
     const MonoSite<CHI>& src = s.state.sites[phys(s, j)];
@@ -301,9 +331,11 @@ struct Mono {
   }
 
   // ---- carried <- site j with the first MPO tensor applied (contractor.py:276-291, first half) ----
-  static MW_PHASE void carried_from_site(SM& s, int j, int tid) {
-    const MonoTensor& T = s.state.tabs[tid + 1];
+  static MW_PHASE void carried_from_site(SM& s, int j, int tid, int jnext) {
+    load_tensor(s, tid);
+    const MonoTensor& T = s.tw;
     const int A = dim_left(s, j), B = dim_right(s, j), vr = T.vr;
+    if (jnext >= 0) prefetch_site(s, jnext);
     load_site(s, j);
     int bad = (T.vl != 1);
     // rows (k, p') of the carried matrix; columns (q, m) = q*B + m
@@ -319,14 +351,16 @@ struct Mono {
   }
 
   // ---- one two-site step: absorb site jn (frame index) with MPO tensor tid ----
-  static MW_PHASE void step(SM& s, int jn, int tid, int chi_lim, double cut, int is_move, int renorm_sv) {
-    const MonoTensor& T = s.state.tabs[tid + 1];
+  static MW_PHASE void step(SM& s, int jn, int tid, int chi_lim, double cut, int is_move, int renorm_sv, int jnext) {
+    load_tensor(s, tid);
+    const MonoTensor& T = s.tw;
     const int vl = T.vl, vr = T.vr, iso = T.iso;
     const int K = s.state.K, Wq = s.state.Wq, Mr = s.state.Mr, mir = s.state.mirrored;
     const int Bn = dim_right(s, jn);
     const int R = K * 2;
     int C = Wq * Mr;
     if (vl != Wq || dim_left(s, jn) != Mr) { s.state.status = ST_CAPACITY; MW_SYNC(); return; }
+    if (jnext >= 0) prefetch_site(s, jnext);
     load_site(s, jn);
     int bad = 0;
     if (!iso) {
@@ -396,33 +430,64 @@ struct Mono {
     // ---- canonical order: sort by (sigma^2, first row); values within the tie width of their predecessor (chained)
     //      form one cluster; inside a cluster the order is by first supporting row ----
     mw_sort_desc<N2>(keys, C);
+    // cluster flags: position p opens a cluster.  Device: one ballot word per 32 sorted positions (position
+    // p = lane + 32*i is bit `lane` of word i, positions >= nnz count as starts), kept in shared memory, so the
+    // bounds of p's cluster are bit scans instead of walks.  The loops stay rolled: the instruction caches, not the
+    // instruction count, limit this kernel.
+    unsigned* fw = reinterpret_cast<unsigned*>(s.own[0]);   // own[] is free after the structure check (NW <= N2/2 ints)
     int multi = 0;
-    MW_FOR(p, nnz) {
-      int flag = 1;   // position p opens a cluster
-      if (p > 0) {
-        double a, b;
-        const unsigned long long ka = keys[p - 1] & ~MONO_ROW_MASK, kb = keys[p] & ~MONO_ROW_MASK;
-#ifdef MDOPT_EMU
-        memcpy(&a, &ka, 8); memcpy(&b, &kb, 8);
-#else
-        a = __longlong_as_double((long long)ka); b = __longlong_as_double((long long)kb);
-#endif
-        flag = (b < a * (1.0 - MONO_TIE_REL2)) ? 1 : 0;
+#ifndef MDOPT_EMU
+    {
+      const int lane = threadIdx.x & 31;
+      const int nw = (nnz + 31) >> 5;
+#pragma unroll 1
+      for (int i = 0; i < nw; ++i) {
+        const int p = lane + 32 * i;
+        int flag = 1;
+        if (p < nnz && p > 0) {
+          const double a = __longlong_as_double((long long)(keys[p - 1] & ~MONO_ROW_MASK));
+          const double b = __longlong_as_double((long long)(keys[p] & ~MONO_ROW_MASK));
+          flag = (b < a * (1.0 - MONO_TIE_REL2)) ? 1 : 0;
+        }
+        const unsigned w = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) fw[i] = w;
+        multi |= (w != 0xffffffffu);
       }
-      s.own[0][p] = (int16_t)flag;   // own[] is free after the structure check
-      multi |= !flag;
     }
-    multi = MW_ANY(multi);
+#else
+    {
+      const int nw = (nnz + 31) >> 5;
+      for (int i = 0; i < nw; ++i) fw[i] = 0u;
+      for (int p = 0; p < 32 * nw; ++p) {
+        int flag = 1;
+        if (p < nnz && p > 0) {
+          double a, b;
+          const unsigned long long ka = keys[p - 1] & ~MONO_ROW_MASK, kb = keys[p] & ~MONO_ROW_MASK;
+          memcpy(&a, &ka, 8); memcpy(&b, &kb, 8);
+          flag = (b < a * (1.0 - MONO_TIE_REL2)) ? 1 : 0;
+        }
+        if (flag) fw[p >> 5] |= 1u << (p & 31); else multi = 1;
+      }
+    }
+#endif
     MW_FOR(c, C) s.rank[c] = -1;
     MW_SYNC();
     double kept2 = 0.0, err2 = 0.0;
     MW_FOR(p, nnz) {
       const int first = (int)(MONO_ROW_MASK - (keys[p] & MONO_ROW_MASK));
       int pos = p;
-      if (multi) {   // rank inside the cluster = members with an earlier first row (clusters are short)
-        int lo = p, hi = p + 1;
-        while (!s.own[0][lo]) --lo;
-        while (hi < nnz && !s.own[0][hi]) ++hi;
+      if (multi) {   // rank inside the cluster = members with an earlier first row
+        const int lane = p & 31, nw = (nnz + 31) >> 5;
+        // lo = last cluster start at or before p; hi = first cluster start after p (or nnz)
+        int wi = p >> 5;
+        unsigned w = fw[wi] & (0xffffffffu >> (31 - lane));
+        while (w == 0u) w = fw[--wi];            // position 0 always opens a cluster
+        const int lo = 32 * wi + (31 - mw_clz(w));
+        int vi = p >> 5;
+        unsigned v = (lane == 31) ? 0u : (fw[vi] & (0xffffffffu << (lane + 1)));
+        while (v == 0u && vi + 1 < nw) v = fw[++vi];
+        int hi = nnz;
+        if (v != 0u) { const int h = 32 * vi + mw_ctz(v); hi = h < nnz ? h : nnz; }
         if (hi - lo > 1) {
           pos = lo;
           for (int q = lo; q < hi; ++q) pos += ((int)(MONO_ROW_MASK - (keys[q] & MONO_ROW_MASK)) < first) ? 1 : 0;
@@ -550,10 +615,10 @@ struct Mono {
   // ---- sweep of an MPO over frame sites start..start+len-1 (tids == nullptr: identity MPO = centre move) ----
   static MD_DEV void sweep(SM& s, int start, int len, const int* tids, int chi_lim, double cut, int renorm_after,
                            int is_move, int renorm_sv) {
-    carried_from_site(s, start, tids ? tids[0] : -1);
+    carried_from_site(s, start, tids ? tids[0] : -1, len > 1 ? start + 1 : -1);
     if (s.state.status == ST_NOT_MONOMIAL) return;
     for (int t = 1; t < len; ++t) {
-      step(s, start + t, tids ? tids[t] : -1, chi_lim, cut, is_move, renorm_sv);
+      step(s, start + t, tids ? tids[t] : -1, chi_lim, cut, is_move, renorm_sv, t + 1 < len ? start + t + 1 : -1);
       const int st = s.state.status;
       if (st == ST_CAPACITY || st == ST_NOT_MONOMIAL) return;
     }

@@ -313,8 +313,10 @@ def test_edge_batches(api):
         api["decode_css_batch"](code, ["IIXIIIIIIIIII"], chi_max=32, bias_type="Bitflip", bias_prob=1.5)
     from mdopt_b200 import _lib
 
-    with pytest.raises(_lib.MdoptCudaError):  # beyond the largest compiled capacity (256)
-        api["decode_css_batch"](code, ["IIXIIIIIIIIII"], chi_max=300, bias_type="Bitflip")
+    with pytest.raises(_lib.MdoptCudaError):  # beyond the largest compiled capacity of the dense engine (256)
+        api["decode_css_batch"](code, ["IIXIIIIIIIIII"], chi_max=300, bias_type="Depolarising")
+    with pytest.raises(_lib.MdoptCudaError):  # ... and of the monomial engine (512)
+        api["decode_css_batch"](code, ["IIXIIIIIIIIII"], chi_max=600, bias_type="Bitflip")
 
 
 def test_non_ok_status_paths(api):
