@@ -114,7 +114,7 @@ def _code_key(code) -> Tuple:
 def _program_for(code, has_x, has_z, renormalise, strategy, orders, bias_type="Bitflip", bias_prob=0.1):
     depol = bias_type != "Bitflip"
     key = (_code_key(code), has_x, has_z, bool(renormalise), strategy,
-           None if not orders else tuple(sorted((k, tuple(v)) for k, v in orders.items())),
+           None if not orders else tuple(sorted((k, v if isinstance(v, str) else tuple(v)) for k, v in orders.items())),
            depol, float(bias_prob) if depol else None)
     if key not in _PROGRAM_CACHE:
         _PROGRAM_CACHE[key] = schedule.build_decode_program(code, has_x, has_z, renormalise, strategy, orders,
@@ -264,7 +264,8 @@ def decode_custom_batch(stabilizers: Sequence[str], x_logicals: Sequence[str], z
             groups.setdefault(schedule.readout_kept_mask(err, k) if "E" in err else default_mask, []).append(b)
     if groups:
         key = ("custom", tuple(stabilizers), tuple(x_logicals), tuple(z_logicals), bool(renormalise),
-               contraction_strategy, None if not orders else tuple(sorted((kk, tuple(v)) for kk, v in orders.items())),
+               contraction_strategy,
+               None if not orders else tuple(sorted((kk, v if isinstance(v, str) else tuple(v)) for kk, v in orders.items())),
                depol, float(bias_prob) if depol else None)
         if key not in _PROGRAM_CACHE:
             _PROGRAM_CACHE[key] = schedule.build_custom_program(

@@ -66,6 +66,7 @@ def generate_errors(lattice_size, error_rate, num_experiments, error_model, seed
 def run_experiment(lattice_size, chi_max, error_rate, bias_prob, num_experiments, error_model, seed, errors, silent,
                    num_processes=1, tolerance=1e-8, cut=1e-8):
     """Decode this rank's shard and assemble the reference's result dictionary (quantum_surface.py:207-268)."""
+    from mdopt_b200 import _abi
     from mdopt_b200 import distributed as D
     from mdopt_b200.codes import surface_code
     from mdopt_b200.decoding import decode_css_batch
@@ -77,19 +78,37 @@ def run_experiment(lattice_size, chi_max, error_rate, bias_prob, num_experiments
     world = dist.get_world_size() if dist.is_initialized() else 1
     lo, hi = D.shard_bounds(num_experiments, rank, world)
     code = surface_code(lattice_size)
-    bias_type = "Bitflip" if error_model in ("Bitflip", "Phaseflip") else error_model
-    dist_rows, success = decode_css_batch(code, errors[lo:hi], chi_max=chi_max, cut=cut, bias_type=bias_type,
-                                          bias_prob=bias_prob, renormalise=True, silent=silent,
-                                          contraction_strategy="Optimised", tolerance=tolerance)
+    shard = errors[lo:hi]
+    # bias_type = error_model, unchanged, like the reference (quantum_surface.py:157-169): in decode_css any string but
+    # "Bitflip" takes the depolarising-bias branch (decoding.py:1267-1283), "Phaseflip" included
+    kw = dict(chi_max=chi_max, cut=cut, bias_type=error_model, bias_prob=bias_prob, renormalise=True, silent=silent,
+              contraction_strategy="Optimised", tolerance=tolerance)
+    dist_rows, success, status = decode_css_batch(code, shard, return_status=True, **kw)
+    dist_rows = np.array(dist_rows, dtype=np.float64)
+    failure = (1 - success).astype(np.float64)
+    # retry path (quantum_surface.py:170-192): the reference re-decodes a syndrome whose decode raised with
+    # multiply_by_stabiliser=True and records NaN if that fails too.  Here "raised" is a per-syndrome status that
+    # invalidates the result (capacity); a zero-norm state is not an exception in the reference either (NaN vector,
+    # success 0, counted as a failure).
+    redo = np.nonzero(status == _abi.ST_CAPACITY)[0]
+    if redo.size:
+        logging.info("Trying to decode %d syndromes with multiply_by_stabiliser=True.", redo.size)
+        d2, s2, st2 = decode_css_batch(code, [shard[b] for b in redo], return_status=True,
+                                       multiply_by_stabiliser=True, rng=np.random.default_rng([seed, rank]), **kw)
+        dist_rows[redo], failure[redo] = d2, (1 - s2)
+        lost = redo[st2 == _abi.ST_CAPACITY]
+        dist_rows[lost], failure[lost] = np.nan, np.nan
+        if lost.size:
+            logging.error("Decoding has not been completed for %d syndromes.", lost.size)
     device = torch.device("cuda", torch.cuda.current_device())
     counts = D.reduce_counts(D.local_counts(dist_rows, success), device)
     all_rows = D.gather_rows(dist_rows, device)
-    all_fail = D.gather_rows((1 - success).astype(np.float64).reshape(-1, 1), device).reshape(-1)
+    all_fail = D.gather_rows(failure.reshape(-1, 1), device).reshape(-1)
     if not silent and rank == 0:
         logging.info("decoded %d syndromes, %d successes, %d NaN", *[int(c) for c in counts])
     return {
         "logicals_distributions": [row for row in all_rows],
-        "failures": [int(f) for f in all_fail],
+        "failures": [int(f) if f == f else float("nan") for f in all_fail],
         "lattice_size": lattice_size, "chi_max": chi_max, "error_rate": error_rate, "bias_prob": bias_prob,
         "error_model": error_model, "seed": seed, "tolerance": tolerance, "cut": cut,
     }

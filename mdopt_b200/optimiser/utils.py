@@ -27,14 +27,66 @@ XOR_RIGHT = _table((2, 1, 2, 2), lambda l, r, u, d: l == u and u == d)          
 SWAP = _table((2, 2, 2, 2), lambda l, r, u, d: l == r and u == d)                 # pass both through
 
 
-def msro(location_matrix: np.ndarray) -> List[int]:
-    """Row order for the "Optimised" strategy.
+def _front_profile(spans, order, n_cols):
+    """(largest front, summed front) of applying the strings in `order`: the front after each string is the number
+    of sites covered by an applied string that still have unapplied strings crossing them."""
+    cover, ahead = np.zeros(n_cols, dtype=int), np.zeros(n_cols, dtype=int)
+    for lo, hi in spans:
+        ahead[lo:hi + 1] += 1
+    worst = total = 0
+    for r in order:
+        lo, hi = spans[r]
+        cover[lo:hi + 1] += 1
+        ahead[lo:hi + 1] -= 1
+        front = int(np.count_nonzero((cover > 0) & (ahead > 0)))
+        worst, total = max(worst, front), total + front
+    return worst, total
 
-    The reference calls ``matrex.msro`` (optimiser/utils.py:270-279), a third-party front-minimisation
-    routine that is not available (no source, wheel or recorded order in the reference tree).  This
-    replacement orders the strings by (first site, last site), which keeps the active front moving left
-    to right; untruncated results do not depend on the order.  Pass ``order=`` to override.
-    """
+
+def front_minimising_order(location_matrix: np.ndarray) -> List[int]:
+    """A matrix-front minimiser for the "Optimised" strategy (what ``matrex.msro`` is described as; the real routine
+    is unavailable -- no source, wheel or recorded order in the reference tree).  The *front* after applying a
+    string is the number of MPS sites covered by an applied string that still have unapplied strings crossing them,
+    which is what drives the intermediate bond dimensions.  Candidates: the (first site, last site) sweep, the
+    (last site, first site) sweep, and a greedy order that always applies the string leaving the smallest front; the
+    candidate with the smallest (largest front, summed front) wins.  Select it with ``order="front"``
+    (``orders={"xc": "front"}`` in the decoders); the default stays the (first site, last site) order the reference
+    fixtures were generated with.  Untruncated results do not depend on the order."""
+    m = np.asarray(location_matrix) != 0
+    n_rows, n_cols = m.shape
+    spans = []
+    for r in range(n_rows):
+        nz = np.nonzero(m[r])[0]
+        spans.append((int(nz[0]), int(nz[-1])) if nz.size else (0, 0))
+    remaining = set(range(n_rows))
+    cover, ahead = np.zeros(n_cols, dtype=int), np.zeros(n_cols, dtype=int)
+    for lo, hi in spans:
+        ahead[lo:hi + 1] += 1
+    greedy: List[int] = []
+    while remaining:
+        best, best_key = None, None
+        for r in remaining:
+            lo, hi = spans[r]
+            cov, ah = cover.copy(), ahead.copy()
+            cov[lo:hi + 1] += 1
+            ah[lo:hi + 1] -= 1
+            key = (int(np.count_nonzero((cov > 0) & (ah > 0))), lo, hi, r)
+            if best_key is None or key < best_key:
+                best, best_key = r, key
+        lo, hi = spans[best]
+        cover[lo:hi + 1] += 1
+        ahead[lo:hi + 1] -= 1
+        remaining.remove(best)
+        greedy.append(best)
+    first_last = sorted(range(n_rows), key=lambda r: (spans[r][0], spans[r][1], r))
+    last_first = sorted(range(n_rows), key=lambda r: (spans[r][1], spans[r][0], r))
+    return min((first_last, last_first, greedy), key=lambda o: _front_profile(spans, o, n_cols))
+
+
+def msro(location_matrix: np.ndarray) -> List[int]:
+    """Default row order for the "Optimised" strategy, standing in for ``matrex.msro`` (optimiser/utils.py:270-279):
+    strings sorted by (first site, last site), which keeps the active front moving left to right.  The order is an
+    explicit input shared with the oracle (``order=`` / ``orders=``); ``front_minimising_order`` is the alternative."""
     m = np.asarray(location_matrix)
     keys = []
     for r in range(m.shape[0]):

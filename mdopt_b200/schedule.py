@@ -13,7 +13,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from mdopt_b200.optimiser.utils import (COPY_LEFT, SWAP, XOR_BULK, XOR_LEFT, XOR_RIGHT, ConstraintString, msro)
+from mdopt_b200.optimiser.utils import (COPY_LEFT, SWAP, XOR_BULK, XOR_LEFT, XOR_RIGHT, ConstraintString,
+                                        front_minimising_order, msro)
 
 OP_END, OP_SWEEP, OP_MOVE, OP_MARGINAL, OP_GATE2, OP_COMPRESS = 0, 1, 2, 3, 4, 5
 MODE_FAST, MODE_SVD, MODE_SVD_GRAM, MODE_MONO = 0, 1, 2, 3
@@ -169,13 +170,18 @@ def order_strings(strings, n_sites: int, strategy: str, order: Optional[Sequence
     """"Optimised" reorders the strings (optimiser/utils.py:270-279); "Naive" keeps them."""
     if strategy != "Optimised":
         return list(strings)
-    if order is None:
+    if order is None or isinstance(order, str):
         loc = np.zeros((len(strings), n_sites), dtype=int)
         for r, groups in enumerate(strings):
             for group in groups:
                 for site in group:
                     loc[r, site] = 1
-        order = msro(loc)
+        if order is None:
+            order = msro(loc)
+        elif order == "front":
+            order = front_minimising_order(loc)
+        else:
+            raise ValueError(f"unknown ordering {order!r} (None, 'front' or an explicit list of rows)")
     return [strings[i] for i in order]
 
 

@@ -173,3 +173,79 @@ def test_stabiliser_helpers_follow_reference_conventions():
     assert multiply_pauli_strings("XZ", "ZX") == "YY"
     with pytest.raises(ValueError):
         multiply_pauli_strings("XX", "X")
+
+
+def test_code_constructors_give_valid_css_codes():
+    """hypergraph_product / repetition_code / random_regular_code (the qecstruct constructors the drivers use)."""
+    from mdopt_b200.codes import hypergraph_product, random_regular_code, repetition_code, surface_code
+
+    s3, ref = hypergraph_product(repetition_code(3), repetition_code(3)), surface_code(3)
+    assert s3.x_stabs_binary().rows() == ref.x_stabs_binary().rows()
+    assert s3.z_stabs_binary().rows() == ref.z_stabs_binary().rows()
+    assert s3.x_logicals_binary().rows() == [[2, 5, 8]] and s3.z_logicals_binary().rows() == [[0, 1, 2]]
+
+    def mat(rows, n):
+        m = np.zeros((len(rows), n), dtype=int)
+        for i, r in enumerate(rows):
+            m[i, r] = 1
+        return m
+
+    def rank(m):
+        m, r = m.copy() % 2, 0
+        for c in range(m.shape[1]):
+            piv = [i for i in range(r, m.shape[0]) if m[i, c]]
+            if not piv:
+                continue
+            m[[r, piv[0]]] = m[[piv[0], r]]
+            for i in range(m.shape[0]):
+                if i != r and m[i, c]:
+                    m[i] ^= m[r]
+            r += 1
+        return r
+
+    ldpc = random_regular_code(16, 12, 3, 4, 7)   # the classical code of quantum_hypergraph_product.py:134-142
+    h = mat(ldpc.par_mat().rows(), 16)
+    assert (h.sum(axis=0) == 3).all() and (h.sum(axis=1) == 4).all()
+    assert random_regular_code(16, 12, 3, 4, 7).par_mat().rows() == ldpc.par_mat().rows()   # seeded
+    with pytest.raises(ValueError):
+        random_regular_code(16, 11, 3, 4, 7)
+    for a, b in [(repetition_code(3), repetition_code(4)), (ldpc, ldpc)]:
+        c = hypergraph_product(a, b)
+        n = len(c)
+        hx, hz = mat(c.x_stabs_binary().rows(), n), mat(c.z_stabs_binary().rows(), n)
+        lx, lz = mat(c.x_logicals_binary().rows(), n), mat(c.z_logicals_binary().rows(), n)
+        k = n - rank(hx) - rank(hz)
+        assert not (hx @ hz.T % 2).any() and not (lx @ hz.T % 2).any() and not (lz @ hx.T % 2).any()
+        assert len(lx) == len(lz) == k == c.num_x_logicals() == c.num_z_logicals()
+        assert rank(np.vstack([hx, lx])) == rank(hx) + k and rank(lx @ lz.T % 2) == k
+    assert len(hypergraph_product(ldpc, ldpc)) == 400
+
+
+def test_front_minimising_order():
+    from mdopt_b200.optimiser.utils import front_minimising_order, msro
+
+    rng = np.random.default_rng(4)
+    loc = np.zeros((12, 40), dtype=int)
+    for r in range(12):
+        lo = rng.integers(0, 30)
+        loc[r, lo:lo + rng.integers(2, 10)] = 1
+    order = front_minimising_order(loc)
+    assert sorted(order) == list(range(12))
+
+    def max_front(o):
+        spans = [(np.nonzero(loc[r])[0][0], np.nonzero(loc[r])[0][-1]) for r in range(12)]
+        cover, ahead, worst = np.zeros(40, int), np.zeros(40, int), 0
+        for lo, hi in spans:
+            ahead[lo:hi + 1] += 1
+        for r in o:
+            lo, hi = spans[r]
+            cover[lo:hi + 1] += 1
+            ahead[lo:hi + 1] -= 1
+            worst = max(worst, int(np.count_nonzero((cover > 0) & (ahead > 0))))
+        return worst
+
+    assert max_front(order) <= max_front(msro(loc))
+    code = __import__("mdopt_b200.codes", fromlist=["surface_code"]).surface_code(3)
+    prog_a = schedule.build_decode_program(code, True, False, True, "Optimised", {"xc": "front"})
+    prog_b = schedule.build_decode_program(code, True, False, True, "Optimised")
+    assert prog_a.n_strings == prog_b.n_strings and sorted(prog_a.spans) == sorted(prog_b.spans)
