@@ -47,12 +47,24 @@ def mps_mpo_contract(mps: Union[ExplicitMPS, CanonicalMPS], mpo: List[np.ndarray
         )
     if len(mpo) < 2:
         raise ValueError("the MPO must cover at least two sites")
+    centre = work.orth_centre if work.orth_centre is not None else work.resolve_orth_centre()
+    from mdopt_b200 import generic
+
+    if generic.needs_generic(work.tensors, mpo):
+        # complex dtype, physical dimension != 2, MPO bond > 2 or bonds beyond the compiled capacities: the same
+        # zip-up through the library tier (cuBLAS / cuSOLVER on the device), see mdopt_b200/generic.py
+        tensors, new_centre = generic.mps_mpo_contract_generic(work.tensors, centre, mpo, start_site, renormalise,
+                                                               chi_max, cut, work.chi_max)
+        out = CanonicalMPS(tensors, new_centre, work.tolerance, work.chi_max)
+        if inplace and isinstance(mps, CanonicalMPS):
+            mps.tensors, mps.orth_centre = out.tensors, out.orth_centre
+            return mps
+        return out
     table = schedule.TensorTable()
     ids = [table.add(np.asarray(t)) for t in mpo]
     ops = np.array([schedule.OP_SWEEP, start_site, len(mpo), 0, int(bool(renormalise))] + ids + [schedule.OP_END],
                    dtype=np.int32)
     wtab, wdim = table.arrays()
-    centre = work.orth_centre if work.orth_centre is not None else work.resolve_orth_centre()
     res = engine.run_program_on_mps(work.tensors, centre, ops, wtab, wdim, chi_max, cut, False, mode=mode)
     tensors = res["tensors"]
     if renormalise:  # reference quirk: the *left neighbour* of the new centre is normalised (:363-369)

@@ -118,7 +118,11 @@ class CanonicalMPS:
         centre = self.orth_centre if self.orth_centre is not None else self.resolve_orth_centre()
         if centre == final_pos:
             return self
-        from mdopt_b200 import engine, schedule
+        from mdopt_b200 import engine, generic, schedule
+
+        if generic.needs_generic(self.tensors):   # complex / phys dim != 2 / large bonds: library tier (generic.py)
+            tensors, c = generic.move_orth_centre_generic(self.tensors, centre, final_pos, self.chi_max)
+            return CanonicalMPS(tensors, c, self.tolerance, self.chi_max)
 
         ops = np.array([schedule.OP_MOVE, final_pos, schedule.OP_END], dtype=np.int32)
         table = schedule.TensorTable()
@@ -167,6 +171,12 @@ class CanonicalMPS:
         if strategy != "svd":
             raise NotImplementedError("the GPU engine provides the 'svd' compression strategy")
         centre = self.orth_centre if self.orth_centre is not None else self.resolve_orth_centre()
+        from mdopt_b200 import generic
+
+        if generic.needs_generic(self.tensors):   # complex / large bonds: library tier, same steps
+            tensors, c, err = generic.compress_bond_generic(self.tensors, centre, bond, chi_max, cut, renormalise,
+                                                            self.chi_max)
+            return (CanonicalMPS(tensors, c, self.tolerance, self.chi_max), (err if return_truncation_error else None))
         out, errors = self._run_compress([bond], chi_max, cut, renormalise, centre)
         return out, (errors[0] if return_truncation_error else None)
 
@@ -185,7 +195,16 @@ class CanonicalMPS:
             work = CanonicalMPS([np.ascontiguousarray(np.transpose(t)) for t in reversed(self.tensors)],
                                 self.num_sites - 1 - centre, self.tolerance, self.chi_max)
             centre = work.orth_centre
-        out, errors = work._run_compress(list(range(self.num_bonds)), chi_max, cut, renormalise, centre)
+        from mdopt_b200 import generic
+
+        if generic.needs_generic(work.tensors):
+            out, errors = work, []
+            for bond in range(self.num_bonds):
+                out, err = out.compress_bond(bond, chi_max=chi_max, cut=cut, renormalise=renormalise,
+                                             return_truncation_error=True)
+                errors.append(err)
+        else:
+            out, errors = work._run_compress(list(range(self.num_bonds)), chi_max, cut, renormalise, centre)
         if from_last:
             out = CanonicalMPS([np.ascontiguousarray(np.transpose(t)) for t in reversed(out.tensors)],
                                self.num_sites - 1 - out.orth_centre, self.tolerance, self.chi_max)
@@ -195,8 +214,9 @@ class CanonicalMPS:
     def marginal(self, sites_to_marginalise: List[int], renormalise: bool = False) -> "CanonicalMPS":
         """Trace sites out with (1,..,1)/sqrt(d); MUTATES and returns self (reference canonical.py:906-991).
 
-        The GPU engine implements the case the decoder uses -- a contiguous tail ``k..N-1`` traced into
-        the leading ``k`` sites (decoding.py:1348-1356); other site sets raise ``NotImplementedError``.
+        The engine kernel implements the case the decoder uses -- a contiguous tail ``k..N-1`` traced into the leading
+        ``k`` sites (decoding.py:1348-1356); any other site set runs the same chain on the device through the library
+        tier (``mdopt_b200/generic.py``).
         """
         if not sites_to_marginalise:
             return self
@@ -204,8 +224,15 @@ class CanonicalMPS:
             raise ValueError("The list of sites to marginalise must be a subset of the list of all sites.")
         sites = sorted(set(sites_to_marginalise))
         k = sites[0]
-        if sites != list(range(k, self.num_sites)) or not 1 <= k <= 12:
-            raise NotImplementedError("the GPU marginal supports a contiguous tail k..N-1 with 1 <= k <= 12")
+        from mdopt_b200 import generic
+
+        if sites != list(range(k, self.num_sites)) or not 1 <= k <= 12 or generic.needs_generic(self.tensors):
+            # any other site set (or dtype / dimensions outside the engine): the same chain through the library tier
+            self.tensors[:] = generic.marginal_generic(self.tensors, sites, renormalise)
+            self.num_sites = len(self.tensors)
+            self.num_bonds = self.num_sites - 1
+            self.orth_centre = self.num_sites - 1
+            return self
         from mdopt_b200 import engine, schedule
         from mdopt_b200.optimiser.utils import IDENTITY
 

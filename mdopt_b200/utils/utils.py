@@ -57,8 +57,15 @@ def svd(mat: np.ndarray, cut: float = float(1e-12), chi_max: int = int(1e4), ren
     mat = np.asarray(mat)
     if mat.ndim != 2:
         raise ValueError(f"A valid matrix must have 2 dimensions while the one given has {mat.ndim}.")
-    if np.iscomplexobj(mat):
-        raise NotImplementedError("the GPU SVD is real FP64")
+    if np.iscomplexobj(mat) or max(mat.shape) > 128:
+        # complex or beyond the shared-memory Jacobi kernel (128 x 128): cuSOLVER through the library tier
+        from mdopt_b200 import generic
+
+        torch = _lib.require_gpu()[1]
+        dmat = torch.as_tensor(np.ascontiguousarray(mat), device=generic._DEVICE)
+        u, s, vh, err = generic.svd_device(dmat, cut=cut, chi_max=chi_max, renormalise=renormalise)
+        out = (u.cpu().numpy(), s.cpu().numpy().astype(float), vh.cpu().numpy())
+        return out + ((err,) if return_truncation_error else (None,))
     u, s, vh, kept, trunc, _ = svd_batch(mat[None], cut=cut, chi_max=chi_max, renormalise=renormalise)
     k = int(kept[0])
     out = (np.ascontiguousarray(u[0][:, :k]), np.ascontiguousarray(s[0][:k]), np.ascontiguousarray(vh[0][:k, :]))
