@@ -484,14 +484,115 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def seeded_depolarising_errors(n_qubits, rate, count, seed, offset=0):
+    """Depolarising error strings from seeded per-syndrome generators (the reference draws the Pauli
+    from the unseeded global RNG, decoding.py:1018, so the letter comes from the syndrome's own generator here)."""
+    ss = np.random.SeedSequence(seed, n_children_spawned=offset)
+    out = []
+    for child in ss.spawn(count):
+        rng = np.random.default_rng(child)
+        out.append("".join("XYZ"[int(rng.integers(3))] if rng.random() < rate else "I" for _ in range(n_qubits)))
+    return out
+
+
+def run_config3(args):
+    """`--workload config3` (BASELINE.json configs[2]): d = 9 surface code, depolarising noise AND depolarising bias,
+    chi_max = 256 -- the rotation-bound regime, on the dense CTA engine (the two-site bias gates leave the monomial
+    structure).  One step decodes `--batch` syndromes (default: one per SM); the CPU reference needs hours per
+    syndrome at this size, so no CPU sample is taken."""
+    import torch
+    import torch.distributed as dist
+
+    from mdopt_b200 import _lib, engine
+    from mdopt_b200.codes import surface_code
+    from mdopt_b200.decoding import decode_css_batch
+
+    _lib.require_gpu()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    L, chi = args.lattice, args.chi
+    code = surface_code(L)
+    n = len(code)
+    B = args.batch
+    errors = seeded_depolarising_errors(n, ERROR_RATE, B, SEED, offset=rank * B)
+    kw = dict(chi_max=chi, cut=CUT, bias_type="Depolarising", bias_prob=BIAS, contraction_strategy="Optimised",
+              mode="svd", return_status=True)
+    fp64_peak = measure_fp64_peak(torch, device) if rank == 0 else 0.0
+    for _ in range(args.warmup):
+        decode_css_batch(code, errors, **kw)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    times, flops, nbytes, steps = [], 0.0, 0.0, 0.0
+    for _ in range(args.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d, s, st = decode_css_batch(code, errors, **kw)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        for eng in engine._ENGINES.values():   # counters of the last launch (one flag group per launch)
+            c = eng.read_counters()
+            flops += c["flops_qr"] + c["flops_jacobi"] + c["flops_apply"]
+            nbytes += c["bytes"]
+            steps += c["steps"]
+    t = torch.tensor([sum(times)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        total = B * world * args.steps
+        value = total / float(t.item())
+        hbm_peak, src = hbm_peak_gbs()
+        line = {
+            "metric": "decoded syndromes/sec", "value": value, "unit": "syndromes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(t.item()) / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"surface_d{L}_depolarising_p{ERROR_RATE}_bias{BIAS}_chi{chi}_cut{CUT}_optimised",
+                       "batch_per_gpu": B, "seed": SEED, "mode": "svd (dense CTA engine)",
+                       "note": "timed through decode_css_batch (host strings in, host arrays out); the flag groups "
+                               "(X only / Z only / X and Z / none) are separate launches; last-launch counters"},
+            "e2e": {"value": value, "unit": "syndromes/s", "h2d_bytes_per_step": int(B * (2 * n + 2)),
+                    "d2h_bytes_per_step": int(B * 40)},
+            "gpu_launches": args.steps * 4,
+            "roofline": {"bound": "tensor", "achieved": flops / sum(times) / 1e12 / max(world, 1), "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": (flops / sum(times) / 1e12) / fp64_peak if fp64_peak else None,
+                         "traffic": None, "kernel": f"decode_kernel<{256 if chi > 128 else (128 if chi > 64 else 64)}>",
+                         "note": "FLOPs counted by the kernel (Jacobi rotations + dot products, contractions) of the "
+                                 "last launch of each step / wall time of the step; peak = cuBLAS DGEMM 8192^3 measured "
+                                 "in this run", "hbm": {"algorithmic_bytes": nbytes, "peak_gbs": hbm_peak, "source": src},
+                         "two_site_steps": steps},
+            "clocks": sampler.summary(),
+            "counts": {"decoded": int(len(errors)), "success": int(s.sum()), "nan": int(np.isnan(d).any(axis=1).sum()),
+                       "status_not_ok_rank0": int((st != 0).sum())},
+            "cpu_baseline": {"value": None, "unit": "syndromes/s", "cores": 0, "kind": "reference",
+                             "sample": "not taken: one decode of this configuration by the reference exceeds the 30 s "
+                                       "bound by orders of magnitude (SURVEY.md 8(d): O(10^2) TFLOP per decode)"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=CONFIG2_BATCH,
-                    help="syndromes per step: per GPU (weak scaling) or in total (--scaling strong)")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="syndromes per step: per GPU (weak scaling) or in total (--scaling strong); default 100000 "
+                         "(config2) / 148 (config3)")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
+                    help="config2 (default, the headline): d=5 bit-flip chi_max=64; config3: d=9 depolarising chi_max=256")
+    ap.add_argument("--lattice", type=int, default=9, help="config3 only: lattice size")
+    ap.add_argument("--chi", type=int, default=256, help="config3 only: chi_max")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): every GPU decodes its own --batch shard; strong: ONE --batch sharded over the GPUs")
     ap.add_argument("--mode", default="mono", choices=["mono", "fast", "svd", "svd-gram"],
@@ -499,10 +600,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = CONFIG2_BATCH if args.workload == "config2" else 148
     if args.cpu_sample:
         cpu_sample_main()
     elif args.impl == "reference":
         run_reference(args)
+    elif args.workload == "config3":
+        run_config3(args)
     else:
         run_ours(args)
 
