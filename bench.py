@@ -468,7 +468,9 @@ def run_ours(args):
             "nontrivial_rate": value * len(nontriv) / max(B, 1),
             "e2e": {"value": e2e_value, "unit": "syndromes/s", "h2d_bytes_per_step": int(syms.nbytes),
                     "d2h_bytes_per_step": int(len(nontriv) * ((1 << k) * 8 + 8))},
-            "gpu_launches": args.steps,
+            # kernels of ours inside the timed region: per step the table set-up kernel + the decode kernel (mono),
+            # or the decode kernel alone (dense modes)
+            "gpu_launches": args.steps * (2 if mono else 1),
             "roofline": roof,
             "clocks": sampler.summary(),
             "counts": {"decoded": int(counts[0]), "success": int(counts[1]), "nan": int(counts[2]),

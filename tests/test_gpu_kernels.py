@@ -253,8 +253,13 @@ def test_marginal_tail_on_gpu(torch_mod):
         got = ours.marginal(list(range(2, 7)), renormalise=ren)
         assert got is ours and len(got.tensors) == 2 and got.orth_centre == 1
         np.testing.assert_allclose(got.dense(), ref.dense(), rtol=1e-12, atol=1e-14)
-    with pytest.raises(NotImplementedError):
-        ours.marginal([0])
+    # any other site set runs the same chain through the library tier (mdopt_b200/generic.py)
+    omps = _random_canonical_mps(rng, 6, 8)
+    ours = CanonicalMPS([t.copy() for t in omps.tensors], 0)
+    ref = O.marginal(omps.copy(), [0, 3], renormalise=False)
+    got = ours.marginal([0, 3])
+    assert len(got.tensors) == len(ref.tensors) == 4
+    np.testing.assert_allclose(got.dense(), ref.dense(), rtol=1e-12, atol=1e-14)
     with pytest.raises(ValueError):
         ours.marginal([99])
 
