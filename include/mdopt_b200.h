@@ -54,6 +54,12 @@ extern "C" {
 #define MDOPT_OP_GATE2 4    /* [4, site, gate_id, renormalise] two-site gate G[j][l][n][o] (16 doubles in wtab) on
                                (site, site+1), then split with chi=capacity / cut_move (depolarising bias) */
 
+#define MDOPT_OP_MARGINAL_DMRG 6 /* [6, sweeps] monomial engine only: marginalise sites n_logical..N-1, then the
+                                   Dephasing-DMRG read-out from |+...+> (decoding.py:1382-1400,
+                                   mdopt/optimiser/dephasing_dmrg.py:147-374); dist[b] = the n_logical bits of the main
+                                   component in the order of the reversed logical chain, success[b] = overlap with
+                                   |0...0> (1 or 0).  For more than 12 logical sites, where the output stride is
+                                   n_logical doubles instead of 2^n_logical */
 #define MDOPT_OP_COMPRESS 5 /* [5, bond, renorm_spectrum] compress_bond (mdopt/mps/canonical.py:684-784, "svd"): centre to
                                `bond`, split theta(bond, bond+1) with chi_max / cut_sweep, leave U.S at `bond` */
 
@@ -133,7 +139,8 @@ int mdopt_decode_batch_host(const mdopt_decode_desc* desc, int chi_cap, int n_ct
  * relies on at every step; a syndrome that leaves it gets MDOPT_ST_NOT_MONOMIAL and must be re-run through
  * mdopt_decode_batch_*.  Arguments as for mdopt_decode_batch_device / _host, with warps in place of CTAs;
  * desc->mode is ignored; counters = {0, 0, 0, bytes, steps, truncating steps, 0, fallbacks, 0...}.
- * Capacities: 8, 16, ..., 512.
+ * Capacities: 8, 16, ..., 512.  n_logical may be up to 64 here: above 12 the program must end with
+ * MDOPT_OP_MARGINAL_DMRG and dist holds n_logical doubles per syndrome.
  */
 int mdopt_mono_chi_capacity(int chi);
 int mdopt_mono_num_warps(int chi_cap);

@@ -47,7 +47,7 @@ struct double2 { double x, y; };  // host stand-in for the CUDA vector type
 #endif
 
 // program opcodes, factorisation modes and per-syndrome status codes (include/mdopt_b200.h), shared by both engines
-enum { OP_END = 0, OP_SWEEP = 1, OP_MOVE = 2, OP_MARGINAL = 3, OP_GATE2 = 4, OP_COMPRESS = 5 };
+enum { OP_END = 0, OP_SWEEP = 1, OP_MOVE = 2, OP_MARGINAL = 3, OP_GATE2 = 4, OP_COMPRESS = 5, OP_MARGINAL_DMRG = 6 };
 enum { MODE_FAST = 0, MODE_SVD = 1, MODE_SVD_GRAM = 2, MODE_MONO = 3 };
 enum { ST_OK = 0, ST_NOT_CONVERGED = 1, ST_CAPACITY = 2, ST_ZERO_NORM = 3, ST_NOT_MONOMIAL = 4 };
 

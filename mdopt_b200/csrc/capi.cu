@@ -156,7 +156,9 @@ int mdopt_mono_decode_batch_device(const mdopt_decode_desc* desc, int chi_cap, i
   if (!desc || !program || !wtab || !wdim || !symbols || !dist || !success || !status || !workspace)
     return MDOPT_E_BADARG;
   if (batch <= 0 || n_warps <= 0 || n_tensors <= 0) return MDOPT_E_BADARG;
-  if (desc->n_logical < 1 || desc->n_logical > 12 || desc->n_sites <= desc->n_logical) return MDOPT_E_BADARG;
+  // up to 12 logical sites: dense read-out (2^k doubles per syndrome); 13..64: Dephasing-DMRG read-out (k doubles)
+  if (desc->n_logical < 1 || desc->n_logical > 64 || desc->n_sites <= desc->n_logical) return MDOPT_E_BADARG;
+  if (desc->n_logical > 2 * chi_cap) return MDOPT_E_CAPACITY;
   const mdopt::MonoOps* ops = mono_ops_for(chi_cap);
   if (!ops || desc->chi_max < 1 || desc->chi_max > chi_cap) return MDOPT_E_CAPACITY;
   return ops->decode(desc, n_warps, program, wtab, wdim, n_tensors, symbols, batch, dist, success, status, trace,
@@ -172,7 +174,7 @@ int mdopt_mono_decode_batch_host(const mdopt_decode_desc* desc, int chi_cap, int
     return MDOPT_E_BADARG;
   if (batch <= 0) return MDOPT_E_BADARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const size_t ncls = (size_t)1 << desc->n_logical;
+  const size_t ncls = desc->n_logical > 12 ? (size_t)desc->n_logical : ((size_t)1 << desc->n_logical);
   cudaError_t e = cudaMemcpyAsync(d_symbols, h_symbols, (size_t)batch * desc->n_sites, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return (int)e;
   mdopt_decode_desc d2 = *desc;

@@ -110,6 +110,7 @@ struct MonoState {
   int* bd;                  // [n_sites + 1] bond dimensions (global)
   const MonoTensor* tabs;   // [1 + n_tensors]
   double* trace;
+  double* env;              // [(n_head + 1) * CHI] Dephasing-DMRG environments (global), or nullptr
   DecodeParams P;
   MonoCounters cnt;
   int n_traced, status, centre, K, Wq, Mr, mirrored;
@@ -653,12 +654,156 @@ struct Mono {
     MW_SYNC();
   }
 
+  // ---- Dephasing-DMRG read-out for more than 12 logical sites (decoding.py:1382-1400 ->
+  //      mdopt/optimiser/dephasing_dmrg.py:147-374, started from |+...+>, mode "LA").
+  // The reference's search MPS is snapped to one computational-basis configuration after every bond update
+  // (:236-249), so it keeps bond dimension 1 and every site is '+', 0 or 1; its environments are then outer products
+  // of a vector with itself and the effective two-site operator (_EINSUM, :47) is diagonal in the computational
+  // basis with entries |l . T_i[a] . T_{i+1}[b] . r|^2.  eigsh(k=1) returns the basis vector of the largest entry
+  // (first maximal index on exact ties).  Here the target tensors are monomial, so l / r are vectors of <= chi
+  // entries updated by gathers / scatters, and a bond update is four warp reductions.
+  // The engine works on the REVERSED logical chain (decoding.py:1351-1356): reversed site i = logical site
+  // kL-1-i.  out[i] = bit of reversed site i (what engine.mps holds); *success = overlap with |0...0>. ----
+  static MW_PHASE void dmrg_readout(SM& s, double* out, int* success, int iters) {
+    const DecodeParams& P = s.state.P;
+    const int kL = P.n_head;
+    const MonoSite<CHI>* sites = s.state.sites;
+    const int* bd = s.state.bd;
+    double* env = s.state.env;                 // [kL + 1][CHI] far-side environments of the current half sweep (global)
+    int16_t* bit = s.rank;                     // per logical site: -1 = '+', else the bit (kL <= 2*CHI)
+    double* near = s.sig;                      // near-side environment, updated as the sweep moves
+    double* tmp = s.sv;
+    const double isq2 = 1.0 / sqrt(2.0);
+    if (kL > N2 || env == nullptr) { s.state.status = ST_CAPACITY; MW_SYNC(); return; }
+    MW_FOR(j, kL) bit[j] = -1;
+    MW_SYNC();
+    // weight of physical value p on site j under the current search state
+    auto wgt = [&](int j, int p) -> double { const int b = bit[j]; return b < 0 ? isq2 : (b == p ? 1.0 : 0.0); };
+    auto dimL = [&](int j) -> int { return bd[j]; };
+    // far-side environments: forward[j] = contraction of sites < j (left bond vector of site j)
+    auto build_forward = [&]() {
+      MW_LANE0 { env[0] = 1.0; }
+      MW_SYNC();
+      for (int j = 0; j + 1 < kL; ++j) {
+        const double* cur = env + (size_t)j * CHI;
+        double* nxt = env + (size_t)(j + 1) * CHI;
+        const int A = dimL(j), B = dimL(j + 1);
+        MW_FOR(b, B) nxt[b] = 0.0;
+        MW_SYNC();
+        for (int p = 0; p < 2; ++p) {     // for a fixed p every target has one writer (p-monomial tensors)
+          const double w = wgt(j, p);
+          if (w != 0.0) {
+            MW_FOR(a, A) {
+              const int t = sites[j].tgt[a * 2 + p];
+              if (t >= 0) nxt[t] += cur[a] * sites[j].val[a * 2 + p] * w;
+            }
+          }
+          MW_SYNC();
+        }
+      }
+    };
+    // backward[j] = contraction of sites >= j (left bond vector of site j), backward[kL] = [1]
+    auto build_backward = [&]() {
+      MW_LANE0 { env[(size_t)kL * CHI] = 1.0; }
+      MW_SYNC();
+      for (int j = kL - 1; j >= 2; --j) {
+        const double* nxt = env + (size_t)(j + 1) * CHI;
+        double* cur = env + (size_t)j * CHI;
+        const int A = dimL(j);
+        MW_FOR(a, A) {
+          double acc = 0.0;
+          for (int p = 0; p < 2; ++p) {
+            const int t = sites[j].tgt[a * 2 + p];
+            if (t >= 0) acc += wgt(j, p) * sites[j].val[a * 2 + p] * nxt[t];
+          }
+          cur[a] = acc;
+        }
+        MW_SYNC();
+      }
+    };
+    // bond update on logical sites (j, j+1): lv = left vector of site j, rv = left vector of site j+2
+    auto update = [&](int j, const double* lv, const double* rv) {
+      const int A = dimL(j);
+      double w[4] = {0.0, 0.0, 0.0, 0.0};    // index a*2 + b: a = bit of logical site j+1 (reversed site i), b = site j
+      MW_FOR(bl, A) {
+        const double l = lv[bl];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int bm = sites[j].tgt[bl * 2 + b];
+          if (bm < 0) continue;
+          const double lb = l * sites[j].val[bl * 2 + b];
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const int br = sites[j + 1].tgt[bm * 2 + a];
+            if (br >= 0) w[a * 2 + b] += lb * sites[j + 1].val[bm * 2 + a] * rv[br];
+          }
+        }
+      }
+      // first maximal index, like the snap's argmax (:245); weights within 1e-9 relative of the largest count as
+      // tied (exact ties -- unconstrained logical sites -- differ by rounding noise between implementations)
+      double v2[4], top = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const double v = mw_sum(w[q]); v2[q] = v * v; top = fmax(top, v2[q]); }
+      int best = 3;
+#pragma unroll
+      for (int q = 3; q >= 0; --q) { if (v2[q] >= top * (1.0 - 1e-9)) best = q; }
+      MW_SYNC();
+      MW_LANE0 { bit[j + 1] = (int16_t)(best >> 1); bit[j] = (int16_t)(best & 1); }
+      MW_SYNC();
+    };
+    for (int it = 0; it < iters; ++it) {
+      // reversed bonds 0 .. kL-2 = logical bonds (kL-2, kL-1) down to (0, 1): far side = forward vectors
+      build_forward();
+      MW_LANE0 { near[0] = 1.0; }            // left vector of site kL (nothing to the right yet)
+      MW_SYNC();
+      for (int j = kL - 2; j >= 0; --j) {
+        update(j, env + (size_t)j * CHI, near);
+        // near <- left vector of site j+1 = site j+1 (now fixed) applied to the old near
+        const int A = dimL(j + 1);
+        MW_FOR(a, A) {
+          const int p = bit[j + 1];
+          const int t = sites[j + 1].tgt[a * 2 + p];
+          tmp[a] = (t >= 0) ? sites[j + 1].val[a * 2 + p] * near[t] : 0.0;
+        }
+        MW_SYNC();
+        MW_FOR(a, A) near[a] = tmp[a];
+        MW_SYNC();
+      }
+      // back: logical bonds (0, 1) up to (kL-2, kL-1): far side = backward vectors, near = forward from the left
+      build_backward();
+      MW_LANE0 { near[0] = 1.0; }
+      MW_SYNC();
+      for (int j = 0; j + 1 < kL; ++j) {
+        update(j, near, env + (size_t)(j + 2) * CHI);
+        const int A = dimL(j), B = dimL(j + 1);
+        MW_FOR(b, B) tmp[b] = 0.0;
+        MW_SYNC();
+        MW_FOR(a, A) {
+          const int p = bit[j];
+          const int t = sites[j].tgt[a * 2 + p];
+          if (t >= 0) tmp[t] = near[a] * sites[j].val[a * 2 + p];
+        }
+        MW_SYNC();
+        MW_FOR(b, B) near[b] = tmp[b];
+        MW_SYNC();
+      }
+    }
+    int nonzero = 0;
+    MW_FOR(i, kL) { const int b = bit[kL - 1 - i]; out[i] = (double)b; nonzero |= (b != 0); }
+    nonzero = MW_ANY(nonzero);
+    MW_LANE0 { *success = nonzero ? 0 : 1; }
+    MW_SYNC();
+  }
+
   // ---- marginal over sites kL..N-1, reverse, dense, |.|, L2 renorm, tolerant arg-max ----
   //   canonical.py:956-989, :150-161, :241-272; decoding.py:1362-1379
-  static MW_PHASE void marginal_readout(SM& s, double* out, int* success) {
+  static MW_PHASE void marginal_readout(SM& s, double* out, int* success, int dmrg_iters) {
     const DecodeParams& P = s.state.P;
     const int N = P.n_sites, kL = P.n_head, ren = P.renormalise;
-    if (P.kept_mask != ((kL >= 32) ? 0xffffffffu : ((1u << kL) - 1u))) { s.state.status = ST_NOT_MONOMIAL; MW_SYNC(); return; }
+    // (erasures of qubits whose index is a logical-site index change the kept sites: dense engine; not with DMRG)
+    if (dmrg_iters == 0 && P.kept_mask != ((kL >= 32) ? 0xffffffffu : ((1u << kL) - 1u))) {
+      s.state.status = ST_NOT_MONOMIAL; MW_SYNC(); return;
+    }
     MonoSite<CHI>* sites = s.state.sites;
     int* bd = s.state.bd;
     double* T = s.cv;     // current last tensor (L x 2)
@@ -692,6 +837,7 @@ struct Mono {
     MW_FOR(t, L * 2) { sites[kL - 1].val[t] = T[t]; sites[kL - 1].tgt[t] = 0; }
     MW_LANE0 { bd[kL] = 1; s.state.cnt.bytes_hbm += bytes; }
     MW_SYNC();
+    if (dmrg_iters > 0) { dmrg_readout(s, out, success, dmrg_iters); return; }
     // dense stage over the kL logical sites: every class follows one path through the monomial tensors
     const int ncls = 1 << kL;
     double nrm2 = 0.0, top = 0.0; int badv = 0;
@@ -736,8 +882,11 @@ struct Mono {
       const int op = prog[pc];
       if (op == OP_END) break;
       if (op == OP_MARGINAL) {
-        marginal_readout(s, out, success);
+        marginal_readout(s, out, success, 0);
         pc += 1;
+      } else if (op == OP_MARGINAL_DMRG) {   // [6, sweeps]: marginal chain, then the Dephasing-DMRG read-out
+        marginal_readout(s, out, success, prog[pc + 1] > 0 ? prog[pc + 1] : 1);
+        pc += 2;
       } else if (op == OP_SWEEP || op == OP_MOVE) {
         const int target = prog[pc + 1];
         for (int phase = (target == s.state.centre) ? 1 : 0; phase < 2; ++phase) {

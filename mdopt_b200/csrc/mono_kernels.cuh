@@ -8,8 +8,20 @@
 namespace mdopt {
 namespace {
 
-// bytes of global workspace one warp needs: its MPS in monomial form + the bond dimensions
+// doubles of output per syndrome: the 2^k class marginals, or (more than 12 logical sites: Dephasing-DMRG read-out)
+// the k bits of the main component
+__host__ __device__ inline int mono_out_per_syndrome(int n_logical) { return n_logical > 12 ? n_logical : (1 << n_logical); }
+
+// bytes of global workspace one warp needs: its MPS in monomial form + the bond dimensions (+ the environment
+// vectors of the Dephasing-DMRG read-out, (n_logical + 1) x chi doubles, sized for up to MONO_MAX_LOGICAL sites)
+constexpr int MONO_MAX_LOGICAL = 64;
 __host__ __device__ inline size_t mono_ws_bytes_per_warp(int chi, int n_sites) {
+  size_t b = (size_t)n_sites * ((size_t)2 * chi * 10) + ((size_t)n_sites + 1) * sizeof(int);
+  b = (b + 255) & ~(size_t)255;
+  b += (size_t)(MONO_MAX_LOGICAL + 1) * chi * sizeof(double);
+  return (b + 255) & ~(size_t)255;
+}
+__host__ __device__ inline size_t mono_env_offset(int chi, int n_sites) {
   size_t b = (size_t)n_sites * ((size_t)2 * chi * 10) + ((size_t)n_sites + 1) * sizeof(int);
   return (b + 255) & ~(size_t)255;
 }
@@ -49,11 +61,12 @@ mono_decode_kernel(DecodeParams P, const int* __restrict__ prog, const MonoTenso
     MonoState<CHI>& st = s.state;
     st.sites = reinterpret_cast<MonoSite<CHI>*>(base);
     st.bd = reinterpret_cast<int*>(base + (size_t)P.n_sites * sizeof(MonoSite<CHI>));
+    st.env = reinterpret_cast<double*>(base + mono_env_offset(CHI, P.n_sites));
     st.tabs = tabs; st.P = P; st.trace = nullptr;
     st.cnt = MonoCounters{};
   }
   __syncwarp();
-  const int ncls = 1 << P.n_logical;
+  const int ncls = mono_out_per_syndrome(P.n_logical);
   while (true) {
     int b = 0;
     if (lane == 0) b = atomicAdd(work_counter, 1);
@@ -110,7 +123,7 @@ int launch_mono_decode(const mdopt_decode_desc* d, int n_warps, const int32_t* p
   P.n_ops = d->n_ops; P.cut_sweep = d->cut_sweep; P.cut_move = d->cut_move; P.rank_tol = d->rank_tol;
   P.bias_p = d->bias_p;
   P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
-  P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
+  P.kept_mask = d->kept_mask ? d->kept_mask : (d->n_logical >= 32 ? 0xffffffffu : ((1u << d->n_logical) - 1u));
   P.readout_rel = d->readout_rel; P.readout_abs = d->readout_abs;
   P.n_tensors = n_tensors;
   int* work_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + per * (size_t)n_warps);

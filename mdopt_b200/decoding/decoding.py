@@ -111,14 +111,15 @@ def _code_key(code) -> Tuple:
     return (len(code),) + tuple(tuple(tuple(int(c) for c in row) for row in m.rows()) for m in mats)
 
 
-def _program_for(code, has_x, has_z, renormalise, strategy, orders, bias_type="Bitflip", bias_prob=0.1):
+def _program_for(code, has_x, has_z, renormalise, strategy, orders, bias_type="Bitflip", bias_prob=0.1, num_runs=1):
     depol = bias_type != "Bitflip"
-    key = (_code_key(code), has_x, has_z, bool(renormalise), strategy,
+    key = (_code_key(code), has_x, has_z, bool(renormalise), strategy, int(num_runs),
            None if not orders else tuple(sorted((k, v if isinstance(v, str) else tuple(v)) for k, v in orders.items())),
            depol, float(bias_prob) if depol else None)
     if key not in _PROGRAM_CACHE:
         _PROGRAM_CACHE[key] = schedule.build_decode_program(code, has_x, has_z, renormalise, strategy, orders,
-                                                            "Depolarising" if depol else "Bitflip", bias_prob)
+                                                            "Depolarising" if depol else "Bitflip", bias_prob,
+                                                            num_runs)
     return _PROGRAM_CACHE[key]
 
 
@@ -126,12 +127,17 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
                      bias_type: str = "Depolarising", bias_prob: float = float(0.1), renormalise: bool = True,
                      silent: bool = True, contraction_strategy: str = "Naive", tolerance: float = float(1e-12),
                      orders: Optional[dict] = None, mode: str = "auto", return_status: bool = False,
-                     multiply_by_stabiliser: bool = False, rng=None):
+                     multiply_by_stabiliser: bool = False, rng=None, num_runs: int = 1):
     """Decode many independent syndromes on the current GPU.
 
     Returns ``(dist float64[B, 2^k], success int32[B])`` (plus ``status int32[B]`` if asked); row b equals
     what ``decode_css(code, errors[b], ...)`` returns.  All-identity errors take the reference's early exit
     (``[1, 0, 0, 0], 1``, decoding.py:1225-1228).
+
+    Codes with more than 12 logical sites take the reference's Dephasing-DMRG read-out (decoding.py:1382-1400,
+    ``num_runs`` sweeps from |+...+>), run inside the monomial kernel: the first array is then ``bits float64[B, k]``
+    -- the main component found, in the order of the reversed logical chain the reference's engine works on
+    (``engine.mps``) -- and the second the overlap with |0...0> (1 or 0).  Bit-flip bias only.
 
     ``mode``: ``"mono"`` is the monomial warp engine (one warp per syndrome, site tensors as 2*chi (value, target)
     pairs; the structure is verified at every step and a syndrome that leaves it is re-run on the dense engine).
@@ -152,18 +158,25 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
     errors = list(errors)
     B = len(errors)
     if B == 0:
-        empty = (np.zeros((0, 1 << k)), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32))
+        empty = (np.zeros((0, k if k > 12 else 1 << k)), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32))
         return empty if return_status else empty[:2]
-    dist = np.zeros((B, 1 << k))
+    n_out = k if k > 12 else (1 << k)
+    dist = np.zeros((B, n_out))
     success = np.zeros(B, dtype=np.int32)
     status = np.zeros(B, dtype=np.int32)
+    if k > 12 and depol:
+        raise NotImplementedError("more than 12 logical sites: the Dephasing-DMRG read-out needs the bit-flip bias "
+                                  "(the monomial engine); the depolarising bias is dense")
     # whole-batch character tests (decoding.py:1225-1231: trivial / "X" in error / "Z" in error), no per-string Python
     raw = schedule.pack_errors(errors, n)
     trivial = (raw == ord("I")).all(axis=1)
     has_x = (raw == ord("X")).any(axis=1)
     has_z = (raw == ord("Z")).any(axis=1)
     erased = (raw == ord("E")).any(axis=1)
-    dist[trivial, 0], success[trivial] = 1.0, 1
+    if k > 12:
+        success[trivial] = 1     # all bits 0, overlap 1 (the reference's early exit returns [1, 0, 0, 0], 1)
+    else:
+        dist[trivial, 0], success[trivial] = 1.0, 1
     default_mask = (1 << k) - 1
     groups: Dict[Tuple[bool, bool, int], np.ndarray] = {}
     plain = ~trivial & ~erased
@@ -188,7 +201,7 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
         state_raw = schedule.pack_errors(_state_errors(errors, stabs_x + stabs_z, rng), n)
     eng = engine.get_engine(n_sites, k, _effective_chi(chi_max, n_sites))
     for (hx, hz, mask), idx in groups.items():
-        prog = _program_for(code, hx, hz, renormalise, contraction_strategy, orders, bias_type, bias_prob)
+        prog = _program_for(code, hx, hz, renormalise, contraction_strategy, orders, bias_type, bias_prob, num_runs)
         syms = schedule.symbols_from_raw(state_raw[idx], k)
         d, s, st = eng.decode_host(prog, syms, cut=cut, bias_p=(-1.0 if depol else bias_prob),
                                    renormalise=renormalise, mode=mode,
@@ -220,13 +233,31 @@ def decode_css(code, error: str, num_runs: int = int(1), chi_max: int = int(1e4)
     if 2 * len(error) != num_sites - num_logicals:
         raise ValueError(f"The error length is {2 * len(error)}, expected {num_sites - num_logicals}.")
     pauli_to_mps(error)  # validates the characters
-    if num_logicals > 12:
-        raise NotImplementedError("more than 12 logical sites needs the Dephasing DMRG read-out (out of scope)")
     dist, success = decode_css_batch(code, [error], chi_max=chi_max, cut=cut, bias_type=bias_type,
                                      bias_prob=bias_prob, renormalise=renormalise, silent=True,
                                      contraction_strategy=contraction_strategy, tolerance=tolerance, orders=orders,
-                                     mode=mode, multiply_by_stabiliser=multiply_by_stabiliser, rng=rng)
+                                     mode=mode, multiply_by_stabiliser=multiply_by_stabiliser, rng=rng,
+                                     num_runs=num_runs)
+    if num_logicals > 12:
+        # decoding.py:1382-1400 returns (engine, overlap); what callers read from the engine is engine.mps
+        return DephasingDMRGResult([int(b) for b in dist[0]]), float(success[0])
     return dist[0], int(success[0])
+
+
+class DephasingDMRGResult:
+    """What ``decode_css`` hands back in place of the reference's ``DephasingDMRG`` engine for codes with more than 12
+    logical sites: ``bits`` -- the main component the sweeps ended on, one bit per site of the reversed logical chain
+    -- and ``mps``, the same as the bond-dimension-1 ``CanonicalMPS`` the reference's ``engine.mps`` is."""
+
+    def __init__(self, bits: List[int]) -> None:
+        self.bits = list(bits)
+
+    @property
+    def mps(self):
+        from mdopt_b200.mps.canonical import CanonicalMPS
+
+        tensors = [np.eye(2)[b].reshape(1, 2, 1) for b in self.bits]
+        return CanonicalMPS(tensors, 0)
 
 
 def decode_custom_batch(stabilizers: Sequence[str], x_logicals: Sequence[str], z_logicals: Sequence[str],

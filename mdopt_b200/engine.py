@@ -38,6 +38,8 @@ def program_is_monomial_candidate(program: schedule.Program) -> bool:
             pc += 2
         elif op == schedule.OP_MARGINAL:
             pc += 1
+        elif op == schedule.OP_MARGINAL_DMRG:
+            pc += 2
         else:
             return False
     return True
@@ -73,14 +75,18 @@ class DecodeEngine:
         torch = self.torch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.n_sites, self.n_logical, self.chi_max = int(n_sites), int(n_logical), int(chi_max)
-        self.cap = _abi.chi_capacity(max(self.chi_max, _abi.readout_min_capacity(n_logical)))
+        self.cap = 0 if n_logical > 12 else _abi.chi_capacity(max(self.chi_max, _abi.readout_min_capacity(n_logical)))
         self.mono_cap = _abi.mono_chi_capacity(self.chi_max)
         if self.cap == 0 and self.mono_cap == 0:
             raise _lib.MdoptCudaError(
                 f"chi_max={chi_max} exceeds the largest compiled capacity ({_abi.MONO_CAPACITIES[-1]})"
             )
-        if not 1 <= self.n_logical <= 12:
-            raise NotImplementedError("the dense read-out supports 1..12 logical sites")
+        if not 1 <= self.n_logical <= 64:
+            raise NotImplementedError("the read-outs support 1..64 logical sites")
+        # more than 12 logical sites: Dephasing-DMRG read-out of the monomial engine (k doubles per syndrome)
+        self.n_out = self.n_logical if self.n_logical > 12 else (1 << self.n_logical)
+        if self.n_logical > 12:
+            self.cap = 0   # the dense engine's read-out stops at 12 logical sites
         self.counters = torch.zeros(16, dtype=torch.float64, device=self.device)
         self.workspace = None
         self.mono_workspace = None
@@ -130,7 +136,7 @@ class DecodeEngine:
 
     def _alloc(self, batch: int) -> None:
         torch = self.torch
-        ncls = 1 << self.n_logical
+        ncls = self.n_out
         self.max_batch = batch
         self.d_sym = torch.empty((batch, self.n_sites), dtype=torch.uint8, device=self.device)
         self.d_dist = torch.empty((batch, ncls), dtype=torch.float64, device=self.device)
@@ -166,7 +172,7 @@ class DecodeEngine:
         torch = self.torch
         dp = self.upload(program)
         batch = int(d_symbols.shape[0])
-        ncls = 1 << self.n_logical
+        ncls = self.n_out
         if d_dist is None:
             d_dist = torch.empty((batch, ncls), dtype=torch.float64, device=self.device)
         if d_success is None:
@@ -210,6 +216,10 @@ class DecodeEngine:
             self._alloc(batch)
         self.h_sym[:batch].numpy()[...] = symbols
         mono = mode_id(mode) == schedule.MODE_MONO
+        if self.n_logical > 12 and not (mono and program_is_monomial_candidate(program) and not kept_mask):
+            raise NotImplementedError(
+                "more than 12 logical sites: the Dephasing-DMRG read-out runs on the monomial engine only "
+                "(bit-flip bias, no erased logical-index qubits)")
         if mono and (kept_mask or not program_is_monomial_candidate(program)):
             mono, mode = False, MONO_FALLBACK_MODE   # erased logical-index qubits / two-site gates: dense engine
         desc = self._desc(program, cut, bias_p, renormalise, mode, rank_tol=rank_tol, kept_mask=kept_mask,
@@ -236,6 +246,8 @@ class DecodeEngine:
         if mono:
             redo = np.nonzero(status == _abi.ST_NOT_MONOMIAL)[0]
             self.last_mono_fallbacks = int(redo.size)
+            if redo.size and self.n_logical > 12:
+                raise NotImplementedError("a syndrome left the monomial structure and has more than 12 logical sites")
             if redo.size:
                 d2, s2, st2 = self.decode_host(program, np.ascontiguousarray(symbols[redo]), cut=cut, bias_p=bias_p,
                                                renormalise=renormalise, mode=MONO_FALLBACK_MODE, rank_tol=rank_tol,
@@ -257,7 +269,7 @@ def get_engine(n_sites: int, n_logical: int, chi_max: int) -> DecodeEngine:
     """Cached engine, keyed on the COMPILED capacities (a sweep over chi_max = 20, 30, 40, 64 shares one engine and one
     workspace; ``chi_max`` itself travels in the descriptor of every call)."""
     lib, torch = _lib.require_gpu()
-    cap = _abi.chi_capacity(max(int(chi_max), _abi.readout_min_capacity(n_logical)))
+    cap = 0 if n_logical > 12 else _abi.chi_capacity(max(int(chi_max), _abi.readout_min_capacity(n_logical)))
     key = (torch.cuda.current_device(), n_sites, n_logical, cap, _abi.mono_chi_capacity(int(chi_max)))
     if key not in _ENGINES:
         _ENGINES[key] = DecodeEngine(n_sites, n_logical, int(chi_max), max_batch=4096)

@@ -16,7 +16,7 @@ import numpy as np
 from mdopt_b200.optimiser.utils import (COPY_LEFT, SWAP, XOR_BULK, XOR_LEFT, XOR_RIGHT, ConstraintString,
                                         front_minimising_order, msro)
 
-OP_END, OP_SWEEP, OP_MOVE, OP_MARGINAL, OP_GATE2, OP_COMPRESS = 0, 1, 2, 3, 4, 5
+OP_END, OP_SWEEP, OP_MOVE, OP_MARGINAL, OP_GATE2, OP_COMPRESS, OP_MARGINAL_DMRG = 0, 1, 2, 3, 4, 5, 6
 MODE_FAST, MODE_SVD, MODE_SVD_GRAM, MODE_MONO = 0, 1, 2, 3
 SYM_ZERO, SYM_ONE, SYM_PLUS = 0, 1, 2
 
@@ -214,7 +214,7 @@ def depolarising_bias(prob_bias: float) -> np.ndarray:
 
 def build_decode_program(code, has_x: bool, has_z: bool, renormalise: bool = True, strategy: str = "Naive",
                          orders: Optional[dict] = None, bias_type: str = "Bitflip",
-                         bias_prob: float = 0.1) -> Program:
+                         bias_prob: float = 0.1, num_runs: int = 1) -> Program:
     """Program for ``decode_css`` on errors with the given literal-character flags (decoding.py:1230-1339).
 
     ``bias_type="Bitflip"`` is applied by the kernel while it builds the product state; any other value takes
@@ -243,7 +243,10 @@ def build_decode_program(code, has_x: bool, has_z: bool, renormalise: bool = Tru
     for strings, tensors, key in plan:
         ordered = order_strings(strings, n_sites, strategy, orders.get(key))
         append_strings(ops, table, ordered, tensors, n_sites, renormalise, spans)
-    ops.extend([OP_MARGINAL, OP_END])
+    if k > 12:   # decoding.py:1382-1400: the Dephasing-DMRG read-out, `num_runs` sweeps
+        ops.extend([OP_MARGINAL_DMRG, max(int(num_runs), 1), OP_END])
+    else:
+        ops.extend([OP_MARGINAL, OP_END])
     if not table.data:
         table.add(SWAP)  # keep the table non-empty for programs without constraints
     wtab, wdim = table.arrays()

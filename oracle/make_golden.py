@@ -132,6 +132,64 @@ def main():
         run_custom("five_qubit_depol", five_qubit_errors(), chi_max=int(1e4), cut=1e-17, bias_type="Depolarising",
                    bias_prob=0.1, contraction_strategy="Naive")
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "dmrg":
+        # Dephasing DMRG from |+...+> on seeded positive targets with a unique main component
+        # (the reference's own test problem, tests/optimiser/test_dephasing_dmrg.py:199-300): target tensors in, the
+        # bitstring engine.mps ends on out, after one and after two sweeps
+        from mdopt.mps.utils import create_simple_product_state
+        from mdopt.optimiser.dephasing_dmrg import DephasingDMRG
+
+        rng = np.random.default_rng(31)
+        cases = []
+        for n, chi in [(8, 4), (13, 6), (16, 8), (14, 3), (20, 5)]:
+            dims = [min(chi, 2 ** i, 2 ** (n - i)) for i in range(n + 1)]
+            tensors = [rng.uniform(0.05, 1.0, size=(dims[i], 2, dims[i + 1])) for i in range(n)]
+            target = CanonicalMPS([t.copy() for t in tensors], n - 1, 1e-12, int(1e4))
+            out = {}
+            for runs in (1, 2):
+                eng = DephasingDMRG(mps=create_simple_product_state(n, which="+"), mps_target=target.copy(),
+                                    chi_max=int(1e4), cut=1e-17, mode="LA", silent=True)
+                eng.run(num_iter=runs)
+                assert eng.mps.bond_dimensions == [1] * (n - 1)
+                out[runs] = [int(np.argmax(np.abs(t.reshape(-1)))) for t in eng.mps.tensors]
+            cases.append({"tensors": [t.tolist() for t in tensors], "bits_1": out[1], "bits_2": out[2]})
+            print("dmrg", n, chi, out[1], out[2])
+        # decode_css with more than 12 logical sites (decoding.py:1382-1400): 7 Steane blocks = 14 logical sites,
+        # errors with X and Z letters so that every logical site is constrained (unique main component); the SVDs
+        # run with the canonical tie-break installed (chi_max = 64 truncates)
+        import structured_svd as S
+
+        rows = [[3, 4, 5, 6], [1, 2, 5, 6], [0, 2, 4, 6]]
+        xs, zs, xl, zl = [], [], [], []
+        for b in range(7):
+            o = 7 * b
+            for r in rows:
+                xs.append([o + c for c in r])
+                zs.append([o + c for c in r])
+            xl.append([o, o + 1, o + 2])
+            zl.append([o, o + 1, o + 2])
+        code = qec.CssCode(49, xs, zs, xl, zl)
+
+        def err(**kw):
+            e = ["I"] * 49
+            for q, p in kw.items():
+                e[int(q[1:])] = p
+            return "".join(e)
+
+        errors = [err(q0="X", q8="Z"), err(q3="X", q4="X", q20="Z"), err(q10="Y", q30="X", q44="Z"),
+                  err(q0="X", q1="X", q2="X", q47="Z"), err(q5="Z", q6="Z", q12="X", q13="X", q40="X")]
+        kw = dict(chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, tolerance=1e-12)
+        decodes = []
+        for e in errors:
+            with S.installed():
+                eng, ov = decode_css(code, e, silent=True, contraction_strategy="Naive", **kw)
+            bits = [int(np.argmax(np.abs(t.reshape(-1)))) for t in eng.mps.tensors]
+            decodes.append({"error": e, "bits": bits, "overlap": float(ov)})
+            print("decode", e[:20], bits, ov)
+        with open(os.path.join(OUT, "dephasing_dmrg.json"), "w") as fh:
+            json.dump({"cases": cases, "steane7": {"x_stabs": xs, "z_stabs": zs, "x_logicals": xl, "z_logicals": zl,
+                                                   "kwargs": kw, "decodes": decodes}}, fh)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "stabiliser":
         # multiply_by_stabiliser=True (decoding.py:1237-1240): the draw comes from numpy's global RNG, so seed it,
         # record which stabiliser np.random.choice returns and replay the same seed for the decode

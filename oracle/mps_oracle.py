@@ -525,8 +525,10 @@ def multiply_pauli_strings(p1, p2):
 
 def decode_css(code, error, chi_max=int(1e4), cut=1e-17, bias_type="Depolarising", bias_prob=0.1,
                renormalise=True, contraction_strategy="Naive", tolerance=1e-12, orders=None, record=None,
-               stabiliser=None):
-    """Reference: decoding.py:1164-1404, dense read-out branch (<= 12 logical sites) only.
+               stabiliser=None, num_runs=1):
+    """Reference: decoding.py:1164-1404.  Up to 12 logical sites: (|marginal|, success).  Above: the Dephasing-DMRG
+    read-out, returned as (bitstring in the order of the reversed logical chain the engine works on, overlap with
+    |0...0>) -- the reference returns (engine, overlap), the bitstring is what engine.mps holds.
 
     ``orders`` optionally maps 'xl','zl','xc','zc' to explicit MPO orders (used with "Optimised").
     ``stabiliser``: the Pauli string ``multiply_by_stabiliser=True`` would have drawn (decoding.py:1237-1240;
@@ -567,9 +569,66 @@ def decode_css(code, error, chi_max=int(1e4), cut=1e-17, bias_type="Depolarising
         mps = marginal(mps, erased, renormalise=renormalise)
     # decoding.py:1351-1356 (there `error` is already the 2n-character site string)
     mps = marginal(mps, list(range(k, len(bits) + k - len(erased))), renormalise=renormalise).reverse()
-    if len(mps) > 12:
-        raise NotImplementedError("Dephasing-DMRG read-out (> 12 logical sites) is out of scope")
+    if len(mps) > 12:   # decoding.py:1382-1400: the Dephasing-DMRG read-out returns (engine, overlap)
+        found = dephasing_dmrg(mps.tensors, num_iter=num_runs)
+        return found, float(all(b == 0 for b in found))
     return readout(mps.dense(flatten=True, renormalise=renormalise, norm=2))
+
+
+# --------------------------------------------------------------------------------------------------
+# Dephasing DMRG started from |+...+> (mdopt/optimiser/dephasing_dmrg.py:147-374 as decode_css uses it,
+# decoding.py:1382-1400).
+# --------------------------------------------------------------------------------------------------
+
+
+def dephasing_dmrg(target, num_iter=1):
+    """Main-component search: returns the bitstring (one bit per site of `target`) the reference's engine ends on.
+
+    What the reference does, restated.  The search MPS starts as |+...+> and every bond update snaps the two-site
+    tensor to ONE computational-basis configuration (``_snap_to_computational_basis``, :236-249), so it always has
+    bond dimension 1 and each site is '+', 0 or 1.  With such a search state the environments (:324-374) are outer
+    products of a vector with itself, the effective two-site operator (``EffectiveDensityOperator._EINSUM``, :47) is
+    DIAGONAL in the computational basis -- the copy tensors tie the operator's physical legs to the target's -- and
+    its entry for the configuration (a, b) of sites (i, i+1) is |l_i . T_i[a] . T_{i+1}[b] . r_{i+2}|^2, where l / r
+    contract the target with the current search state to the left / right ('+' sites sum over both bit values).
+    ``eigsh(k=1, which="LA")`` (:279) therefore returns the basis vector of the largest entry and the snap keeps it.
+    One sweep updates the bonds left to right, then right to left (:251-256).
+
+    Tie-break: when the largest entry is degenerate the reference's answer depends on ARPACK's restart vectors and is
+    not reproducible; here the first maximal (a, b) in row-major order wins (the rule the snap's ``np.argmax``
+    itself uses), with weights within 1e-9 relative of the largest counted as tied.  Parity with the reference is pinned on non-degenerate targets (tests/golden/dephasing_dmrg.json)."""
+    t = [np.asarray(x) for x in target]
+    n = len(t)
+    state = [None] * n   # None = '+', else the bit
+
+    def site_vec(k):
+        return np.ones(2) / np.sqrt(2.0) if state[k] is None else np.eye(2)[state[k]]
+
+    def left_env(i):
+        v = np.ones(1)
+        for k in range(i):
+            v = np.einsum("a,apb,p->b", v, t[k], site_vec(k))
+        return v
+
+    def right_env(j):
+        v = np.ones(1)
+        for k in range(n - 1, j, -1):
+            v = np.einsum("apb,p,b->a", t[k], site_vec(k), v)
+        return v
+
+    def update(i):
+        l, r = left_env(i), right_env(i + 1)
+        amp = np.einsum("a,apb,bqc,c->pq", l, t[i], t[i + 1], r)
+        w = np.abs(amp.reshape(-1)) ** 2
+        a, b = divmod(int(np.nonzero(w >= w.max() * (1.0 - 1e-9))[0][0]), 2)   # first maximal index, ties to 1e-9
+        state[i], state[i + 1] = a, b
+
+    for _ in range(num_iter):
+        for i in range(n - 1):
+            update(i)
+        for i in reversed(range(n - 1)):
+            update(i)
+    return [int(b) for b in state]
 
 
 def custom_sites(stabilizers, x_logicals, z_logicals):

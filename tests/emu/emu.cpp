@@ -67,22 +67,23 @@ int mono_impl(const mdopt_decode_desc* d, const int32_t* program, const double* 
   std::vector<MonoSite<CHI>> sites(d->n_sites);
   std::vector<int> bd(d->n_sites + 1);
   std::vector<MonoTensor> tabs(n_tensors + 1);
+  std::vector<double> env((size_t)(d->n_logical + 2) * CHI);
   mono_build_identity(&tabs[0]);
   for (int t = 0; t < n_tensors; ++t) mono_build_tensor(wtab + (size_t)t * 16, wdim + (size_t)t * 4, &tabs[1 + t]);
   MonoState<CHI>& st = sm->state;
-  st.sites = sites.data(); st.bd = bd.data(); st.tabs = tabs.data();
+  st.sites = sites.data(); st.bd = bd.data(); st.tabs = tabs.data(); st.env = env.data();
   DecodeParams P;
   P.n_sites = d->n_sites; P.n_logical = d->n_logical; P.chi_max = d->chi_max; P.mode = d->mode;
   P.renormalise = d->renormalise; P.trace_stride = d->trace_stride; P.trace_max = d->trace_max;
   P.n_ops = d->n_ops; P.cut_sweep = d->cut_sweep; P.cut_move = d->cut_move; P.rank_tol = d->rank_tol;
   P.bias_p = d->bias_p;
   P.n_head = d->n_head > 0 ? d->n_head : d->n_logical;
-  P.kept_mask = d->kept_mask ? d->kept_mask : ((1u << d->n_logical) - 1u);
+  P.kept_mask = d->kept_mask ? d->kept_mask : (d->n_logical >= 32 ? 0xffffffffu : ((1u << d->n_logical) - 1u));
   P.readout_rel = d->readout_rel; P.readout_abs = d->readout_abs;
   P.n_tensors = n_tensors;
   st.P = P;
   st.cnt = MonoCounters{};
-  const int ncls = 1 << d->n_logical;
+  const int ncls = d->n_logical > 12 ? d->n_logical : (1 << d->n_logical);
   for (int b = 0; b < batch; ++b) {
     st.trace = (trace && d->trace_stride > 0) ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
     Mono<CHI>::run(*sm, program, symbols + (size_t)b * d->n_sites, dist + (size_t)b * ncls, success + b);

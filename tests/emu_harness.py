@@ -49,7 +49,7 @@ def decode(program: schedule.Program, symbols, chi_max, cut, bias_p, renormalise
         cap = (_abi.mono_chi_capacity(max(chi_max, 1)) if mono else
                _abi.chi_capacity(max(chi_max, 1, _abi.readout_min_capacity(program.n_logical))))
     B = symbols.shape[0]
-    ncls = 1 << program.n_logical
+    ncls = program.n_logical if (mono and program.n_logical > 12) else 1 << program.n_logical
     stride = (4 + 2 * cap) if trace_max else 0
     desc = _abi.make_desc(program.n_sites, program.n_logical, chi_max, mode, renormalise, program.ops.size, cut,
                           bias_p, stride, trace_max, rank_tol=rank_tol, kept_mask=kept_mask,

@@ -276,3 +276,57 @@ def test_structured_svd_hook_unit():
     dense = rng.standard_normal((6, 9))
     u2, s2, v2 = S.structured_svd(dense)
     np.testing.assert_allclose(s2, np.linalg.svd(dense, compute_uv=False), rtol=1e-13)
+
+
+# ---- more than 12 logical sites: the Dephasing-DMRG read-out (decoding.py:1382-1400) -------------------------------
+
+
+def test_dephasing_dmrg_restatement_equals_the_reference():
+    """The numpy restatement (oracle) against the unmodified reference's DephasingDMRG on seeded positive targets with
+    a unique main component (the reference's own test problem, tests/optimiser/test_dephasing_dmrg.py:199-300)."""
+    g = load_golden("dephasing_dmrg")
+    for c in g["cases"]:
+        t = [np.array(x) for x in c["tensors"]]
+        assert O.dephasing_dmrg(t, 1) == c["bits_1"]
+        assert O.dephasing_dmrg(t, 2) == c["bits_2"]
+
+
+def _steane7():
+    from mdopt_b200.codes import CssCode
+
+    s7 = load_golden("dephasing_dmrg")["steane7"]
+    args = (49, s7["x_stabs"], s7["z_stabs"], s7["x_logicals"], s7["z_logicals"])
+    return s7, CssCode(*args), O.CssCode(*args)
+
+
+def test_decode_with_14_logical_sites_equals_the_reference():
+    """decode_css on 7 Steane blocks (14 logical sites) by the unmodified reference (canonical SVD tie-break installed):
+    the in-kernel read-out ends on the same bitstring, overlap included; so does the oracle port."""
+    s7, code, ocode = _steane7()
+    kw = s7["kwargs"]
+    for row in s7["decodes"]:
+        e = row["error"]
+        prog = schedule.build_decode_program(code, "X" in e, "Z" in e, True, "Naive", None, "Bitflip", kw["bias_prob"], 1)
+        assert prog.ops[-3] == schedule.OP_MARGINAL_DMRG
+        sym = schedule.symbols_from_errors([e], prog.n_logical)
+        d, s, st, _, _ = H.decode(prog, sym, kw["chi_max"], kw["cut"], kw["bias_prob"], True, MONO, mono=True)
+        assert st[0] == 0 and d.shape == (1, 14)
+        assert d[0].astype(int).tolist() == row["bits"] and float(s[0]) == row["overlap"], e
+    e = s7["decodes"][2]["error"]
+    with S.installed():
+        bits, ov = O.decode_css(ocode, e, contraction_strategy="Naive", **kw)
+    assert bits == s7["decodes"][2]["bits"] and ov == s7["decodes"][2]["overlap"]
+
+
+def test_dmrg_sweeps_parameter_and_x_only_errors():
+    """num_runs sweeps; an X-only error leaves the Z-logical sites unconstrained: their weights tie exactly and the
+    first maximal configuration (bit 0) is kept -- the rule of the snap's argmax (dephasing_dmrg.py:245)."""
+    s7, code, ocode = _steane7()
+    e = "X" + "I" * 48
+    for runs in (1, 2):
+        prog = schedule.build_decode_program(code, True, False, True, "Naive", None, "Bitflip", 0.1, runs)
+        sym = schedule.symbols_from_errors([e], prog.n_logical)
+        d, s, st, _, _ = H.decode(prog, sym, 64, 1e-17, 0.1, True, MONO, mono=True)
+        bits, ov = O.decode_css(ocode, e, chi_max=64, cut=1e-17, bias_type="Bitflip", bias_prob=0.1,
+                                contraction_strategy="Naive", num_runs=runs)
+        assert st[0] == 0 and d[0].astype(int).tolist() == bits and float(s[0]) == ov == 1.0

@@ -185,3 +185,45 @@ def test_full_bench_batch_properties(api):
     np.testing.assert_array_equal(dist[:512], dist[8192:])
     np.testing.assert_array_equal(succ[:512], succ[8192:])
     assert api["engine"].get_engine(84, 2, 64).last_mono_fallbacks == 0
+
+
+def test_dephasing_dmrg_readout_for_14_logical_sites(api):
+    """decode_css with more than 12 logical sites (decoding.py:1382-1400) against the unmodified reference's
+    (bits of engine.mps, overlap) on 7 Steane blocks; the return convention mirrors (engine, overlap)."""
+    s7 = load_golden("dephasing_dmrg")["steane7"]
+    code = api["CssCode"](49, s7["x_stabs"], s7["z_stabs"], s7["x_logicals"], s7["z_logicals"])
+    kw = dict(s7["kwargs"])
+    errors = [r["error"] for r in s7["decodes"]] + ["I" * 49]
+    bits, overlap, status = api["decode_css_batch"](code, errors, contraction_strategy="Naive", return_status=True, **kw)
+    assert bits.shape == (len(errors), 14) and (status == 0).all()
+    for b, r in enumerate(s7["decodes"]):
+        assert bits[b].astype(int).tolist() == r["bits"] and float(overlap[b]) == r["overlap"], r["error"]
+    assert not bits[-1].any() and overlap[-1] == 1
+    eng, ov = api["decode_css"](code, errors[1], contraction_strategy="Naive", silent=True, **kw)
+    assert eng.bits == s7["decodes"][1]["bits"] and ov == s7["decodes"][1]["overlap"]
+    assert eng.mps.bond_dimensions == [1] * 13
+    with pytest.raises(NotImplementedError):
+        api["decode_css_batch"](code, errors[:1], chi_max=64, bias_type="Depolarising")
+
+
+def test_hypergraph_product_ldpc_code_chi512(api):
+    """BASELINE.json configs[3]-shaped work: HGP of a (3,4)-regular LDPC code (n = 400 qubits, 32 logical sites, 832 MPS
+    sites), bit-flip errors, chi_max = 512, Dephasing-DMRG read-out -- against the host build of the same engine."""
+    import emu_harness as H
+    from mdopt_b200.codes import hypergraph_product, random_regular_code
+
+    classical = random_regular_code(16, 12, 3, 4, 7)
+    code = hypergraph_product(classical, classical)
+    k = code.num_x_logicals() + code.num_z_logicals()
+    assert len(code) == 400 and k == 32
+    rng = np.random.default_rng(5)
+    errors = ["".join("X" if rng.random() < 0.01 else "I" for _ in range(400)) for _ in range(6)]
+    errors = [e for e in errors if "X" in e][:3]
+    kw = dict(chi_max=512, cut=1e-17, bias_type="Bitflip", bias_prob=0.1, contraction_strategy="Optimised")
+    bits, overlap, status = api["decode_css_batch"](code, errors, return_status=True, **kw)
+    assert (status == 0).all() and bits.shape == (len(errors), 32)
+    prog = api["schedule"].build_decode_program(code, True, False, True, "Optimised", None, "Bitflip", 0.1, 1)
+    for b, e in enumerate(errors):
+        sym = api["schedule"].symbols_from_errors([e], k)
+        d, s, st, _, _ = H.decode(prog, sym, 512, 1e-17, 0.1, True, api["schedule"].MODE_MONO, mono=True)
+        assert st[0] == 0 and d[0].astype(int).tolist() == bits[b].astype(int).tolist() and int(s[0]) == int(overlap[b])
