@@ -190,6 +190,33 @@ def main():
             json.dump({"cases": cases, "steane7": {"x_stabs": xs, "z_stabs": zs, "x_logicals": xl, "z_logicals": zl,
                                                    "kwargs": kw, "decodes": decodes}}, fh)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "randcirc":
+        # examples/random_circuit/mps-rand-circ.py:48-83 on a seeded 8-qubit circuit: fidelity tail per layer
+        from scipy.stats import unitary_group
+
+        from mdopt.contractor.contractor import mps_mpo_contract
+        from mdopt.mps.utils import create_simple_product_state
+
+        nq, chi, nl, seed = 8, 6, 6, 11
+        rng = np.random.default_rng(seed)
+        st = create_simple_product_state(num_sites=nq, phys_dim=2, which="0", form="Right-canonical", tolerance=np.inf)
+        tails = []
+        for k in range(nl):
+            layer = unitary_group.rvs(4, size=nq // 2 - k % 2, random_state=rng)
+            mpo = []
+            for gate in layer:   # random_circuit.py:9-71
+                q, r = np.linalg.qr(gate)
+                mpo += [q.reshape((1, q.shape[1], 2, 2)), r.reshape((r.shape[0], 1, 2, 2))]
+            st = mps_mpo_contract(mps=st, mpo=mpo, start_site=k % 2, renormalise=True, chi_max=1e4, cut=1e-12,
+                                  inplace=False)
+            st, errs = st.compress(chi_max=chi, cut=1e-12, renormalise=True, strategy="svd",
+                                   return_truncation_errors=True)
+            tails.append(float(np.prod([1 - e for e in errs])))
+        with open(os.path.join(OUT, "random_circuit.json"), "w") as fh:
+            json.dump({"num_qubits": nq, "bond_dim": chi, "num_layers": nl, "seed": seed, "fidelity_tail": tails,
+                       "bond_dimensions": [int(b) for b in st.bond_dimensions]}, fh)
+        print("random_circuit", tails)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "stabiliser":
         # multiply_by_stabiliser=True (decoding.py:1237-1240): the draw comes from numpy's global RNG, so seed it,
         # record which stabiliser np.random.choice returns and replay the same seed for the decode

@@ -134,3 +134,15 @@ def test_random_circuit_layer_and_compress_complex():
     np.testing.assert_allclose(np.abs(a), np.abs(b), atol=1e-12)
     comp, errs = out.compress(chi_max=2, cut=1e-12, renormalise=True, return_truncation_errors=True)
     assert max(comp.bond_dimensions) <= 2 and len(errs) == n - 1
+
+
+def test_random_circuit_driver_matches_the_reference_fixture(golden):
+    """examples/random_circuit/mps-rand-circ.py on a seeded 8-qubit circuit: the fidelity tail per layer (contract with
+    renormalise=True, then compress from the nearer border) equals the unmodified reference's."""
+    from mdopt_b200.drivers import random_circuit as rc
+
+    g = golden("random_circuit")
+    state, tails, _ = rc.run(g["num_qubits"], g["bond_dim"], g["num_layers"], g["seed"])
+    np.testing.assert_allclose(tails, g["fidelity_tail"], rtol=1e-10)
+    assert [int(b) for b in state.bond_dimensions] == g["bond_dimensions"]
+    assert state.tensors[0].dtype == np.complex128
