@@ -5,6 +5,7 @@
 
 #include "../../include/mdopt_b200.h"
 #include "mps_core.cuh"
+#include "site_apply_mma.cuh"
 
 namespace mdopt {
 namespace {
@@ -290,6 +291,19 @@ int launch_site_apply(int sms, int batch, int rows, int vl, int vr, int mr, int 
   if constexpr (C_ > SMEM_CHI_MAX) {
     return MDOPT_E_CAPACITY;
   } else {
+    // TMA-staged FP64-MMA kernel for tile-aligned shapes (every full-chi step); the scalar kernel otherwise
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(m_in) | reinterpret_cast<uintptr_t>(a_site) |
+                             reinterpret_cast<uintptr_t>(theta)) & 15u) == 0;
+    if (C_ >= 16 && aligned16 && site_apply_mma_ok(rows, vl, vr, mr, bn)) {
+      const size_t smem = sizeof(SiteApplyMmaSmem<C_>);
+      cudaError_t e = cudaFuncSetAttribute((const void*)site_apply_mma_kernel<C_>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      const int threads = (rows / 16) * (bn / 32) * 2 * vr >= 16 ? 512 : 256;
+      int grid = batch < sms ? batch : sms;
+      site_apply_mma_kernel<C_><<<grid, threads, smem, st>>>(batch, rows, vl, vr, mr, bn, m_in, a_site, w, theta);
+      return (int)cudaGetLastError();
+    }
     cudaError_t e = set_smem_attr<C_>((const void*)site_apply_kernel<C_>);
     if (e != cudaSuccess) return (int)e;
     int per = 1;

@@ -63,10 +63,13 @@ def main():
                                                                    vp(w), vp(theta), C.c_void_p(0)), "site_apply"))
     nbytes = 8.0 * batch * (rows * vl * mr + mr * 2 * bn + rows * 2 * vr * bn)
     flops = 2.0 * batch * rows * bn * mr * 4  # XOR_BULK has 4 non-zeros
-    out.append({"kernel": "K1 site_apply_kernel<64> (theta-build)", "batch": batch, "ms": t * 1e3,
-                "roofline": {"bound": "hbm", "achieved": nbytes / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": nbytes / t / 1e9 / hbm_peak}, "gflops": flops / t / 1e9,
-                "bytes_per_item": nbytes / batch})
+    # 16 FLOP/B is above the FP64 machine balance (35.5 TFLOP/s / 6.55 TB/s = 5.4 FLOP/B): FP64-bound
+    out.append({"kernel": "K1 site_apply_mma_kernel<64> (theta-build, TMA-staged operands, FP64 mma tiles)",
+                "batch": batch, "ms": t * 1e3,
+                "roofline": {"bound": "tensor", "achieved": flops / t / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": flops / t / 1e12 / fp64_peak},
+                "hbm": {"achieved_gbs": nbytes / t / 1e9, "peak_gbs": hbm_peak, "frac": nbytes / t / 1e9 / hbm_peak},
+                "bytes_per_item": nbytes / batch, "flops_per_item": flops / batch})
     del m_in, a_site, theta
 
     # K2: truncated SVD, the reference's move shape 128x128 and chi_max=64 (46.1 MFLOP in LAPACK's count)

@@ -97,6 +97,35 @@ def test_site_apply_kernel_matches_einsum(torch_mod):
         np.testing.assert_allclose(d_out.cpu().numpy(), ref, rtol=1e-13, atol=1e-13)
 
 
+def test_site_apply_tma_dmma_kernel_matches_einsum(torch_mod):
+    """Tile-aligned shapes take the TMA-staged FP64-MMA kernel (site_apply_mma.cuh); same contraction, same answer."""
+    import ctypes as C
+
+    from mdopt_b200 import _lib
+
+    torch = torch_mod
+    lib = _lib.load()
+    rng = np.random.default_rng(8)
+    for cap, rows, mr, bn in [(64, 128, 64, 64), (64, 64, 32, 32), (32, 32, 16, 32), (64, 16, 4, 64)]:
+        for w in (O.XOR_BULK, O.SWAP, O.XOR_RIGHT, O.IDENTITY, O.XOR_LEFT):
+            vl, vr = w.shape[0], w.shape[1]
+            if rows > 2 * cap or vl * mr > 2 * cap:
+                continue
+            batch = 300 if rows == 128 else 41
+            m_in = rng.standard_normal((batch, rows, vl, mr))
+            a = rng.standard_normal((batch, mr, 2, bn))
+            ref = np.einsum("brqm,bmpn,qwpd->brdwn", m_in, a, w)
+            d_m, d_a = torch.from_numpy(m_in).cuda(), torch.from_numpy(a).cuda()
+            d_w = torch.from_numpy(np.ascontiguousarray(w)).cuda()
+            d_out = torch.full((batch, rows, 2, vr, bn), float("nan"), dtype=torch.float64, device="cuda")
+            rc = lib.mdopt_site_apply_batch_device(cap, batch, rows, vl, vr, mr, bn, C.c_void_p(d_m.data_ptr()),
+                                                   C.c_void_p(d_a.data_ptr()), C.c_void_p(d_w.data_ptr()),
+                                                   C.c_void_p(d_out.data_ptr()), C.c_void_p(0))
+            assert rc == 0
+            torch.cuda.synchronize()
+            np.testing.assert_allclose(d_out.cpu().numpy(), ref, rtol=1e-12, atol=1e-12)
+
+
 def test_readout_kernel(torch_mod):
     import ctypes as C
 
