@@ -66,6 +66,55 @@ def svd_device(mat, cut: float = 1e-12, chi_max: int = int(1e4), renormalise: bo
     return u, s, vh, err
 
 
+def qr_pivoted_device(a):
+    """Householder QR with column pivoting on the device (what ``scipy.linalg.qr(pivoting=True, mode="economic")``
+    gives the reference at utils.py:188-190: at every step the remaining column of largest norm is eliminated next).
+    Returns (Q (m, k), R (k, n) in pivoted column order, pivots) with k = min(m, n)."""
+    torch = _torch()
+    m, n = a.shape
+    k = min(m, n)
+    r = a.clone()
+    q = torch.eye(m, dtype=a.dtype, device=a.device)
+    piv = torch.arange(n, device=a.device)
+    for j in range(k):
+        norms = (r[j:, j:].abs() ** 2).sum(dim=0)
+        p = j + int(torch.argmax(norms).item())
+        if p != j:
+            r[:, [j, p]] = r[:, [p, j]]
+            piv[[j, p]] = piv[[p, j]]
+        x = r[j:, j]
+        normx = torch.linalg.norm(x)
+        if float(normx.item()) == 0.0:
+            break
+        alpha = x[0]
+        phase = alpha / alpha.abs() if float(alpha.abs().item()) > 0 else torch.ones((), dtype=a.dtype, device=a.device)
+        v = x.clone()
+        v[0] = v[0] + phase * normx          # beta = -phase * |x| (LAPACK's sign choice: no cancellation)
+        v = v / torch.linalg.norm(v)
+        r[j:, j:] = r[j:, j:] - 2.0 * torch.outer(v, v.conj() @ r[j:, j:])
+        q[:, j:] = q[:, j:] - 2.0 * torch.outer(q[:, j:] @ v, v.conj())
+    return q[:, :k], torch.triu(r[:k, :]), piv
+
+
+def qr_device(mat, cut: float = 1e-12, chi_max: int = int(1e4), renormalise: bool = False,
+              return_truncation_error: bool = False):
+    """``mdopt.utils.utils.qr`` (utils.py:141-212): pivoted QR truncated to ``min(chi_max, #(|diag R| > cut))`` rows,
+    pivoting undone on R, optional renormalisation by the norm of the kept diagonal, truncation error ||A - QR||."""
+    torch = _torch()
+    q, r, piv = qr_pivoted_device(mat)
+    diag = torch.diagonal(r).abs()
+    rank = min(int(chi_max), int((diag > cut).sum().item()))
+    inv = torch.argsort(piv)
+    r = r[:rank, :][:, inv]
+    q = q[:, :rank]
+    if renormalise and rank > 0:
+        nrm = float(torch.linalg.norm(torch.diagonal(r[:rank, :rank])).item())
+        if nrm > 0:
+            r = r / nrm
+    err = float(torch.linalg.norm(mat - q @ r).item()) if return_truncation_error else None
+    return q, r, err
+
+
 def split_device(theta, chi_max=int(1e4), cut=1e-12, renormalise=False):
     i, j, k, l = theta.shape
     u, s, vh, err = svd_device(theta.reshape(i * j, k * l), cut=cut, chi_max=chi_max, renormalise=renormalise)
@@ -162,14 +211,39 @@ def marginal_generic(tensors: Sequence[np.ndarray], sites: Sequence[int], renorm
     return [x.cpu().numpy() for x in t]
 
 
-def compress_bond_generic(tensors, centre, bond, chi_max, cut, renormalise, mps_chi_max):
-    """canonical.py:684-784 ("svd"): centre to `bond`, split the two-site tensor with the user's chi_max / cut, leave
-    U.S on `bond`.  Returns (host tensors, centre, truncation error)."""
+def compress_bond_generic(tensors, centre, bond, chi_max, cut, renormalise, mps_chi_max, strategy="svd",
+                          want_error=True):
+    """canonical.py:684-835: centre to `bond`, then
+    "svd": split the two-site tensor with the user's chi_max / cut, leave U.S on `bond` (:741-760);
+    "qr": pivoted-QR split, Q on `bond`, R on `bond + 1` (:762-775);
+    "svd_advanced": SVD of each tensor, SVD of the small core, sqrt(s) on both sides (:777-833).
+    Returns (host tensors, centre, truncation error)."""
     torch = _torch()
     dt = _dtype_for(tensors)
     ts, _ = move_centre_device([_dev(t, dt) for t in tensors], centre, bond, mps_chi_max)
-    theta = torch.tensordot(ts[bond], ts[bond + 1], dims=([2], [0]))
-    u, s, v, err = split_device(theta, chi_max=chi_max, cut=cut, renormalise=renormalise)
-    ts[bond] = u * s.to(u.dtype)[None, None, :]
-    ts[bond + 1] = v
+    left, right = ts[bond], ts[bond + 1]
+    if strategy == "svd":
+        theta = torch.tensordot(left, right, dims=([2], [0]))
+        u, s, v, err = split_device(theta, chi_max=chi_max, cut=cut, renormalise=renormalise)
+        ts[bond] = u * s.to(u.dtype)[None, None, :]
+        ts[bond + 1] = v
+    elif strategy == "qr":
+        theta = torch.tensordot(left, right, dims=([2], [0]))
+        i, j, k, l = theta.shape
+        q, r, err = qr_device(theta.reshape(i * j, k * l), cut=cut, chi_max=chi_max, renormalise=renormalise,
+                              return_truncation_error=want_error)
+        ts[bond] = q.reshape(i, j, q.shape[1])
+        ts[bond + 1] = r.reshape(r.shape[0], k, l)
+    elif strategy == "svd_advanced":
+        cl, pl, _ = left.shape
+        _, pr, cr = right.shape
+        u0, sl, u1, _ = svd_device(left.reshape(cl * pl, -1), cut=cut, chi_max=chi_max, renormalise=renormalise)
+        v0, sr, v1, _ = svd_device(right.reshape(-1, pr * cr), cut=cut, chi_max=chi_max, renormalise=renormalise)
+        core = (u1 * sl.to(u1.dtype)[:, None]) @ (v0 * sr.to(v0.dtype)[None, :])
+        un, sn, vn, err = svd_device(core, cut=cut, chi_max=chi_max, renormalise=renormalise)
+        root = torch.sqrt(sn).to(un.dtype)
+        ts[bond] = (u0 @ (un * root[None, :])).reshape(cl, pl, sn.numel())
+        ts[bond + 1] = ((root[:, None] * vn) @ v1).reshape(sn.numel(), pr, cr)
+    else:
+        raise ValueError(f"Unsupported compression strategy: {strategy}")
     return [t.cpu().numpy() for t in ts], bond, err

@@ -168,14 +168,13 @@ class CanonicalMPS:
             raise ValueError(f"Bond given {bond}, with the number of bonds in the MPS {self.num_bonds}.")
         if strategy not in ["svd", "qr", "svd_advanced"]:
             raise ValueError(f"Unsupported compression strategy: {strategy}")
-        if strategy != "svd":
-            raise NotImplementedError("the GPU engine provides the 'svd' compression strategy")
         centre = self.orth_centre if self.orth_centre is not None else self.resolve_orth_centre()
         from mdopt_b200 import generic
 
-        if generic.needs_generic(self.tensors):   # complex / large bonds: library tier, same steps
+        if strategy != "svd" or generic.needs_generic(self.tensors):
+            # "qr" / "svd_advanced" (canonical.py:762-833), complex or large bonds: library tier, same steps
             tensors, c, err = generic.compress_bond_generic(self.tensors, centre, bond, chi_max, cut, renormalise,
-                                                            self.chi_max)
+                                                            self.chi_max, strategy, return_truncation_error)
             return (CanonicalMPS(tensors, c, self.tolerance, self.chi_max), (err if return_truncation_error else None))
         out, errors = self._run_compress([bond], chi_max, cut, renormalise, centre)
         return out, (errors[0] if return_truncation_error else None)
@@ -186,8 +185,6 @@ class CanonicalMPS:
         border; from the last site the chain is processed mirrored and the errors are reported in bond order."""
         if strategy not in ["svd", "qr", "svd_advanced"]:
             raise ValueError(f"Unsupported compression strategy: {strategy}")
-        if strategy != "svd":
-            raise NotImplementedError("the GPU engine provides the 'svd' compression strategy")
         centre = self.orth_centre if self.orth_centre is not None else self.resolve_orth_centre()
         from_last = centre != 0 and (centre == self.num_sites - 1 or centre > int(self.num_bonds / 2))
         work = self
@@ -197,11 +194,11 @@ class CanonicalMPS:
             centre = work.orth_centre
         from mdopt_b200 import generic
 
-        if generic.needs_generic(work.tensors):
+        if strategy != "svd" or generic.needs_generic(work.tensors):
             out, errors = work, []
             for bond in range(self.num_bonds):
                 out, err = out.compress_bond(bond, chi_max=chi_max, cut=cut, renormalise=renormalise,
-                                             return_truncation_error=True)
+                                             strategy=strategy, return_truncation_error=True)
                 errors.append(err)
         else:
             out, errors = work._run_compress(list(range(self.num_bonds)), chi_max, cut, renormalise, centre)

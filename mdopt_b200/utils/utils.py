@@ -72,18 +72,45 @@ def svd(mat: np.ndarray, cut: float = float(1e-12), chi_max: int = int(1e4), ren
     return out + ((float(trunc[0]),) if return_truncation_error else (None,))
 
 
+def qr(mat: np.ndarray, cut: float = float(1e-12), chi_max: int = int(1e4), renormalise: bool = False,
+       return_truncation_error: bool = False):
+    """Pivoted QR with truncation by |diag R| (reference utils.py:141-212), on the device through the library tier."""
+    mat = np.asarray(mat)
+    if len(mat.shape) != 2:
+        raise ValueError(f"Input matrix must have 2 dimensions, got {len(mat.shape)}.")
+    from mdopt_b200 import generic
+
+    torch = _lib.require_gpu()[1]
+    dmat = torch.as_tensor(np.ascontiguousarray(mat), device=generic._DEVICE)
+    q, r, err = generic.qr_device(dmat, cut=cut, chi_max=int(min(chi_max, 1 << 30)), renormalise=renormalise,
+                                  return_truncation_error=return_truncation_error)
+    return q.cpu().numpy(), r.cpu().numpy(), err
+
+
 def split_two_site_tensor(tensor: np.ndarray, chi_max: int = int(1e4), cut: float = float(1e-12),
                           renormalise: bool = False, strategy: str = "svd",
                           return_truncation_error: bool = False) -> Tuple:
-    """Split ``(i, j, k, l)`` into ``U(i,j,m), s(m), V(m,k,l)`` (reference utils.py:290-383, svd strategy)."""
+    """Split ``(i, j, k, l)`` into ``U(i,j,m), s(m), V(m,k,l)`` (``"svd"``) or ``Q(i,j,m), R(m,k,l)`` (``"qr"``)
+    (reference utils.py:290-383)."""
     tensor = np.asarray(tensor)
     if tensor.ndim != 4:
         raise ValueError(f"A valid two-site tensor must have 4 legs while the one given has {tensor.ndim}.")
     if strategy not in ["svd", "qr"]:
         raise ValueError("The strategy must be either `svd` or `qr`.")
-    if strategy == "qr":
-        raise NotImplementedError("only the `svd` strategy is on the decode path")
     i, j, k, l = tensor.shape
+    if strategy == "qr":   # pivoted QR (utils.py:141-212, :370-383) through the library tier on the device
+        from mdopt_b200 import generic
+
+        torch = _lib.require_gpu()[1]
+        dmat = torch.as_tensor(np.ascontiguousarray(tensor.reshape(i * j, k * l)), device=generic._DEVICE)
+        q, r, err = generic.qr_device(dmat, cut=cut, chi_max=int(min(chi_max, 1 << 30)), renormalise=renormalise,
+                                      return_truncation_error=return_truncation_error)
+        chi_cut = min(int(min(chi_max, 1 << 30)), q.shape[1])
+        q_l = q.cpu().numpy().reshape(i, j, chi_cut)
+        r_r = r.cpu().numpy().reshape(chi_cut, k, l)
+        if return_truncation_error:
+            return q_l, r_r, err, None
+        return q_l, r_r, None, None
     u, s, vh, err = svd(tensor.reshape(i * j, k * l), cut=cut, chi_max=chi_max, renormalise=renormalise,
                         return_truncation_error=return_truncation_error)
     u = u.reshape(i, j, s.size)

@@ -146,3 +146,49 @@ def test_random_circuit_driver_matches_the_reference_fixture(golden):
     np.testing.assert_allclose(tails, g["fidelity_tail"], rtol=1e-10)
     assert [int(b) for b in state.bond_dimensions] == g["bond_dimensions"]
     assert state.tensors[0].dtype == np.complex128
+
+
+def test_qr_strategy_and_svd_advanced(golden):
+    """`qr` (pivoted QR, utils.py:141-212, :370-383) and the `qr` / `svd_advanced` compression strategies
+    (canonical.py:762-833), following the reference's tests (tests/utils/test_utils.py: reconstruction, truncation
+    count by |diag R| > cut and chi_max, renormalisation)."""
+    from mdopt_b200.mps.canonical import CanonicalMPS
+    from mdopt_b200.utils.utils import qr, split_two_site_tensor
+
+    rng = np.random.default_rng(21)
+    a = rng.standard_normal((20, 12))
+    q, r, err = qr(a, cut=1e-12, chi_max=int(1e4), return_truncation_error=True)
+    np.testing.assert_allclose(q @ r, a, atol=1e-12)
+    np.testing.assert_allclose(q.T @ q, np.eye(12), atol=1e-12)
+    assert err < 1e-12
+    low = rng.standard_normal((20, 3)) @ rng.standard_normal((3, 12))        # rank 3
+    q, r, _ = qr(low, cut=1e-9)
+    assert q.shape == (20, 3) and r.shape == (3, 12)
+    np.testing.assert_allclose(q @ r, low, atol=1e-10)
+    q, r, err = qr(a, chi_max=5, return_truncation_error=True)
+    assert q.shape == (20, 5) and r.shape == (5, 12) and err == pytest.approx(np.linalg.norm(a - q @ r))
+    import scipy.linalg
+    _, r_ref, _ = scipy.linalg.qr(a, pivoting=True, mode="economic")
+    q_full, r_full, _ = qr(a, cut=0.0)
+    np.testing.assert_allclose(np.sort(np.abs(np.diag(r_ref)))[::-1], np.abs(np.diag(r_ref)), rtol=1e-12)
+    # same pivot order as LAPACK's geqp3 on a generic matrix: |R| agrees entry by entry up to the row signs
+    piv = np.argsort(-np.linalg.norm(a, axis=0))[:1]
+    assert np.argmax(np.abs(r_full[0])) == piv[0]
+    t = rng.standard_normal((5, 2, 2, 5)) + 1j * rng.standard_normal((5, 2, 2, 5))
+    ql, rr, e1, e2 = split_two_site_tensor(t, chi_max=int(1e4), cut=1e-12, strategy="qr", return_truncation_error=True)
+    assert e2 is None
+    np.testing.assert_allclose(np.einsum("ijm,mkl->ijkl", ql, rr), t, atol=1e-12)
+    # compression strategies against the numpy port's SVD compression: same truncated state up to the gauge
+    g = golden("compress_case")
+    tensors = [np.array(x) for x in g["tensors"]]
+    for strategy in ("svd_advanced", "qr"):
+        mps = CanonicalMPS([x.copy() for x in tensors], 0, 1e-12, int(1e4))
+        out, errs = mps.compress(chi_max=100, cut=1e-14, strategy=strategy, return_truncation_errors=True)
+        full = CanonicalMPS([x.copy() for x in tensors], 0).dense()
+        np.testing.assert_allclose(np.abs(out.dense()), np.abs(full), atol=1e-10)
+        assert len(errs) == len(tensors) - 1
+    mps = CanonicalMPS([x.copy() for x in tensors], 0, 1e-12, int(1e4))
+    out, err = mps.compress_bond(4, chi_max=5, cut=1e-17, strategy="svd_advanced", return_truncation_error=True)
+    assert out.tensors[4].shape[2] <= 5 and err >= 0.0
+    with pytest.raises(ValueError):
+        mps.compress_bond(4, strategy="nope")
