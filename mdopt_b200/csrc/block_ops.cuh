@@ -399,6 +399,31 @@ MD_DEV void form_q(Smem<CHI>& s, int R, int K) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// Canonical order of the columns by singular value (the tie-break that makes truncating decodes well-posed; the
+// monomial engine and oracle/structured_svd.py state the same rule): sigma descending; values that agree to
+// ORDER_TIE_REL relative are tied, and ties go to the column whose first non-zero row comes first, then to the lower
+// column index.  first_row[c] must hold the first row with a non-zero entry in column c (R if none).
+//   before(o, c) == true  <=>  column o is ranked ahead of column c
+// -------------------------------------------------------------------------------------------------
+constexpr double ORDER_TIE_REL = 1e-10;
+MD_HD bool canon_before(double w, int fo, int o, double v, int fc, int c) {
+  if (w > v * (1.0 + ORDER_TIE_REL)) return true;
+  if (v > w * (1.0 + ORDER_TIE_REL)) return false;
+  return (fo < fc) || (fo == fc && o < c);
+}
+// first non-zero row of every column of X (R x C, ld LD) -> out[c]
+template <int CHI>
+MD_DEV void first_rows(const Smem<CHI>& s, int R, int C, int* out) {
+  constexpr int LD = Smem<CHI>::LD;
+  MD_PAR_FOR(c, C) {
+    int f = R;
+    for (int i = 0; i < R; ++i) { if (s.X[i * LD + c] != 0.0) { f = i; break; } }
+    out[c] = f;
+  }
+  MD_SYNC();
+}
+
+// -------------------------------------------------------------------------------------------------
 // One-sided (Hestenes) Jacobi on the columns of X (R x C), in place: X <- X J = U diag(sigma).
 //   Round-robin pair schedule, partial dot products through shared memory, rotation applied by all
 //   threads.  On exit: s.sig[c] = ||X[:,c]||, s.order[] = columns sorted by sigma descending (ties by
@@ -517,13 +542,11 @@ MD_DEV void jacobi_columns(Smem<CHI>& s, int R, int C, int max_sweeps = 60) {
     s.sig[c] = sqrt(acc);
   }
   MD_SYNC();
+  first_rows<CHI>(s, R, C, s.flag);
   MD_PAR_FOR(c, C) {
     double v = s.sig[c];
     int pos = 0;
-    for (int o = 0; o < C; ++o) {
-      double w = s.sig[o];
-      pos += (w > v) || (w == v && o < c);
-    }
+    for (int o = 0; o < C; ++o) pos += canon_before(s.sig[o], s.flag[o], o, v, s.flag[c], c) ? 1 : 0;
     s.order[pos] = c;
   }
   MD_LEADER {
@@ -614,13 +637,11 @@ MD_DEV int ortho_probe(Smem<CHI>& s, int R, int C) {
   if (!s.iscr[11]) return 0;
   MD_PAR_FOR(c, C) s.sig[c] = sqrt(s.vn2[c]);   // overwrites z1, which is no longer needed
   MD_SYNC();
+  first_rows<CHI>(s, R, C, s.flag);
   MD_PAR_FOR(c, C) {
     const double v = s.sig[c];
     int pos = 0;
-    for (int o = 0; o < C; ++o) {
-      const double w = s.sig[o];
-      pos += (w > v) || (w == v && o < c);
-    }
+    for (int o = 0; o < C; ++o) pos += canon_before(s.sig[o], s.flag[o], o, v, s.flag[c], c) ? 1 : 0;
     s.order[pos] = c;
   }
   MD_LEADER { s.iscr[4] = 0; s.iscr[5] = 0; }
@@ -1371,17 +1392,16 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     }
   }
   __syncthreads();
-  // rank of every column among the singular values (descending, ties by column index): four adjacent lanes per
-  // column, each counting a quarter of the others (blockDim.x == 4 * N2)
+  // rank of every column in the canonical order (sigma descending, ties by first non-zero row, then column index):
+  // four adjacent lanes per column, each counting a quarter of the others (blockDim.x == 4 * N2)
+  first_rows<CHI>(s, R, C, s.flag);
   for (int t4 = tid; t4 < 4 * N2; t4 += blockDim.x) {
     const int c = t4 >> 2, q = t4 & 3;
     int pos = 0;
     if (c < C) {
       const double v = s.sig[c];
-      for (int o = q; o < C; o += 4) {
-        const double w = s.sig[o];
-        pos += (w > v) || (w == v && o < c);
-      }
+      const int fc = s.flag[c];
+      for (int o = q; o < C; o += 4) pos += canon_before(s.sig[o], s.flag[o], o, v, fc, c) ? 1 : 0;
     }
     pos += __shfl_xor_sync(0xffffffffu, pos, 1);
     pos += __shfl_xor_sync(0xffffffffu, pos, 2);

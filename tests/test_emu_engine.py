@@ -290,3 +290,18 @@ def test_cluster_default_cut_is_svd_mode_parity():
         ref, ref_ok = O.decode_css(ocode, e, **kw)
         assert st == 0 and ok == ref_ok
         np.testing.assert_allclose(dist, np.asarray(ref, float), rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("mode", [schedule.MODE_SVD, schedule.MODE_SVD_GRAM])
+def test_dense_engine_uses_the_canonical_tie_break(mode):
+    """The dense engine orders singular values like the monomial engine and oracle/structured_svd.py (sigma descending,
+    ties by first non-zero row): on truncating d=5 / chi_max=64 syndromes it equals the unmodified reference run with
+    the canonical tie-break at its SVD hook to 1e-10."""
+    g = load_golden("d5_chi64_bitflip_1024_canonical")
+    idx = [i for i, e in enumerate(g["errors"]) if e != "I" * 41][:40]
+    prog = schedule.build_decode_program(surface_code(5), True, False, True, "Optimised", None, "Bitflip", 0.1)
+    sym = schedule.symbols_from_errors([g["errors"][i] for i in idx], 2)
+    d, s, st, _, _ = H.decode(prog, sym, 64, 1e-17, 0.1, True, mode)
+    ref, ok = np.array(g["dist"])[idx], np.array(g["success"])[idx]
+    assert (st == 0).all() and (s == ok).all()
+    assert (np.abs(d - ref).max(axis=1) / ref.max(axis=1)).max() < 1e-10

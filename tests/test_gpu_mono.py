@@ -227,3 +227,21 @@ def test_hypergraph_product_ldpc_code_chi512(api):
         sym = api["schedule"].symbols_from_errors([e], k)
         d, s, st, _, _ = H.decode(prog, sym, 512, 1e-17, 0.1, True, api["schedule"].MODE_MONO, mono=True)
         assert st[0] == 0 and d[0].astype(int).tolist() == bits[b].astype(int).tolist() and int(s[0]) == int(overlap[b])
+
+
+@pytest.mark.parametrize("mode", ["svd-gram", "svd"])
+def test_dense_engine_equals_reference_with_canonical_tie_break(api, mode):
+    """The dense CTA engine (the monomial engine's fallback) applies the same canonical order: 1 024 syndromes of the
+    headline config against the unmodified reference + hook, and against the monomial engine, to 1e-10."""
+    g = load_golden("d5_chi64_bitflip_1024_canonical")
+    code = api["surface_code"](5)
+    dist, succ, status = api["decode_css_batch"](code, g["errors"], contraction_strategy="Optimised", mode=mode,
+                                                 return_status=True, **g["kwargs"])
+    ref = np.array(g["dist"])
+    assert (status == 0).all() and (succ == np.array(g["success"])).all()
+    rel = np.abs(dist - ref).max(axis=1) / ref.max(axis=1)
+    print(f"dense {mode}: max rel vs reference+canonical {rel.max():.2e}")
+    assert rel.max() < 1e-10
+    mono, msucc = api["decode_css_batch"](code, g["errors"], contraction_strategy="Optimised", mode="mono", **g["kwargs"])
+    assert (msucc == succ).all()
+    np.testing.assert_allclose(mono, dist, rtol=1e-10, atol=1e-14)
