@@ -127,13 +127,15 @@ struct MonoSmem {
   double acc[2][N2];
   double sig[N2];        // sigma per column
   double sv[N2];         // staged next site, frame view: rows (m, p) -> (st, sv)
-  double uv[N2];         // outgoing record in the mirrored frame (values)
   int16_t cc[N2];
   int16_t own[2][N2];    // k of the row with p = 0 / 1 that hits the column, -1 none; then the cluster flags
   int16_t rank[N2];      // new bond index of a column, -1 dropped
   int16_t order[N2];     // column at sorted position
   int16_t st[N2];
-  int16_t ut[N2];
+  // the outgoing record of a mirrored-frame store is assembled in acc[1] (values) / own[1] (targets): both are dead
+  // once the columns are ordered, and the 1.25 KB this saves per warp is what lets 28 warps share an SM
+  MD_DEV double* uv_buf() { return acc[1]; }
+  MD_DEV int16_t* ut_buf() { return own[1]; }
   MonoTensor tw;         // the MPO tensor of the current step (copied from the per-launch table)
   MonoState<CHI> state;
 };
@@ -532,16 +534,16 @@ struct Mono {
           dst.tgt[r] = (int16_t)tt; dst.val[r] = v;
         }
       } else {   // stored dims (Knew, 2, K): rows (kn, p) -> k
-        MW_FOR(r, 2 * Knew) { s.ut[r] = -1; s.uv[r] = 0.0; }
+        MW_FOR(r, 2 * Knew) { s.ut_buf()[r] = -1; s.uv_buf()[r] = 0.0; }
         MW_SYNC();
         MW_FOR(r, R) {
           const int c = s.cc[r];
           const int t = (c >= 0) ? s.rank[c] : -1;
-          if (t >= 0 && !zero) { const int o = t * 2 + (r & 1); s.ut[o] = (int16_t)(r >> 1); s.uv[o] = s.cv[r] * s.acc[0][c]; }
+          if (t >= 0 && !zero) { const int o = t * 2 + (r & 1); s.ut_buf()[o] = (int16_t)(r >> 1); s.uv_buf()[o] = s.cv[r] * s.acc[0][c]; }
         }
-        if (zero) { MW_LANE0 { s.ut[0] = 0; s.uv[0] = 1.0; } }
+        if (zero) { MW_LANE0 { s.ut_buf()[0] = 0; s.uv_buf()[0] = 1.0; } }
         MW_SYNC();
-        MW_FOR(r, 2 * Knew) { dst.tgt[r] = s.ut[r]; dst.val[r] = s.uv[r]; }
+        MW_FOR(r, 2 * Knew) { dst.tgt[r] = s.ut_buf()[r]; dst.val[r] = s.uv_buf()[r]; }
       }
     }
     MW_SYNC();
@@ -600,14 +602,14 @@ struct Mono {
     if (!mir) {
       MW_FOR(r, n) { const int c = s.cc[r]; dst.tgt[r] = (int16_t)c; dst.val[r] = (c >= 0) ? s.cv[r] * scale : 0.0; }
     } else {   // stored dims (Mr, 2, K): rows (m, p) -> k
-      MW_FOR(r, 2 * Mr) { s.ut[r] = -1; s.uv[r] = 0.0; }
+      MW_FOR(r, 2 * Mr) { s.ut_buf()[r] = -1; s.uv_buf()[r] = 0.0; }
       MW_SYNC();
       MW_FOR(r, n) {
         const int c = s.cc[r];
-        if (c >= 0) { const int o = c * 2 + (r & 1); s.ut[o] = (int16_t)(r >> 1); s.uv[o] = s.cv[r] * scale; }
+        if (c >= 0) { const int o = c * 2 + (r & 1); s.ut_buf()[o] = (int16_t)(r >> 1); s.uv_buf()[o] = s.cv[r] * scale; }
       }
       MW_SYNC();
-      MW_FOR(r, 2 * Mr) { dst.tgt[r] = s.ut[r]; dst.val[r] = s.uv[r]; }
+      MW_FOR(r, 2 * Mr) { dst.tgt[r] = s.ut_buf()[r]; dst.val[r] = s.uv_buf()[r]; }
     }
     MW_LANE0 { s.state.cnt.bytes_hbm += 10.0 * 2 * (mir ? Mr : K); }
     MW_SYNC();

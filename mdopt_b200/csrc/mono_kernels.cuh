@@ -45,8 +45,11 @@ __global__ void mono_prepare_kernel(const double* __restrict__ wtab, const int* 
 // A warp's whole state is its ~8 KB of shared memory (chi = 64) plus its MPS slice in the workspace, so an SM
 // keeps 24 syndromes in flight and the site records stream through L2 / HBM.
 // -------------------------------------------------------------------------------------------------
-// resident one-warp CTAs per SM the register budget is tuned for (shared memory allows 24 at chi <= 64)
-constexpr int mono_min_ctas(int chi) { return chi <= 64 ? 24 : (chi <= 128 ? 12 : (chi <= 256 ? 6 : 3)); }
+// resident one-warp CTAs per SM the register budget is tuned for (shared memory allows 28 at chi = 64)
+#ifndef MONO_CTAS_64
+#define MONO_CTAS_64 28
+#endif
+constexpr int mono_min_ctas(int chi) { return chi <= 64 ? MONO_CTAS_64 : (chi <= 128 ? 12 : (chi <= 256 ? 6 : 3)); }
 template <int CHI>
 __global__ void __launch_bounds__(32, mono_min_ctas(CHI))
 mono_decode_kernel(DecodeParams P, const int* __restrict__ prog, const MonoTensor* __restrict__ tabs,
