@@ -425,7 +425,10 @@ def run_ours(args):
             roof = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src,
                     "note": "achieved = site records read + written per launch (10 bytes per (value, target) pair, "
-                            "counted by the kernel itself) / CUDA-event duration of the launch"}
+                            "counted by the kernel itself) / CUDA-event duration of the launch.  The kernel is bound "
+                            "by instruction issue, not by HBM (profiles/r02_mono_decode_kernel_ncu_summary.md: ~1 850 "
+                            "warp instructions and ~2.7 KB of records per two-site step), so this fraction is small "
+                            "by construction"}
         else:
             flops = counters["flops_qr"] + counters["flops_jacobi"] + counters["flops_apply"]
             roof = roofline_head(flops / kernel_s / 1e12, fp64_peak, counters["bytes"] / kernel_s / 1e9)
