@@ -926,6 +926,73 @@ struct Mono {
       if (st == ST_CAPACITY || st == ST_NOT_MONOMIAL) break;
     }
   }
+
+#ifndef MDOPT_EMU
+  // ---- the same program with all warps of the CTA in LOCK-STEP: one `bar.sync` after every two-site step.  The
+  //      program is error-independent, so its control flow is the same for every syndrome; a warp without work, or
+  //      whose syndrome has failed, keeps walking the program and only takes the barriers.  Purpose: the warps of an
+  //      SM then run the same ~2 K instructions of a step at the same time and share the L0 / L1.5 instruction
+  //      caches instead of evicting each other (no_instruction is the largest stall of the free-running kernel). ----
+  static __device__ __forceinline__ void run_lockstep(SM& s, const int* prog, const uint8_t* sym, double* out,
+                                                      int* success, bool active) {
+    if (active) init_product(s, sym);
+    const int n_ops = s.state.P.n_ops, n_sites = s.state.P.n_sites;
+    int pc = 0, centre = 0;     // CTA-uniform: follows the program, not the data
+    auto ok = [&]() -> bool {
+      if (!active) return false;
+      const int st = s.state.status;
+      return st != ST_CAPACITY && st != ST_NOT_MONOMIAL;
+    };
+    while (pc < n_ops) {
+      const int op = prog[pc];
+      if (op == OP_END) break;
+      if (op == OP_MARGINAL || op == OP_MARGINAL_DMRG) {
+        const int iters = (op == OP_MARGINAL) ? 0 : (prog[pc + 1] > 0 ? prog[pc + 1] : 1);
+        if (ok()) marginal_readout(s, out, success, iters);
+        pc += (op == OP_MARGINAL) ? 1 : 2;
+      } else if (op == OP_SWEEP || op == OP_MOVE) {
+        const int target = prog[pc + 1];
+        for (int phase = (target == centre) ? 1 : 0; phase < 2; ++phase) {
+          if (phase == 1 && op == OP_MOVE) break;
+          int start, len, chi_lim, ren = 0, rsv = 0, mir = 0;
+          double cut;
+          const int* tids = nullptr;
+          if (phase == 0) {
+            mir = (target < centre) ? 1 : 0;
+            start = mir ? (n_sites - 1 - centre) : centre;
+            len = (mir ? (centre - target) : (target - centre)) + 1;
+            chi_lim = CHI; cut = s.state.P.cut_move;
+          } else {
+            start = target; len = prog[pc + 2]; ren = prog[pc + 3]; rsv = prog[pc + 4];
+            tids = prog + pc + 5; chi_lim = s.state.P.chi_max; cut = s.state.P.cut_sweep;
+          }
+          MW_SYNC();
+          MW_LANE0 { s.state.mirrored = mir; }
+          MW_SYNC();
+          if (ok()) carried_from_site(s, start, tids ? tids[0] : -1, len > 1 ? start + 1 : -1);
+          __syncthreads();
+          for (int t = 1; t < len; ++t) {
+            if (ok()) step(s, start + t, tids ? tids[t] : -1, chi_lim, cut, phase == 0, rsv, t + 1 < len ? start + t + 1 : -1);
+            __syncthreads();
+          }
+          if (ok()) {
+            if (s.state.Wq != 1) { MW_LANE0 { s.state.status = ST_CAPACITY; } }
+            else carried_to_site(s, start + len - 1, ren);
+          }
+          MW_SYNC();
+          MW_LANE0 { s.state.mirrored = 0; }
+          centre = (phase == 0) ? target : (target + len - 1);
+          MW_SYNC();
+        }
+        pc += (op == OP_MOVE) ? 2 : (5 + prog[pc + 2]);
+      } else {
+        MW_LANE0 { s.state.status = ST_NOT_MONOMIAL; }   // two-site gates / compression: dense engine
+        MW_SYNC();
+        pc = n_ops;    // uniform: the program itself is outside the engine's domain
+      }
+    }
+  }
+#endif
 };
 
 }  // namespace mdopt

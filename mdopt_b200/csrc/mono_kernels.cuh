@@ -1,6 +1,7 @@
 // Kernel and launcher of the monomial warp engine (mono_core.cuh); included by mono_inst.cu once per capacity.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "../../include/mdopt_b200.h"
 #include "mono_core.cuh"
@@ -95,6 +96,59 @@ mono_decode_kernel(DecodeParams P, const int* __restrict__ prog, const MonoTenso
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Lock-step variant: ONE CTA per SM, WPC warps, one syndrome per warp, `bar.sync` after every two-site step so that
+// the warps of the SM walk the program together and share the instruction caches (Mono::run_lockstep).
+// -------------------------------------------------------------------------------------------------
+template <int CHI, int WPC>
+__global__ void __launch_bounds__(32 * WPC, 1)
+mono_decode_lockstep_kernel(DecodeParams P, const int* __restrict__ prog, const MonoTensor* __restrict__ tabs,
+                            const uint8_t* __restrict__ syms, int batch, double* dist, int* success, int* status,
+                            double* trace, double* counters, unsigned char* ws, int* work_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  MonoSmem<CHI>& s = reinterpret_cast<MonoSmem<CHI>*>(smem_raw)[warp];
+  if (lane == 0) {
+    unsigned char* base = ws + (size_t)(blockIdx.x * WPC + warp) * mono_ws_bytes_per_warp(CHI, P.n_sites);
+    MonoState<CHI>& st = s.state;
+    st.sites = reinterpret_cast<MonoSite<CHI>*>(base);
+    st.bd = reinterpret_cast<int*>(base + (size_t)P.n_sites * sizeof(MonoSite<CHI>));
+    st.env = reinterpret_cast<double*>(base + mono_env_offset(CHI, P.n_sites));
+    st.tabs = tabs; st.P = P; st.trace = nullptr;
+    st.cnt = MonoCounters{};
+    st.status = ST_OK;
+  }
+  __syncwarp();
+  const int ncls = mono_out_per_syndrome(P.n_logical);
+  while (true) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(work_counter, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    const bool active = b < batch;
+    if (!__syncthreads_or(active ? 1 : 0)) break;
+    if (lane == 0) s.state.trace = (active && trace) ? trace + (size_t)b * P.trace_max * P.trace_stride : nullptr;
+    __syncwarp();
+    Mono<CHI>::run_lockstep(s, prog, syms + (size_t)(active ? b : 0) * P.n_sites, dist + (size_t)(active ? b : 0) * ncls,
+                            success + (active ? b : 0), active);
+    __syncwarp();
+    if (active) {
+      const int st = s.state.status;
+      if (st == ST_CAPACITY || st == ST_NOT_MONOMIAL) {
+        for (int i = lane; i < ncls; i += 32) dist[(size_t)b * ncls + i] = nan("");
+        if (lane == 0) { success[b] = 0; s.state.cnt.n_fallback += 1.0; }
+      }
+      if (lane == 0) status[b] = st;
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && counters) {
+    atomicAdd(counters + 3, s.state.cnt.bytes_hbm);
+    atomicAdd(counters + 4, s.state.cnt.n_steps);
+    atomicAdd(counters + 5, s.state.cnt.n_trunc);
+    atomicAdd(counters + 7, s.state.cnt.n_fallback);
+  }
+}
+
 template <int CHI>
 int mono_num_warps_impl() {
   int dev = 0, sms = 0, per = 0;
@@ -137,6 +191,33 @@ int launch_mono_decode(const mdopt_decode_desc* d, int n_warps, const int32_t* p
   if (counters) {
     e = cudaMemsetAsync(counters, 0, 16 * sizeof(double), st);
     if (e != cudaSuccess) return (int)e;
+  }
+  if constexpr (CHI == 64) {
+    // default at chi = 64: the lock-step kernel, one CTA of 28 warps per SM (+15 % over 28 free-running one-warp
+    // CTAs: 227 k vs 198 k non-trivial syndromes/s).  MDOPT_MONO_LOCKSTEP=0 selects the free-running kernel,
+    // 16 / 24 other CTA sizes (measurement switches).
+    const char* ls = getenv("MDOPT_MONO_LOCKSTEP");
+    const int wpc = ls ? atoi(ls) : 28;
+    if (wpc == 16 || wpc == 24 || wpc == 28) {
+      int dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const int ctas = (n_warps / wpc) < sms ? (n_warps / wpc) : sms;
+      if (ctas < 1) return MDOPT_E_BADARG;
+      const size_t smem = (size_t)wpc * sizeof(MonoSmem<CHI>);
+#define MD_LAUNCH_LS(W)                                                                                          \
+  {                                                                                                              \
+    e = cudaFuncSetAttribute((const void*)mono_decode_lockstep_kernel<CHI, W>,                                   \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                            \
+    if (e != cudaSuccess) return (int)e;                                                                         \
+    mono_decode_lockstep_kernel<CHI, W><<<ctas, 32 * W, smem, st>>>(                                             \
+        P, program, tabs, symbols, batch, dist, success, status, d->trace_stride > 0 ? trace : nullptr, counters, \
+        reinterpret_cast<unsigned char*>(workspace), work_counter);                                              \
+  }
+      if (wpc == 16) MD_LAUNCH_LS(16) else if (wpc == 24) MD_LAUNCH_LS(24) else MD_LAUNCH_LS(28)
+#undef MD_LAUNCH_LS
+      return (int)cudaGetLastError();
+    }
   }
   const int grid = batch < n_warps ? batch : n_warps;
   mono_decode_kernel<CHI><<<grid, 32, sizeof(MonoSmem<CHI>), st>>>(
