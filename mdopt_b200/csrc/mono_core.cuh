@@ -41,7 +41,11 @@
 #define MW_PHASE __device__ __noinline__
 // lane loops are NOT unrolled: trip counts are <= 2*chi/32, and the unrolled copies (4x + remainder per loop) made the
 // hot code of a step larger than the 32 KB L1.5 instruction cache
+#ifdef MW_UNROLL_LANE_LOOPS
+#define MW_FOR(i, n) for (int i = (int)(threadIdx.x & 31u); i < (n); i += 32)
+#else
 #define MW_FOR(i, n) _Pragma("unroll 1") for (int i = (int)(threadIdx.x & 31u); i < (n); i += 32)
+#endif
 #define MW_SYNC() __syncwarp()
 #define MW_ANY(x) __any_sync(0xffffffffu, (x))
 #define MW_LANE0 if ((threadIdx.x & 31u) == 0)
