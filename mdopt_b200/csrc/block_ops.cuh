@@ -1237,7 +1237,9 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     if (tid == 0) s.cnt.flops_jacobi += 10.0 * R * C;
     __syncthreads();
   }
-  if (!converged && try_ortho) {
+  // ---- Gram check (also the convergence test after every sweep: one register-tiled pass over X^T X and three
+  //      barriers instead of a whole checking sweep of C-1 barrier-separated rounds) ----
+  auto gram_check = [&]() -> bool {
     // ---- Gram check: are the columns already mutually orthogonal (to the rotation threshold)?  In the decode
     // with bit-flip bias every bond stays in its Schmidt basis under the XOR / SWAP constraint tensors, so the
     // matrix handed to an SVD-mode split needs no rotation at all; one register-tiled pass over X^T X (warp w
@@ -1310,9 +1312,15 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
           }
         }
     }
-    converged = !__syncthreads_or(bad);
-    ortho_done = converged;
+    const bool gram_ok = !__syncthreads_or(bad);
     if (tid == 0) s.cnt.flops_jacobi += 1.0 * R * C * (C + 1);   // R (C^2 + C) / 2 multiply-adds
+      return gram_ok;
+  };
+  int norms_ready = 0;   // s.vn2 holds the squared column norms of the final X (the Gram diagonal)
+  if (!converged && try_ortho) {
+    converged = gram_check();
+    ortho_done = converged;
+    norms_ready = converged;
   }
   if (!converged && spill != nullptr) {
     // the rotations are about to change X: keep the original for the coefficient product (flat, ld C)
@@ -1350,8 +1358,10 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
           sab += __shfl_xor_sync(0xffffffffu, sab, off);
         }
         if (valid && sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) {
-          const double zeta = (sbb - saa) / (2.0 * sab);
-          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)) with zeta = alpha / beta, written with one division:
+          // t = sign(alpha) beta / (|alpha| + sqrt(alpha^2 + beta^2))   (the round's latency is a chain of these)
+          const double alpha = sbb - saa, beta = 2.0 * sab;
+          const double t = copysign(beta, alpha * beta) / (fabs(alpha) + sqrt(alpha * alpha + beta * beta));
           const double c = rsqrt(1.0 + t * t);
           const double sn = c * t;
 #pragma unroll
@@ -1372,9 +1382,17 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     converged = (nrot == 0);
     if (tid == 0) s.cnt.flops_jacobi += 6.0 * R * npair * (n - 1) + 6.0 * R * nrot;
     __syncthreads();
+    // did this sweep finish the job?  (same pair threshold as the rotations.)  Only asked when the sweep rotated
+    // less than a quarter of its pairs: a sweep that still rotates most pairs is far from done and the check would be
+    // wasted (random dense matrices: ~10 sweeps, only the last ones qualify)
+    if (!converged && 4 * nrot <= npair * (n - 1)) {
+      converged = gram_check();
+      norms_ready = converged;
+      __syncthreads();
+    }
   }
   // singular values = column norms; order by value (descending), ties by column index
-  if (ortho_done) {
+  if (norms_ready) {
     MD_PAR_FOR(c, C) s.sig[c] = sqrt(s.vn2[c]);   // the Gram diagonal
   } else {
     MD_PAR_FOR(t, NCH * C) {

@@ -168,11 +168,11 @@ def decode_css_batch(code, errors: Sequence[str], chi_max: int = int(1e4), cut: 
         raise NotImplementedError("more than 12 logical sites: the Dephasing-DMRG read-out needs the bit-flip bias "
                                   "(the monomial engine); the depolarising bias is dense")
     # whole-batch character tests (decoding.py:1225-1231: trivial / "X" in error / "Z" in error), no per-string Python
-    raw = schedule.pack_errors(errors, n)
-    trivial = (raw == ord("I")).all(axis=1)
-    has_x = (raw == ord("X")).any(axis=1)
-    has_z = (raw == ord("Z")).any(axis=1)
-    erased = (raw == ord("E")).any(axis=1)
+    raw, flags = schedule.pack_errors_with_flags(errors, n)
+    trivial = flags == 0
+    has_x = (flags & schedule.FLAG_X) != 0
+    has_z = (flags & schedule.FLAG_Z) != 0
+    erased = (flags & schedule.FLAG_E) != 0
     if k > 12:
         success[trivial] = 1     # all bits 0, overlap 1 (the reference's early exit returns [1, 0, 0, 0], 1)
     else:

@@ -277,17 +277,27 @@ def readout_kept_mask(error: str, n_logical: int) -> int:
     return mask
 
 
-_LUT = np.zeros((256, 2), dtype=np.uint8)
-_VALID = np.zeros(256, dtype=bool)
+# Character tables for whole-batch packing (one table look-up per character, no per-string Python):
+#   _FLAG[c]  : bit 0 = 'X', bit 1 = 'Z', bit 2 = 'Y', bit 3 = 'E', bit 7 = not a Pauli character ('I' -> 0)
+#   _SYM16[c] : the two product-state symbols of the qubit as one little-endian uint16 (low byte = X site, high = Z site)
+_FLAG = np.full(256, 128, dtype=np.uint8)
+_SYM16 = np.zeros(256, dtype=np.uint16)
 for _ch, _bits in _PAULI_BITS.items():
-    _LUT[ord(_ch)] = _bits
-    _VALID[ord(_ch)] = True
+    _FLAG[ord(_ch)] = {"I": 0, "X": 1, "Z": 2, "Y": 4, "E": 8}[_ch]
+    _SYM16[ord(_ch)] = _bits[0] | (_bits[1] << 8)
+FLAG_X, FLAG_Z, FLAG_Y, FLAG_E = 1, 2, 4, 8
 
 
 def pack_errors(errors: Sequence[str], n: int) -> np.ndarray:
     """uint8 [B, n] array of the Pauli characters of a batch of error strings, validated like the reference does
     (length: decoding.py:1249-1252, characters: :318).  One buffer for the whole batch: the per-string work of a
     100k-syndrome batch must stay out of Python loops."""
+    return pack_errors_with_flags(errors, n)[0]
+
+
+def pack_errors_with_flags(errors: Sequence[str], n: int):
+    """(raw uint8 [B, n], flags uint8 [B]): the characters and, per string, the OR of their _FLAG bits -- which is all
+    the reference's literal-character tests need (all-'I': flags == 0; "X" in error: flags & FLAG_X; ...)."""
     B = len(errors)
     lengths = set(map(len, errors))
     if lengths - {n}:
@@ -298,11 +308,12 @@ def pack_errors(errors: Sequence[str], n: int) -> np.ndarray:
     except UnicodeEncodeError:
         bad = next(ch for e in errors for ch in e if ord(ch) > 127)
         raise ValueError(f"Invalid Pauli encountered -- {bad}.") from None
-    ok = _VALID[raw]
-    if not ok.all():
-        b, q = np.argwhere(~ok)[0]
+    flags = np.bitwise_or.reduce(_FLAG[raw], axis=1) if B else np.zeros(0, dtype=np.uint8)
+    if (flags & 128).any():
+        b = int(np.argmax(flags & 128))
+        q = int(np.argmax(_FLAG[raw[b]] & 128))
         raise ValueError(f"Invalid Pauli encountered -- {errors[b][q]}.")
-    return raw
+    return raw, flags
 
 
 def symbols_from_raw(raw: np.ndarray, n_logical: int) -> np.ndarray:
@@ -310,7 +321,7 @@ def symbols_from_raw(raw: np.ndarray, n_logical: int) -> np.ndarray:
     B, n = raw.shape
     out = np.empty((B, n_logical + 2 * n), dtype=np.uint8)
     out[:, :n_logical] = SYM_PLUS
-    out[:, n_logical:] = _LUT[raw].reshape(B, 2 * n)
+    out[:, n_logical:] = _SYM16[raw].view(np.uint8).reshape(B, 2 * n)   # little-endian: X-site symbol, Z-site symbol
     return out
 
 
