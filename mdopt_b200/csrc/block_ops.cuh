@@ -1331,8 +1331,8 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     if (tid == 0) s.iscr[6] = 0;
     __syncthreads();
     for (int rnd = 0; rnd < n - 1; ++rnd) {
-      // every lane runs the load / dot / shuffle sequence (invalid slots contribute zeros), so the three
-      // reductions are plain full-mask shuffles in converged code; only the rotation itself is conditional
+      // every lane of a warp with a valid pair runs the load / dot / shuffle sequence (invalid slots contribute
+      // zeros), so the three reductions are plain full-mask shuffles; only the rotation itself is conditional
       int a = 0, b = 0;
       bool valid = false;
       if (slot < npair) {
@@ -1340,7 +1340,10 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
         else { a = (rnd + slot) % (n - 1); b = (rnd - slot + (n - 1)) % (n - 1); }
         valid = (a < C && b < C);  // uniform over the 8 lanes of the slot
       }
-      {
+      // A round is issue-bound (~350 instructions per warp): warps none of whose four pair slots is valid (small C)
+      // go straight to the barrier.  (Stopping the unrolled row-slot loops at the matrix height with uniform breaks
+      // was tried and lost 2x: the loads no longer issue as one batch.)
+      if (__any_sync(0xffffffffu, valid)) {
         double xa[RPT], xb[RPT];
         double saa = 0.0, sbb = 0.0, sab = 0.0;
 #pragma unroll
