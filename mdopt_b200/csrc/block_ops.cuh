@@ -1239,7 +1239,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
   }
   // ---- Gram check (also the convergence test after every sweep: one register-tiled pass over X^T X and three
   //      barriers instead of a whole checking sweep of C-1 barrier-separated rounds) ----
-  auto gram_check = [&]() -> bool {
+  auto gram_check = [&](bool record) -> bool {
     // ---- Gram check: are the columns already mutually orthogonal (to the rotation threshold)?  In the decode
     // with bit-flip bias every bond stays in its Schmidt basis under the XOR / SWAP constraint tensors, so the
     // matrix handed to an SVD-mode split needs no rotation at all; one register-tiled pass over X^T X (warp w
@@ -1308,7 +1308,14 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
           const int ca = a0 + u, cb = lane + 32 * v;
           if (use[v] && ca < C && cb < C && ca != cb) {
             const double saa = s.vn2[ca], sbb = s.vn2[cb], sab = g[u][v];
-            if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) bad = 1;
+            if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) {
+              bad = 1;
+              if (record) {   // remember the offending pair; a column with two different partners breaks the matching
+                const int o1 = atomicCAS(&s.perm[ca], -1, cb);
+                const int o2 = atomicCAS(&s.perm[cb], -1, ca);
+                if ((o1 != -1 && o1 != cb) || (o2 != -1 && o2 != ca)) s.iscr[12] = 1;
+              }
+            }
           }
         }
     }
@@ -1317,14 +1324,68 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       return gram_ok;
   };
   int norms_ready = 0;   // s.vn2 holds the squared column norms of the final X (the Gram diagonal)
+  int pair_round_done = 0;
   if (!converged && try_ortho) {
-    converged = gram_check();
+    MD_PAR_FOR(c, C) s.perm[c] = -1;       // partner of a column in an offending pair (s.perm is free in the SVD path)
+    if (tid == 0) s.iscr[12] = 0;          // 1: the offending pairs do not form a matching
+    __syncthreads();
+    converged = gram_check(true);
     ortho_done = converged;
     norms_ready = converged;
   }
   if (!converged && spill != nullptr) {
     // the rotations are about to change X: keep the original for the coefficient product (flat, ld C)
     MD_PAR_FOR(t, R * C) { int r = t / C, c = t - r * C; spill[t] = X[r * LD + c]; }
+    __syncthreads();
+  }
+  if (!converged && try_ortho && s.iscr[12] == 0) {
+    // ---- Pair round.  Measured on depolarising-bias decodes (4 012 rotating splits): the columns are mutually
+    // orthogonal except for DISJOINT pairs -- the first cyclic sweep never rotates a column twice (median 6 rotations,
+    // at most C/2) and the second sweep only confirms.  So when the offending pairs the Gram check recorded form a
+    // matching, all of them are rotated in ONE barrier-separated round (8 lanes per pair, fresh dot products) and the
+    // Gram check is asked again; a cyclic sweep is C-1 rounds of ~1 500 cycles each.  Anything else falls through to
+    // the sweeps below. ----
+    int nrot_pairs = 0;
+    for (int a = grp; a < ((C + NGRP - 1) / NGRP) * NGRP; a += NGRP) {
+      const int b = (a < C) ? s.perm[a] : -1;
+      const bool valid = (b > a);
+      double xa[RPT], xb[RPT];
+      double saa = 0.0, sbb = 0.0, sab = 0.0;
+#pragma unroll
+      for (int idx = 0; idx < RPT; ++idx) {
+        const int r = 8 * idx + sub;
+        const bool ok = valid && r < R;
+        xa[idx] = ok ? X[r * LD + a] : 0.0;
+        xb[idx] = ok ? X[r * LD + b] : 0.0;
+        saa += xa[idx] * xa[idx]; sbb += xb[idx] * xb[idx]; sab += xa[idx] * xb[idx];
+      }
+#pragma unroll
+      for (int off = 1; off < 8; off <<= 1) {
+        saa += __shfl_xor_sync(0xffffffffu, saa, off);
+        sbb += __shfl_xor_sync(0xffffffffu, sbb, off);
+        sab += __shfl_xor_sync(0xffffffffu, sab, off);
+      }
+      if (valid && sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) {
+        const double alpha = sbb - saa, beta = 2.0 * sab;
+        const double t = copysign(beta, alpha * beta) / (fabs(alpha) + sqrt(alpha * alpha + beta * beta));
+        const double c = rsqrt(1.0 + t * t);
+        const double sn = c * t;
+#pragma unroll
+        for (int idx = 0; idx < RPT; ++idx) {
+          const int r = 8 * idx + sub;
+          if (r < R) {
+            X[r * LD + a] = c * xa[idx] - sn * xb[idx];
+            X[r * LD + b] = sn * xa[idx] + c * xb[idx];
+          }
+        }
+        if (sub == 0) ++nrot_pairs;
+      }
+    }
+    pair_round_done = 1;
+    if (nrot_pairs) atomicAdd(&s.cnt.flops_jacobi, 12.0 * R * nrot_pairs);
+    __syncthreads();
+    converged = gram_check(false);
+    norms_ready = converged;
     __syncthreads();
   }
   while (!converged && sweeps < max_sweeps) {
@@ -1389,7 +1450,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     // less than a quarter of its pairs: a sweep that still rotates most pairs is far from done and the check would be
     // wasted (random dense matrices: ~10 sweeps, only the last ones qualify)
     if (!converged && 4 * nrot <= npair * (n - 1)) {
-      converged = gram_check();
+      converged = gram_check(false);
       norms_ready = converged;
       __syncthreads();
     }
@@ -1429,9 +1490,9 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     if (c < C && q == 0) s.order[pos] = c;
   }
   if (tid == 0) {
-    s.iscr[4] = sweeps; s.iscr[5] = converged ? 0 : 1;
-    s.iscr[9] = (sweeps == 0 && C >= 2) ? 1 : 0;   // columns were orthogonal on entry: X is untouched
-    s.cnt.n_jacobi_sweeps += sweeps;
+    s.iscr[4] = sweeps + pair_round_done; s.iscr[5] = converged ? 0 : 1;
+    s.iscr[9] = (sweeps == 0 && !pair_round_done && C >= 2) ? 1 : 0;   // columns were orthogonal on entry: X is untouched
+    s.cnt.n_jacobi_sweeps += sweeps + pair_round_done;
     s.cnt.flops_jacobi += 2.0 * R * C;
   }
   __syncthreads();
