@@ -1141,7 +1141,8 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
   int sweeps = 0;
   int converged = (C < 2);
   int ortho_done = 0;
-  if (!converged && try_ortho == 1) {
+  // ---- Probe check (Freivalds), see below; a lambda because it is asked again after a pair round ----
+  auto probe_check = [&]() -> bool {
     // ---- Probe check (Freivalds): for two fixed pseudo-random vectors z the identity X^T (X z) = D z with
     // D = diag(|x_c|^2) holds for every z exactly when the columns are mutually orthogonal; a deviation above
     // 1e-12 |x_c| |X z| in any component sends the call to the deterministic machinery below (Gram check /
@@ -1163,21 +1164,21 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     // Thread t works on index t % N2 (a row in pass 1, a column in pass 2) and on the quarter t / N2 of the
     // other dimension; consecutive lanes touch consecutive rows / columns, which is conflict-free with the odd
     // leading dimension.  The four partial sums meet in shared memory (s.part viewed as [3][4][N2]).
-    const int idx = tid % N2, grp = tid / N2;      // blockDim.x == 4 * N2 for every capacity with CHI >= 8
+    const int idx = tid % N2, qtr = tid / N2;      // blockDim.x == 4 * N2 for every capacity with CHI >= 8
     double* pr = s.part;
     // pass 1: y = X z
     {
       double a0s = 0.0, a1s = 0.0;
       if (idx < R) {
 #pragma unroll 4
-        for (int c = grp; c < C; c += 4) { const double x = X[idx * LD + c]; a0s += x * z0[c]; a1s += x * z1[c]; }
+        for (int c = qtr; c < C; c += 4) { const double x = X[idx * LD + c]; a0s += x * z0[c]; a1s += x * z1[c]; }
       }
-      pr[(0 * 4 + grp) * N2 + idx] = a0s;
-      pr[(1 * 4 + grp) * N2 + idx] = a1s;
+      pr[(0 * 4 + qtr) * N2 + idx] = a0s;
+      pr[(1 * 4 + qtr) * N2 + idx] = a1s;
     }
     __syncthreads();
     double ny0 = 0.0, ny1 = 0.0;
-    if (grp == 0 && idx < R) {
+    if (qtr == 0 && idx < R) {
       const double a0s = (pr[idx] + pr[N2 + idx]) + (pr[2 * N2 + idx] + pr[3 * N2 + idx]);
       const double a1s = (pr[4 * N2 + idx] + pr[5 * N2 + idx]) + (pr[6 * N2 + idx] + pr[7 * N2 + idx]);
       y0[idx] = a0s; y1[idx] = a1s; ny0 = a0s * a0s; ny1 = a1s * a1s;
@@ -1201,16 +1202,16 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       double w0 = 0.0, w1 = 0.0, d = 0.0;
       if (idx < C) {
 #pragma unroll 4
-        for (int r = grp; r < R; r += 4) { const double x = X[r * LD + idx]; w0 += x * y0[r]; w1 += x * y1[r]; d += x * x; }
+        for (int r = qtr; r < R; r += 4) { const double x = X[r * LD + idx]; w0 += x * y0[r]; w1 += x * y1[r]; d += x * x; }
       }
-      pr[(0 * 4 + grp) * N2 + idx] = w0;
-      pr[(1 * 4 + grp) * N2 + idx] = w1;
-      pr[(2 * 4 + grp) * N2 + idx] = d;
+      pr[(0 * 4 + qtr) * N2 + idx] = w0;
+      pr[(1 * 4 + qtr) * N2 + idx] = w1;
+      pr[(2 * 4 + qtr) * N2 + idx] = d;
     }
     __syncthreads();
     int bad = 0;
     double mxd = 0.0;
-    if (grp == 0 && idx < C) {
+    if (qtr == 0 && idx < C) {
       const double w0 = (pr[idx] + pr[N2 + idx]) + (pr[2 * N2 + idx] + pr[3 * N2 + idx]);
       const double w1 = (pr[4 * N2 + idx] + pr[5 * N2 + idx]) + (pr[6 * N2 + idx] + pr[7 * N2 + idx]);
       const double d = (pr[8 * N2 + idx] + pr[9 * N2 + idx]) + (pr[10 * N2 + idx] + pr[11 * N2 + idx]);
@@ -1218,6 +1219,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       mxd = d;
       const double e0 = w0 - d * z0[idx], e1 = w1 - d * z1[idx];
       if (e0 * e0 > 1e-24 * d * ny0 || e1 * e1 > 1e-24 * d * ny1) bad = 1;
+      s.flag[idx] = bad;   // columns whose component of X^T X z deviates: they take part in a non-orthogonal pair
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) mxd = fmax(mxd, __shfl_xor_sync(0xffffffffu, mxd, off));
@@ -1232,10 +1234,15 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       floor2 = mx * (4.0 * EPS) * (4.0 * EPS);
       if (tid == 0) s.dscr[6] = floor2;
     }
-    converged = !any_bad;
-    ortho_done = converged;
     if (tid == 0) s.cnt.flops_jacobi += 10.0 * R * C;
     __syncthreads();
+    return !any_bad;
+    };
+  int probe_failed = 0;
+  if (!converged && try_ortho == 1) {
+    converged = probe_check();
+    ortho_done = converged;
+    probe_failed = !converged;
   }
   // ---- Gram check (also the convergence test after every sweep: one register-tiled pass over X^T X and three
   //      barriers instead of a whole checking sweep of C-1 barrier-separated rounds) ----
@@ -1323,48 +1330,59 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     if (tid == 0) s.cnt.flops_jacobi += 1.0 * R * C * (C + 1);   // R (C^2 + C) / 2 multiply-adds
       return gram_ok;
   };
-  int norms_ready = 0;   // s.vn2 holds the squared column norms of the final X (the Gram diagonal)
+  int norms_ready = ortho_done;   // s.vn2 holds the squared column norms of the final X (Gram diagonal / the probe's d)
   int pair_round_done = 0;
-  if (!converged && try_ortho) {
-    MD_PAR_FOR(c, C) s.perm[c] = -1;       // partner of a column in an offending pair (s.perm is free in the SVD path)
-    if (tid == 0) s.iscr[12] = 0;          // 1: the offending pairs do not form a matching
+  int gram_recorded = 0;
+  int spilled = 0;
+  int want_probe_pairs = 0;
+  if (probe_failed) {
+    // ---- Probe mode, failed probe: the columns the probe flagged are the only candidates for non-orthogonal pairs.
+    // With few of them, the pairs AMONG them are tested exactly (8 lanes per pair), and if the offending ones form a
+    // matching they are rotated in one round and the probe is asked again -- no Gram matrix, no sweep. ----
+    if (tid == 0) {
+      int nf = 0;
+      for (int c = 0; c < C; ++c) if (s.flag[c]) s.order[nf++] = c;
+      s.iscr[13] = nf;
+      s.iscr[12] = 0;
+    }
+    MD_PAR_FOR(c, C) s.perm[c] = -1;
     __syncthreads();
-    converged = gram_check(true);
-    ortho_done = converged;
-    norms_ready = converged;
+    const int nf = s.iscr[13];
+    want_probe_pairs = (nf >= 2 && nf <= 48);
   }
-  if (!converged && spill != nullptr) {
-    // the rotations are about to change X: keep the original for the coefficient product (flat, ld C)
-    MD_PAR_FOR(t, R * C) { int r = t / C, c = t - r * C; spill[t] = X[r * LD + c]; }
-    __syncthreads();
-  }
-  if (!converged && try_ortho && s.iscr[12] == 0) {
-    // ---- Pair round.  Measured on depolarising-bias decodes (4 012 rotating splits): the columns are mutually
-    // orthogonal except for DISJOINT pairs -- the first cyclic sweep never rotates a column twice (median 6 rotations,
-    // at most C/2) and the second sweep only confirms.  So when the offending pairs the Gram check recorded form a
-    // matching, all of them are rotated in ONE barrier-separated round (8 lanes per pair, fresh dot products) and the
-    // Gram check is asked again; a cyclic sweep is C-1 rounds of ~1 500 cycles each.  Anything else falls through to
-    // the sweeps below. ----
+  // one 8-lane group: dot products of columns a, b (all lanes of the warp take part in the shuffles)
+  auto pair_dots = [&](int a, int b, bool valid, double (&xa)[RPT], double (&xb)[RPT], double& saa, double& sbb,
+                       double& sab) {
+    saa = 0.0; sbb = 0.0; sab = 0.0;
+#pragma unroll
+    for (int idx = 0; idx < RPT; ++idx) {
+      const int r = 8 * idx + sub;
+      const bool ok = valid && r < R;
+      xa[idx] = ok ? X[r * LD + a] : 0.0;
+      xb[idx] = ok ? X[r * LD + b] : 0.0;
+      saa += xa[idx] * xa[idx]; sbb += xb[idx] * xb[idx]; sab += xa[idx] * xb[idx];
+    }
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+      saa += __shfl_xor_sync(0xffffffffu, saa, off);
+      sbb += __shfl_xor_sync(0xffffffffu, sbb, off);
+      sab += __shfl_xor_sync(0xffffffffu, sab, off);
+    }
+  };
+  // ---- Pair round.  Measured on depolarising-bias decodes (4 012 rotating splits): the columns are mutually
+  // orthogonal except for DISJOINT pairs -- the first cyclic sweep never rotates a column twice (median 6 rotations,
+  // at most C/2) and the second sweep only confirms.  So when the offending pairs the Gram check recorded form a
+  // matching, all of them are rotated in ONE barrier-separated round (8 lanes per pair, fresh dot products) and the
+  // Gram check is asked again; a cyclic sweep is C-1 rounds of ~1 500 cycles each.  Anything else falls through to
+  // the sweeps below. ----
+  auto pair_round = [&]() {
     int nrot_pairs = 0;
     for (int a = grp; a < ((C + NGRP - 1) / NGRP) * NGRP; a += NGRP) {
       const int b = (a < C) ? s.perm[a] : -1;
       const bool valid = (b > a);
       double xa[RPT], xb[RPT];
-      double saa = 0.0, sbb = 0.0, sab = 0.0;
-#pragma unroll
-      for (int idx = 0; idx < RPT; ++idx) {
-        const int r = 8 * idx + sub;
-        const bool ok = valid && r < R;
-        xa[idx] = ok ? X[r * LD + a] : 0.0;
-        xb[idx] = ok ? X[r * LD + b] : 0.0;
-        saa += xa[idx] * xa[idx]; sbb += xb[idx] * xb[idx]; sab += xa[idx] * xb[idx];
-      }
-#pragma unroll
-      for (int off = 1; off < 8; off <<= 1) {
-        saa += __shfl_xor_sync(0xffffffffu, saa, off);
-        sbb += __shfl_xor_sync(0xffffffffu, sbb, off);
-        sab += __shfl_xor_sync(0xffffffffu, sab, off);
-      }
+      double saa, sbb, sab;
+      pair_dots(a, b, valid, xa, xb, saa, sbb, sab);
       if (valid && sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) {
         const double alpha = sbb - saa, beta = 2.0 * sab;
         const double t = copysign(beta, alpha * beta) / (fabs(alpha) + sqrt(alpha * alpha + beta * beta));
@@ -1384,6 +1402,54 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     pair_round_done = 1;
     if (nrot_pairs) atomicAdd(&s.cnt.flops_jacobi, 12.0 * R * nrot_pairs);
     __syncthreads();
+  };
+  if (want_probe_pairs) {
+    const int nf = s.iscr[13];
+    int found = 0;
+    for (int p = grp; p < ((nf * nf + NGRP - 1) / NGRP) * NGRP; p += NGRP) {
+      const int i = p / nf, j = p - i * nf;
+      const bool valid = (p < nf * nf) && (i < j);
+      const int a = valid ? s.order[i] : 0, b = valid ? s.order[j] : 0;
+      double xa[RPT], xb[RPT];
+      double saa, sbb, sab;
+      pair_dots(a, b, valid, xa, xb, saa, sbb, sab);
+      if (valid && sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2 && sub == 0) {
+        found = 1;
+        const int o1 = atomicCAS(&s.perm[a], -1, b);
+        const int o2 = atomicCAS(&s.perm[b], -1, a);
+        if ((o1 != -1 && o1 != b) || (o2 != -1 && o2 != a)) s.iscr[12] = 1;
+      }
+    }
+    const int any_found = __syncthreads_or(found);
+    if (any_found && s.iscr[12] == 0) {
+      if (spill != nullptr) {   // the rotations are about to change X: keep the original for the coefficient product
+        MD_PAR_FOR(t, R * C) { int r = t / C, c = t - r * C; spill[t] = X[r * LD + c]; }
+        __syncthreads();
+        spilled = 1;
+      }
+      pair_round();
+      converged = probe_check();
+      norms_ready = converged;
+      __syncthreads();
+    }
+  }
+  if (!converged && try_ortho) {
+    MD_PAR_FOR(c, C) s.perm[c] = -1;       // partner of a column in an offending pair (s.perm is free in the SVD path)
+    if (tid == 0) s.iscr[12] = 0;          // 1: the offending pairs do not form a matching
+    __syncthreads();
+    converged = gram_check(true);
+    gram_recorded = 1;
+    if (!pair_round_done) ortho_done = converged;
+    norms_ready = converged;
+  }
+  if (!converged && !spilled && spill != nullptr) {
+    // the rotations are about to change X: keep the original for the coefficient product (flat, ld C)
+    MD_PAR_FOR(t, R * C) { int r = t / C, c = t - r * C; spill[t] = X[r * LD + c]; }
+    __syncthreads();
+    spilled = 1;
+  }
+  if (!converged && try_ortho && gram_recorded && s.iscr[12] == 0) {
+    pair_round();
     converged = gram_check(false);
     norms_ready = converged;
     __syncthreads();
