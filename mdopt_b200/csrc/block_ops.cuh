@@ -1375,9 +1375,17 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
   // matching, all of them are rotated in ONE barrier-separated round (8 lanes per pair, fresh dot products) and the
   // Gram check is asked again; a cyclic sweep is C-1 rounds of ~1 500 cycles each.  Anything else falls through to
   // the sweeps below. ----
-  auto pair_round = [&]() {
+  // rotation (cos, sin) of the pairs this thread's group rotated (a group sees at most two pairs: C <= 2 NGRP)
+  double keep_c[2] = {1.0, 1.0}, keep_s[2] = {0.0, 0.0};
+  int keep_a[2] = {-1, -1};
+  int pair_rounds = 0;
+  static_assert(2 * NGRP >= N2, "a pair round visits every column in two passes of the groups");
+  auto pair_round = [&](bool save_orig) {
     int nrot_pairs = 0;
-    for (int a = grp; a < ((C + NGRP - 1) / NGRP) * NGRP; a += NGRP) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      if (it * NGRP >= C) continue;   // uniform
+      const int a = grp + it * NGRP;
       const int b = (a < C) ? s.perm[a] : -1;
       const bool valid = (b > a);
       double xa[RPT], xb[RPT];
@@ -1394,12 +1402,18 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
           if (r < R) {
             X[r * LD + a] = c * xa[idx] - sn * xb[idx];
             X[r * LD + b] = sn * xa[idx] + c * xb[idx];
+            if (save_orig) { spill[(size_t)r * C + a] = xa[idx]; spill[(size_t)r * C + b] = xb[idx]; }
           }
         }
+        keep_c[it] = c; keep_s[it] = sn; keep_a[it] = a;
         if (sub == 0) ++nrot_pairs;
+      } else if (valid && sub == 0) {
+        // below the threshold on the fresh dot product: the pair stays as it is and counts as untouched
+        s.perm[a] = -1; s.perm[b] = -1;
       }
     }
     pair_round_done = 1;
+    ++pair_rounds;
     if (nrot_pairs) atomicAdd(&s.cnt.flops_jacobi, 12.0 * R * nrot_pairs);
     __syncthreads();
   };
@@ -1422,18 +1436,21 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     }
     const int any_found = __syncthreads_or(found);
     if (any_found && s.iscr[12] == 0) {
-      if (spill != nullptr) {   // the rotations are about to change X: keep the original for the coefficient product
-        MD_PAR_FOR(t, R * C) { int r = t / C, c = t - r * C; spill[t] = X[r * LD + c]; }
-        __syncthreads();
-        spilled = 1;
-      }
-      pair_round();
+      // the rotations change X: the round saves the original of the columns it rotates (the coefficient product
+      // reads it if sweeps follow); when the round settles the split the coefficients come from the rotations
+      // themselves and nothing else is copied
+      pair_round(spill != nullptr);
       converged = probe_check();
       norms_ready = converged;
+      if (!converged && spill != nullptr) {   // complete the copy: untouched columns still hold the original
+        MD_PAR_FOR(t, R * C) { int r = t / C, c = t - r * C; if (s.perm[c] < 0) spill[t] = X[r * LD + c]; }
+        spilled = 1;
+      }
       __syncthreads();
     }
   }
   if (!converged && try_ortho) {
+    if (pair_rounds) pair_rounds = 2;      // s.perm is about to be reused: the earlier round no longer counts as the only one
     MD_PAR_FOR(c, C) s.perm[c] = -1;       // partner of a column in an offending pair (s.perm is free in the SVD path)
     if (tid == 0) s.iscr[12] = 0;          // 1: the offending pairs do not form a matching
     __syncthreads();
@@ -1449,7 +1466,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     spilled = 1;
   }
   if (!converged && try_ortho && gram_recorded && s.iscr[12] == 0) {
-    pair_round();
+    pair_round(false);
     converged = gram_check(false);
     norms_ready = converged;
     __syncthreads();
@@ -1521,6 +1538,20 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       __syncthreads();
     }
   }
+  // One pair round and nothing else: X' = X J with J the identity plus 2x2 rotation blocks, so the coefficient
+  // matrix sigma J^T has one or two entries per row.  s.vn1[c] = J[c, c], s.wv[c] = J[partner, c] (s.perm[c] = the
+  // partner, -1 for untouched columns); step() reads them instead of forming U^T X (layout 4).
+  const int pairs_only = (converged && sweeps == 0 && pair_rounds == 1);
+  if (pairs_only) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      if (keep_a[it] >= 0 && sub == 0) {
+        const int a = keep_a[it], b = s.perm[a];
+        s.vn1[a] = keep_c[it]; s.wv[a] = -keep_s[it];
+        s.vn1[b] = keep_c[it]; s.wv[b] = keep_s[it];
+      }
+    }
+  }
   // singular values = column norms; order by value (descending), ties by column index
   if (norms_ready) {
     MD_PAR_FOR(c, C) s.sig[c] = sqrt(s.vn2[c]);   // the Gram diagonal
@@ -1557,7 +1588,8 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
   }
   if (tid == 0) {
     s.iscr[4] = sweeps + pair_round_done; s.iscr[5] = converged ? 0 : 1;
-    s.iscr[9] = (sweeps == 0 && !pair_round_done && C >= 2) ? 1 : 0;   // columns were orthogonal on entry: X is untouched
+    // 1: columns were orthogonal on entry, X is untouched; 2: one round of disjoint pair rotations settled it
+    s.iscr[9] = (sweeps == 0 && !pair_round_done && C >= 2) ? 1 : (pairs_only ? 2 : 0);
     s.cnt.n_jacobi_sweeps += sweeps + pair_round_done;
     s.cnt.flops_jacobi += 2.0 * R * C;
   }

@@ -222,7 +222,9 @@ struct Engine {
   //      out[((k*2+p')*vr + w')*Bn + b] = Min[k, c_k] sum_p W(q,w',p,p') As[(m*2+p)*Bn + b] ----
   //      The coefficient of row k is scale * s.sig[s.order[k]]; the result goes straight into s.X (ld LD), where
   //      the next split looks for it (st.in_x), so the carried matrix never leaves the SM on this path.
-  MD_DEV void apply_site_diag(double scale, int rows, int vl, int vr, int mr, int Bn, const double* As) {
+  // pairs = 0: M' = diag(sigma) in the sorted order (layout 3).  pairs = 1 (layout 4): the rows of rotated columns
+  // carry a second entry at the partner column, M'[k, c] = sigma_c J[c, c], M'[k, partner] = sigma_c J[partner, c].
+  MD_DEV void apply_site_diag(double scale, int rows, int vl, int vr, int mr, int Bn, const double* As, int pairs) {
     const int Cn = vr * Bn;
     // one 32-lane group per output row segment (k, p', w'): the index arithmetic is done once per segment and
     // the lanes run along b (coalesced reads of the staged site, conflict-free writes of X)
@@ -232,15 +234,36 @@ struct Engine {
       const int wo = (vr == 2) ? (r & 1) : 0; r = (vr == 2) ? (r >> 1) : r;
       const int pd = r & 1, k = r >> 1;
       const int c = s.order[k];
+      const int c2 = pairs ? s.perm[c] : -1;
+      const double g = scale * s.sig[c];
+      const double ga = (c2 >= 0) ? g * s.vn1[c] : g;
       const int q = (c >= mr) ? 1 : 0, m = c - q * mr;
-      const double f0 = scale * s.sig[c] * w_at(vr, q, wo, 0, pd), f1 = scale * s.sig[c] * w_at(vr, q, wo, 1, pd);
+      const double f0 = ga * w_at(vr, q, wo, 0, pd), f1 = ga * w_at(vr, q, wo, 1, pd);
       const double* a0 = As + (m * 2 + 0) * Bn;
       const double* a1 = As + (m * 2 + 1) * Bn;
       double* dst = s.X + (k * 2 + pd) * LD + wo * Bn;
-      for (int b = l; b < Bn; b += 32) dst[b] = f0 * a0[b] + f1 * a1[b];
+      if (c2 < 0) {
+        for (int b = l; b < Bn; b += 32) dst[b] = f0 * a0[b] + f1 * a1[b];
+      } else {
+        const double gb = g * s.wv[c];
+        const int q2 = (c2 >= mr) ? 1 : 0, m2 = c2 - q2 * mr;
+        const double h0 = gb * w_at(vr, q2, wo, 0, pd), h1 = gb * w_at(vr, q2, wo, 1, pd);
+        const double* b0 = As + (m2 * 2 + 0) * Bn;
+        const double* b1 = As + (m2 * 2 + 1) * Bn;
+        for (int b = l; b < Bn; b += 32) dst[b] = (f0 * a0[b] + f1 * a1[b]) + (h0 * b0[b] + h1 * b1[b]);
+      }
     }
     MD_LEADER { s.cnt.flops_apply += 4.0 * rows * 2 * Cn; st.in_x = 1; }
     MD_SYNC();
+  }
+
+  // entry (k, c) of the coefficient matrix of layouts 3 / 4 (see apply_site_diag)
+  MD_DEV double sparse_coef(int lay, int k, int c) const {
+    const int a = s.order[k];
+    const int b = (lay == 4) ? s.perm[a] : -1;
+    if (c == a) return (b >= 0) ? s.sig[a] * s.vn1[a] : s.sig[a];
+    if (b >= 0 && c == b) return s.sig[a] * s.wv[a];
+    return 0.0;
   }
 
   MD_DEV void load_x(const double* src, int R, int C) {
@@ -370,8 +393,10 @@ struct Engine {
     if (s.iscr[9]) {
       // no rotation happened: X == orig with orthogonal columns, so M' = diag(sigma) in the sorted order (the
       // off-diagonal dot products are below the check's threshold).  It is not materialised: step() reads
-      // s.sig / s.order directly (layout 3).
-      MD_LEADER { s.iscr[7] = 3; }
+      // s.sig / s.order directly (layout 3).  One round of disjoint pair rotations (s.iscr[9] == 2): M' =
+      // sigma J^T has at most two entries per row, read from s.vn1 / s.wv / s.perm (layout 4).
+      const int lay34 = (s.iscr[9] == 2) ? 4 : 3;
+      MD_LEADER { s.iscr[7] = lay34; }
     } else {
       constexpr int TK = 8;
       const int nkt = (Knew + TK - 1) / TK;
@@ -401,7 +426,7 @@ struct Engine {
   // ---- site j <- U (R = st.K*2 rows, Knew columns), frame layout (k, r, k') ----
   MD_DEV double u_at(int lay, int row, int kn, int Knew) const {
     if (lay == 2) return s.P2[row * Knew + (kn ^ q_swizzle(row, Knew))];
-    if (lay == 1 || lay == 3) return s.X[row * LD + s.order[kn]] * s.tau[kn];   // s.tau[kn] = 1 / sigma_kn
+    if (lay == 1 || lay >= 3) return s.X[row * LD + s.order[kn]] * s.tau[kn];   // s.tau[kn] = 1 / sigma_kn
     return s.X[row * LD + kn];
   }
   MD_DEV void store_u(int j, int Kl, int Knew) {
@@ -450,10 +475,11 @@ struct Engine {
     if (st.status == ST_CAPACITY) { if (pre) stage_wait(); return; }
     const int lay = s.iscr[7];
     double* coef = (lay == 2) ? s.X : s.P2;                 // coefficients M' (Knew x C, ld LD); layout 3: diagonal
-    double* stage = (lay == 2) ? (s.X + CHI * LD) : ((lay == 3) ? s.P2 : s.X);  // staging area for the next site
-    // layout 3 (orthogonal fast path): M' = diag(sigma) is not materialised; ||s|| comes from the truncation rule
-    const double dscale = (lay == 3 && renorm_sv && s.dscr[3] > 0.0) ? 1.0 / s.dscr[3] : 1.0;
-    if (renorm_sv && lay != 3) {  // mps_mpo_contract(renormalise=True): s /= ||s|| (utils.py:126-129); ||s|| = ||M'||_F
+    double* stage = (lay == 2) ? (s.X + CHI * LD) : ((lay >= 3) ? s.P2 : s.X);  // staging area for the next site
+    // layouts 3 / 4 (orthogonal or pair-rotated fast path): M' is not materialised; its rows have norm sigma_k, so
+    // ||s|| comes from the truncation rule
+    const double dscale = (lay >= 3 && renorm_sv && s.dscr[3] > 0.0) ? 1.0 / s.dscr[3] : 1.0;
+    if (renorm_sv && lay < 3) {  // mps_mpo_contract(renormalise=True): s /= ||s|| (utils.py:126-129); ||s|| = ||M'||_F
       MD_PAR_FOR(ch, 256) {
         double acc = 0.0;
         for (int t = ch; t < Knew * C; t += 256) { int k = t / C, c = t - k * C; double v = coef[k * LD + c]; acc += v * v; }
@@ -473,18 +499,18 @@ struct Engine {
     long long ts = MD_CLOCK();
     store_u(jn - 1, st.K, Knew);
     if (iso) {
-      if (!(pre && lay == 3)) stage_site(jn, stage, st.Mr, Bn);   // layout 3: already in s.P2 (prefetched)
+      if (!(pre && lay >= 3)) stage_site(jn, stage, st.Mr, Bn);   // layouts 3 / 4: already in s.P2 (prefetched)
       MD_LEADER { s.cnt.cyc_io += (double)(MD_CLOCK() - ts); }
       long long ta = MD_CLOCK();
-      if (lay == 3) apply_site_diag(dscale, Knew, vl, vr, st.Mr, Bn, stage);   // result stays in s.X (st.in_x)
+      if (lay >= 3) apply_site_diag(dscale, Knew, vl, vr, st.Mr, Bn, stage, lay == 4);   // result stays in s.X (st.in_x)
       else {
         apply_site(coef, LD, Knew, vl, vr, st.Mr, Bn, stage, st.scr0);
         MD_LEADER { st.in_x = 0; }
       }
       MD_LEADER { s.cnt.cyc_apply += (double)(MD_CLOCK() - ta); }
     } else {
-      if (lay == 3) {
-        MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; st.scr0[t] = (c == s.order[k]) ? dscale * s.sig[c] : 0.0; }
+      if (lay >= 3) {
+        MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; st.scr0[t] = dscale * sparse_coef(lay, k, c); }
       } else {
         MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; st.scr0[t] = coef[k * LD + c]; }
       }
@@ -598,10 +624,10 @@ struct Engine {
     const int Knew = factor(theta, R, C, CHI, st.P.cut_move, 1);
     if (st.status == ST_CAPACITY) return;
     int lay = s.iscr[7];
-    if (lay == 3) {
-      // orthogonal-columns fast path of the SVD modes: the coefficient matrix diag(sigma) is not materialised by
+    if (lay >= 3) {
+      // orthogonal / pair-rotated fast path of the SVD modes: the coefficient matrix is not materialised by
       // factor(); this op reads it as a matrix, so write it out (layout 1: coefficients in s.P2)
-      MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; s.P2[k * LD + c] = (c == s.order[k]) ? s.sig[c] : 0.0; }
+      MD_PAR_FOR(t, Knew * C) { int k = t / C, c = t - k * C; s.P2[k * LD + c] = sparse_coef(lay, k, c); }
       MD_LEADER { s.iscr[7] = 1; }
       MD_SYNC();
       lay = 1;
