@@ -406,6 +406,9 @@ MD_DEV void form_q(Smem<CHI>& s, int R, int K) {
 //   before(o, c) == true  <=>  column o is ranked ahead of column c
 // -------------------------------------------------------------------------------------------------
 constexpr double ORDER_TIE_REL = 1e-10;
+// probe mode: up to this many flagged columns are paired by exact dot products among themselves (above it the full
+// Gram check is the cheaper way to find the offending pairs)
+constexpr int PROBE_PAIR_MAX = 96;
 MD_HD bool canon_before(double w, int fo, int o, double v, int fc, int c) {
   if (w > v * (1.0 + ORDER_TIE_REL)) return true;
   if (v > w * (1.0 + ORDER_TIE_REL)) return false;
@@ -415,11 +418,27 @@ MD_HD bool canon_before(double w, int fo, int o, double v, int fc, int c) {
 template <int CHI>
 MD_DEV void first_rows(const Smem<CHI>& s, int R, int C, int* out) {
   constexpr int LD = Smem<CHI>::LD;
+#ifdef MDOPT_EMU
   MD_PAR_FOR(c, C) {
     int f = R;
     for (int i = 0; i < R; ++i) { if (s.X[i * LD + c] != 0.0) { f = i; break; } }
     out[c] = f;
   }
+#else
+  // four adjacent lanes per column, each scanning every fourth row without an early exit (independent loads
+  // instead of a chain of dependent ones); the minimum meets by shuffle
+  for (int t4 = threadIdx.x; t4 < 4 * (((C + 7) >> 3) << 3); t4 += blockDim.x) {
+    const int c = t4 >> 2, q = t4 & 3;
+    int f = R;
+    if (c < C) {
+#pragma unroll 8
+      for (int i = R - 4 + q; i >= 0; i -= 4) { if (s.X[i * LD + c] != 0.0) f = i; }
+    }
+    f = min(f, __shfl_xor_sync(0xffffffffu, f, 1));
+    f = min(f, __shfl_xor_sync(0xffffffffu, f, 2));
+    if (c < C && q == 0) out[c] = f;
+  }
+#endif
   MD_SYNC();
 }
 
@@ -1219,12 +1238,11 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       mxd = d;
       const double e0 = w0 - d * z0[idx], e1 = w1 - d * z1[idx];
       if (e0 * e0 > 1e-24 * d * ny0 || e1 * e1 > 1e-24 * d * ny1) bad = 1;
-      s.flag[idx] = bad;   // columns whose component of X^T X z deviates: they take part in a non-orthogonal pair
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) mxd = fmax(mxd, __shfl_xor_sync(0xffffffffu, mxd, off));
     if (lane == 0) s.rot[warp] = mxd;
-    const int any_bad = __syncthreads_or(bad);
+    __syncthreads();
     {
       double mx = 0.0;
       const double2* r2 = reinterpret_cast<const double2*>(s.rot);
@@ -1234,6 +1252,13 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       floor2 = mx * (4.0 * EPS) * (4.0 * EPS);
       if (tid == 0) s.dscr[6] = floor2;
     }
+    // a numerically zero column (rounding residue of earlier rotations, below the floor the rotations and the
+    // truncation rule ignore) has a random direction and would fail the test for ever: it does not count
+    if (qtr == 0 && idx < C) {
+      bad = bad && (s.vn2[idx] > floor2);
+      s.flag[idx] = bad;   // columns whose component of X^T X z deviates: they take part in a non-orthogonal pair
+    }
+    const int any_bad = __syncthreads_or(bad);
     if (tid == 0) s.cnt.flops_jacobi += 10.0 * R * C;
     __syncthreads();
     return !any_bad;
@@ -1339,17 +1364,28 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     // ---- Probe mode, failed probe: the columns the probe flagged are the only candidates for non-orthogonal pairs.
     // With few of them, the pairs AMONG them are tested exactly (8 lanes per pair), and if the offending ones form a
     // matching they are rotated in one round and the probe is asked again -- no Gram matrix, no sweep. ----
-    if (tid == 0) {
+    if (tid < 32) {   // warp 0 compacts the flagged columns into s.order (ascending), 32 columns per ballot
       int nf = 0;
-      for (int c = 0; c < C; ++c) if (s.flag[c]) s.order[nf++] = c;
-      s.iscr[13] = nf;
-      s.iscr[12] = 0;
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + tid;
+        const int f = (c < C) ? s.flag[c] : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (f) s.order[nf + __popc(m & ((1u << tid) - 1u))] = c;
+        nf += __popc(m);
+      }
+      if (tid == 0) { s.iscr[13] = nf; s.iscr[12] = 0; s.iscr[14] = 0; }
     }
     MD_PAR_FOR(c, C) s.perm[c] = -1;
     __syncthreads();
     const int nf = s.iscr[13];
-    want_probe_pairs = (nf >= 2 && nf <= 48);
+    want_probe_pairs = (nf >= 2 && nf <= PROBE_PAIR_MAX);
+#ifdef MD_JPROF
+    if (tid == 0) { s.cnt.flops_qr += 1.0 + 1e7 * want_probe_pairs; s.cnt.cyc_pad += nf; }
+#endif
   }
+#ifdef MD_JPROF
+  long long tpp0 = clock64();
+#endif
   // one 8-lane group: dot products of columns a, b (all lanes of the warp take part in the shuffles)
   auto pair_dots = [&](int a, int b, bool valid, double (&xa)[RPT], double (&xb)[RPT], double& saa, double& sbb,
                        double& sab) {
@@ -1380,7 +1416,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
   int keep_a[2] = {-1, -1};
   int pair_rounds = 0;
   static_assert(2 * NGRP >= N2, "a pair round visits every column in two passes of the groups");
-  auto pair_round = [&](bool save_orig) {
+  auto pair_round = [&](bool save_orig, bool write_norms) {
     int nrot_pairs = 0;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
@@ -1396,16 +1432,28 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
         const double t = copysign(beta, alpha * beta) / (fabs(alpha) + sqrt(alpha * alpha + beta * beta));
         const double c = rsqrt(1.0 + t * t);
         const double sn = c * t;
+        double na = 0.0, nb = 0.0;
 #pragma unroll
         for (int idx = 0; idx < RPT; ++idx) {
           const int r = 8 * idx + sub;
           if (r < R) {
-            X[r * LD + a] = c * xa[idx] - sn * xb[idx];
-            X[r * LD + b] = sn * xa[idx] + c * xb[idx];
+            const double ya = c * xa[idx] - sn * xb[idx], yb = sn * xa[idx] + c * xb[idx];
+            X[r * LD + a] = ya;
+            X[r * LD + b] = yb;
+            na += ya * ya; nb += yb * yb;
             if (save_orig) { spill[(size_t)r * C + a] = xa[idx]; spill[(size_t)r * C + b] = xb[idx]; }
           }
         }
         keep_c[it] = c; keep_s[it] = sn; keep_a[it] = a;
+        if (write_norms) {   // fresh squared norms of the two new columns (the 8 lanes of the group are all here)
+          const unsigned gm = 0xffu << ((tid & 31) & ~7);
+#pragma unroll
+          for (int off = 1; off < 8; off <<= 1) {
+            na += __shfl_xor_sync(gm, na, off);
+            nb += __shfl_xor_sync(gm, nb, off);
+          }
+          if (sub == 0) { s.vn2[a] = na; s.vn2[b] = nb; }
+        }
         if (sub == 0) ++nrot_pairs;
       } else if (valid && sub == 0) {
         // below the threshold on the fresh dot product: the pair stays as it is and counts as untouched
@@ -1423,6 +1471,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     for (int p = grp; p < ((nf * nf + NGRP - 1) / NGRP) * NGRP; p += NGRP) {
       const int i = p / nf, j = p - i * nf;
       const bool valid = (p < nf * nf) && (i < j);
+      if (!__any_sync(0xffffffffu, valid)) continue;   // the lower triangle: nothing to do for the whole warp
       const int a = valid ? s.order[i] : 0, b = valid ? s.order[j] : 0;
       double xa[RPT], xb[RPT];
       double saa, sbb, sab;
@@ -1432,6 +1481,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
         const int o1 = atomicCAS(&s.perm[a], -1, b);
         const int o2 = atomicCAS(&s.perm[b], -1, a);
         if ((o1 != -1 && o1 != b) || (o2 != -1 && o2 != a)) s.iscr[12] = 1;
+        atomicAdd(&s.iscr[14], 2);   // columns that found a partner
       }
     }
     const int any_found = __syncthreads_or(found);
@@ -1439,8 +1489,17 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       // the rotations change X: the round saves the original of the columns it rotates (the coefficient product
       // reads it if sweeps follow); when the round settles the split the coefficients come from the rotations
       // themselves and nothing else is copied
-      pair_round(spill != nullptr);
-      converged = probe_check();
+      //
+      // Perfect matching (every flagged column has exactly one partner, also flagged): the probe's verdict on the
+      // other columns stands -- an unflagged column is orthogonal to ALL columns within the probe's tolerance, a
+      // property rotations among other columns preserve -- and the rotated pairs are orthogonal by construction,
+      // so the round settles the split without asking the probe again; the round writes the new squared norms.
+      const bool perfect = (s.iscr[14] == nf);
+      pair_round(spill != nullptr, perfect);
+      converged = perfect ? 1 : probe_check();
+#ifdef MD_JPROF
+      if (tid == 0) s.cnt.n_qr_reflectors += 1.0 + 1e7 * converged;
+#endif
       norms_ready = converged;
       if (!converged && spill != nullptr) {   // complete the copy: untouched columns still hold the original
         MD_PAR_FOR(t, R * C) { int r = t / C, c = t - r * C; if (s.perm[c] < 0) spill[t] = X[r * LD + c]; }
@@ -1449,6 +1508,10 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       __syncthreads();
     }
   }
+#ifdef MD_JPROF
+  if (tid == 0 && probe_failed) s.cnt.cyc_formq += (double)(clock64() - tpp0);
+  if (tid == 0 && !converged && try_ortho) s.cnt.cyc_qr += 1.0;
+#endif
   if (!converged && try_ortho) {
     if (pair_rounds) pair_rounds = 2;      // s.perm is about to be reused: the earlier round no longer counts as the only one
     MD_PAR_FOR(c, C) s.perm[c] = -1;       // partner of a column in an offending pair (s.perm is free in the SVD path)
@@ -1466,7 +1529,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     spilled = 1;
   }
   if (!converged && try_ortho && gram_recorded && s.iscr[12] == 0) {
-    pair_round(false);
+    pair_round(false, false);
     converged = gram_check(false);
     norms_ready = converged;
     __syncthreads();
@@ -1538,6 +1601,9 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       __syncthreads();
     }
   }
+#ifdef MD_JPROF
+  long long tfin0 = clock64();
+#endif
   // One pair round and nothing else: X' = X J with J the identity plus 2x2 rotation blocks, so the coefficient
   // matrix sigma J^T has one or two entries per row.  s.vn1[c] = J[c, c], s.wv[c] = J[partner, c] (s.perm[c] = the
   // partner, -1 for untouched columns); step() reads them instead of forming U^T X (layout 4).
@@ -1591,6 +1657,9 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     // 1: columns were orthogonal on entry, X is untouched; 2: one round of disjoint pair rotations settled it
     s.iscr[9] = (sweeps == 0 && !pair_round_done && C >= 2) ? 1 : (pairs_only ? 2 : 0);
     s.cnt.n_jacobi_sweeps += sweeps + pair_round_done;
+#ifdef MD_JPROF
+    s.cnt.n_trunc += (double)(clock64() - tfin0);
+#endif
     s.cnt.flops_jacobi += 2.0 * R * C;
   }
   __syncthreads();

@@ -35,4 +35,6 @@ out = {"config": f"d{L}_depol_chi{chi}", "syndromes": len(both), "seconds": roun
        "cycles_per_step": {k: round(v / steps) for k, v in c.items() if k.startswith("cyc_")},
        "flops_per_step": {k: round(c[k] / steps) for k in ("flops_qr", "flops_jacobi", "flops_apply")},
        "status_not_ok": int((st != 0).sum())}
+if "--raw" in sys.argv:
+    out["raw"] = {k: float(v) for k, v in c.items()}
 print(json.dumps(out))
