@@ -677,7 +677,12 @@ MD_DEV void truncation_rule(Smem<CHI>& s, int C, int chi_lim, double cut) {
     int k = 0;
     const double sig_floor = sqrt(s.dscr[6]);
     for (int i = 0; i < C; ++i) { double v = s.sig[s.order[i]]; k += (v > cut && v > sig_floor); }
-    if (k > chi_lim) k = chi_lim;
+    if (k > chi_lim) {   // chi_max cuts into the values the cut would have kept: a truncating step
+      k = chi_lim;
+#ifndef MD_JPROF
+      s.cnt.n_trunc += 1.0;
+#endif
+    }
     double err = 0.0, kept = 0.0;
     for (int i = 0; i < C; ++i) {
       double v = s.sig[s.order[i]];
@@ -1094,7 +1099,12 @@ __device__ __forceinline__ void truncation_rule_dev(Smem<CHI>& s, int C, int chi
   int pred = 0;
   if (tid < C) { v = s.sig[s.order[tid]]; pred = (v > cut && v > sig_floor); }
   int k = __syncthreads_count(pred);
-  if (k > chi_lim) k = chi_lim;
+  if (k > chi_lim) {   // chi_max cuts into the values the cut would have kept: a truncating step
+    k = chi_lim;
+#ifndef MD_JPROF
+    if (tid == 0) s.cnt.n_trunc += 1.0;
+#endif
+  }
   double err = (tid < C && tid >= k) ? v * v : 0.0;
   double kept = (tid < C && tid < k) ? v * v : 0.0;
 #pragma unroll
@@ -1378,7 +1388,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     MD_PAR_FOR(c, C) s.perm[c] = -1;
     __syncthreads();
     const int nf = s.iscr[13];
-    want_probe_pairs = (nf >= 2 && nf <= PROBE_PAIR_MAX);
+    want_probe_pairs = (nf >= 1 && nf <= PROBE_PAIR_MAX);
 #ifdef MD_JPROF
     if (tid == 0) { s.cnt.flops_qr += 1.0 + 1e7 * want_probe_pairs; s.cnt.cyc_pad += nf; }
 #endif
@@ -1484,13 +1494,52 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
         atomicAdd(&s.iscr[14], 2);   // columns that found a partner
       }
     }
-    const int any_found = __syncthreads_or(found);
+    int any_found = __syncthreads_or(found);
+    if (s.iscr[12] == 0 && s.iscr[14] < nf) {
+      // Flagged columns without a partner among the flagged: the probe's criterion for a column is relative to that
+      // column's own norm, so the larger column of a very unequal pair can pass while the smaller one is flagged.
+      // Their partners are looked for among the unflagged columns (exact dot products again).
+      if (tid < 32) {   // warp 0: the unmatched flagged columns, compacted in place at the head of s.order
+        int nu = 0;
+        for (int i0 = 0; i0 < nf; i0 += 32) {
+          const int i = i0 + tid;
+          const int c = (i < nf) ? s.order[i] : 0;
+          const int f = (i < nf) && (s.perm[c] < 0);
+          const unsigned m = __ballot_sync(0xffffffffu, f);
+          __syncwarp();
+          if (f) s.order[nu + __popc(m & ((1u << tid) - 1u))] = c;
+          nu += __popc(m);
+          __syncwarp();
+        }
+        if (tid == 0) s.iscr[13] = nu;
+      }
+      __syncthreads();
+      const int nu = s.iscr[13];
+      int found2 = 0;
+      for (int p = grp; p < ((nu * C + NGRP - 1) / NGRP) * NGRP; p += NGRP) {
+        const int i = p / C, j = p - i * C;
+        const bool valid = (p < nu * C) && (s.flag[j] == 0);
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        const int a = valid ? s.order[i] : 0, b = valid ? j : 0;
+        double xa[RPT], xb[RPT];
+        double saa, sbb, sab;
+        pair_dots(a, b, valid, xa, xb, saa, sbb, sab);
+        if (valid && sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2 && sub == 0) {
+          found2 = 1;
+          const int o1 = atomicCAS(&s.perm[a], -1, b);
+          const int o2 = atomicCAS(&s.perm[b], -1, a);
+          if ((o1 != -1 && o1 != b) || (o2 != -1 && o2 != a)) s.iscr[12] = 1;
+          atomicAdd(&s.iscr[14], 1);   // one more flagged column with a partner
+        }
+      }
+      any_found |= __syncthreads_or(found2);
+    }
     if (any_found && s.iscr[12] == 0) {
       // the rotations change X: the round saves the original of the columns it rotates (the coefficient product
       // reads it if sweeps follow); when the round settles the split the coefficients come from the rotations
       // themselves and nothing else is copied
       //
-      // Perfect matching (every flagged column has exactly one partner, also flagged): the probe's verdict on the
+      // Perfect matching (every flagged column has exactly one partner): the probe's verdict on the
       // other columns stands -- an unflagged column is orthogonal to ALL columns within the probe's tolerance, a
       // property rotations among other columns preserve -- and the rotated pairs are orthogonal by construction,
       // so the round settles the split without asking the probe again; the round writes the new squared norms.

@@ -299,8 +299,7 @@ struct Engine {
       MD_LEADER { s.cnt.cyc_qr += (double)(MD_CLOCK() - t0); }
       Knew = s.iscr[0];
       if (s.iscr[1]) {  // more than chi_lim significant directions: genuine truncation needed
-        use_svd = 1;
-        MD_LEADER { s.cnt.n_trunc += 1.0; }
+        use_svd = 1;   // (the truncation rule counts the step as truncating)
       }
     }
     if (!use_svd) {
