@@ -85,6 +85,12 @@ __device__ __forceinline__ void md_async_copy8(double* dst_shared, const double*
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src_global) : "memory");
 }
+// one FP64 tensor-core tile product, D(8x8) += A(8x4, row) B(4x8, col)  (SASS: DMMA.8x8x4)
+__device__ __forceinline__ void md_dmma_8x8x4(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
 __device__ __forceinline__ void md_async_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 #endif
 
@@ -1396,6 +1402,38 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
 #ifdef MD_JPROF
   long long tpp0 = clock64();
 #endif
+  // Dot products between two lists of columns (la[0..na) x lb[0..nb); a null list is the identity) on the FP64
+  // tensor pipe: a warp task is one 8 x 8 tile, accumulated over the rows in steps of 4 with mma.m8n8k4.f64 (DMMA);
+  // lane l feeds A[m = l/4][k = l%4] = X[r0 + k][la[m]] and B[k][n = l/4] = X[r0 + k][lb[n]] and receives the
+  // entries (m = l/4, n = 2 (l%4) + {0, 1}).  `same` lists: only the tiles / entries above the diagonal.
+  auto tile_dots = [&](const int* la, int na, const int* lb, int nb, bool same, auto&& visit) {
+    const int lane = tid & 31, warp = tid >> 5, nwarps = (int)(blockDim.x >> 5);
+    const int nta = (na + 7) >> 3, ntb = (nb + 7) >> 3;
+    for (int t = warp; t < nta * ntb; t += nwarps) {
+      const int ti = t / ntb, tj = t - ti * ntb;
+      if (same && tj < ti) continue;   // warp-uniform
+      const int ia = min(8 * ti + (lane >> 2), na - 1), ib = min(8 * tj + (lane >> 2), nb - 1);
+      const int ca = la ? la[ia] : ia, cb = lb ? lb[ib] : ib;
+      const double* pa = X + (lane & 3) * LD + ca;
+      const double* pb = X + (lane & 3) * LD + cb;
+      double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
+      const int R8 = R & ~7;
+      for (int r0 = 0; r0 < R8; r0 += 8) {
+        const double a0 = pa[r0 * LD], b0 = pb[r0 * LD], a1 = pa[(r0 + 4) * LD], b1 = pb[(r0 + 4) * LD];
+        md_dmma_8x8x4(acc0, a0, b0);
+        md_dmma_8x8x4(acc1, a1, b1);
+      }
+      for (int r0 = R8; r0 < R; r0 += 4) {
+        const bool ok = r0 + (lane & 3) < R;
+        md_dmma_8x8x4(acc0, ok ? pa[r0 * LD] : 0.0, ok ? pb[r0 * LD] : 0.0);
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int oa = 8 * ti + (lane >> 2), ob = 8 * tj + 2 * (lane & 3) + e;
+        if (oa < na && ob < nb && (!same || ob > oa)) visit(ca, lb ? lb[ob] : ob, acc0[e] + acc1[e]);
+      }
+    }
+  };
   // one 8-lane group: dot products of columns a, b (all lanes of the warp take part in the shuffles)
   auto pair_dots = [&](int a, int b, bool valid, double (&xa)[RPT], double (&xb)[RPT], double& saa, double& sbb,
                        double& sab) {
@@ -1478,22 +1516,17 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
   if (want_probe_pairs) {
     const int nf = s.iscr[13];
     int found = 0;
-    for (int p = grp; p < ((nf * nf + NGRP - 1) / NGRP) * NGRP; p += NGRP) {
-      const int i = p / nf, j = p - i * nf;
-      const bool valid = (p < nf * nf) && (i < j);
-      if (!__any_sync(0xffffffffu, valid)) continue;   // the lower triangle: nothing to do for the whole warp
-      const int a = valid ? s.order[i] : 0, b = valid ? s.order[j] : 0;
-      double xa[RPT], xb[RPT];
-      double saa, sbb, sab;
-      pair_dots(a, b, valid, xa, xb, saa, sbb, sab);
-      if (valid && sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2 && sub == 0) {
+    // every pair of flagged columns, one 8 x 8 tile of dot products per warp task on the FP64 tensor pipe
+    tile_dots(s.order, nf, s.order, nf, true, [&](int a, int b, double sab) {
+      const double saa = s.vn2[a], sbb = s.vn2[b];   // squared norms from the probe's second pass
+      if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) {
         found = 1;
         const int o1 = atomicCAS(&s.perm[a], -1, b);
         const int o2 = atomicCAS(&s.perm[b], -1, a);
         if ((o1 != -1 && o1 != b) || (o2 != -1 && o2 != a)) s.iscr[12] = 1;
         atomicAdd(&s.iscr[14], 2);   // columns that found a partner
       }
-    }
+    });
     int any_found = __syncthreads_or(found);
     if (s.iscr[12] == 0 && s.iscr[14] < nf) {
       // Flagged columns without a partner among the flagged: the probe's criterion for a column is relative to that
@@ -1516,22 +1549,17 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       __syncthreads();
       const int nu = s.iscr[13];
       int found2 = 0;
-      for (int p = grp; p < ((nu * C + NGRP - 1) / NGRP) * NGRP; p += NGRP) {
-        const int i = p / C, j = p - i * C;
-        const bool valid = (p < nu * C) && (s.flag[j] == 0);
-        if (!__any_sync(0xffffffffu, valid)) continue;
-        const int a = valid ? s.order[i] : 0, b = valid ? j : 0;
-        double xa[RPT], xb[RPT];
-        double saa, sbb, sab;
-        pair_dots(a, b, valid, xa, xb, saa, sbb, sab);
-        if (valid && sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2 && sub == 0) {
+      tile_dots(s.order, nu, nullptr, C, false, [&](int a, int b, double sab) {
+        if (s.flag[b]) return;   // flagged x flagged pairs were all tested above
+        const double saa = s.vn2[a], sbb = s.vn2[b];
+        if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) {
           found2 = 1;
           const int o1 = atomicCAS(&s.perm[a], -1, b);
           const int o2 = atomicCAS(&s.perm[b], -1, a);
           if ((o1 != -1 && o1 != b) || (o2 != -1 && o2 != a)) s.iscr[12] = 1;
           atomicAdd(&s.iscr[14], 1);   // one more flagged column with a partner
         }
-      }
+      });
       any_found |= __syncthreads_or(found2);
     }
     if (any_found && s.iscr[12] == 0) {
