@@ -589,6 +589,26 @@ MD_DEV void jacobi_columns(Smem<CHI>& s, int R, int C, int max_sweeps = 60) {
 // Returns 1 when every component agrees to 1e-12 |x_c| |X z|; then s.sig = column norms, s.order = their ranking
 // (descending, ties by column index), s.dscr[6] = the zero-column floor, and X is untouched.
 // -------------------------------------------------------------------------------------------------
+#ifdef MDOPT_EMU
+// host emulation only: lets a test run the same decode with and without the pair rotations (tests/emu/emu.cpp)
+inline int& emu_pair_fix_off() { static int off = 0; return off; }
+#endif
+// s.vn2 (squared column norms) -> s.sig, s.order (the canonical ranking); s.iscr[4] = s.iscr[5] = 0
+template <int CHI>
+MD_DEV void rank_columns(Smem<CHI>& s, int R, int C) {
+  MD_PAR_FOR(c, C) s.sig[c] = sqrt(s.vn2[c]);
+  MD_SYNC();
+  first_rows<CHI>(s, R, C, s.flag);
+  MD_PAR_FOR(c, C) {
+    const double v = s.sig[c];
+    int pos = 0;
+    for (int o = 0; o < C; ++o) pos += canon_before(s.sig[o], s.flag[o], o, v, s.flag[c], c) ? 1 : 0;
+    s.order[pos] = c;
+  }
+  MD_LEADER { s.iscr[4] = 0; s.iscr[5] = 0; }
+  MD_SYNC();
+}
+
 MD_HD double probe_z(int c, unsigned salt) {
   unsigned h = (unsigned)c * 2654435761u + salt;
   h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
@@ -651,25 +671,159 @@ MD_DEV int ortho_probe(Smem<CHI>& s, int R, int C) {
   }
   MD_SYNC();
   MD_LEADER {
-    int bad = 0;
     double mx = 0.0;
-    for (int c = 0; c < C; ++c) { bad |= s.flag[c]; mx = fmax(mx, s.vn2[c]); }
-    s.iscr[11] = bad ? 0 : 1;
+    for (int c = 0; c < C; ++c) mx = fmax(mx, s.vn2[c]);
     s.dscr[6] = mx * (4.0 * EPS) * (4.0 * EPS);
+    // a numerically zero column (rounding residue of earlier rotations, below the floor the rotations and the
+    // truncation rule ignore) has a random direction and would fail the test for ever: it does not count
+    int bad = 0;
+    for (int c = 0; c < C; ++c) {
+      if (s.flag[c] && !(s.vn2[c] > s.dscr[6])) s.flag[c] = 0;
+      bad |= s.flag[c];
+    }
+    s.iscr[11] = bad ? 0 : 1;
     s.cnt.flops_jacobi += 10.0 * R * C;
   }
   MD_SYNC();
   if (!s.iscr[11]) return 0;
-  MD_PAR_FOR(c, C) s.sig[c] = sqrt(s.vn2[c]);   // overwrites z1, which is no longer needed
-  MD_SYNC();
-  first_rows<CHI>(s, R, C, s.flag);
-  MD_PAR_FOR(c, C) {
-    const double v = s.sig[c];
-    int pos = 0;
-    for (int o = 0; o < C; ++o) pos += canon_before(s.sig[o], s.flag[o], o, v, s.flag[c], c) ? 1 : 0;
-    s.order[pos] = c;
+  rank_columns<CHI>(s, R, C);
+  return 1;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Portable form of the probe-mode pair rotations of jacobi_columns_dev (same rule, same outputs), asked after a failed
+// ortho_probe: the flagged columns (s.flag) are the candidates; their mutual dot products, then those of the still
+// unmatched ones with the unflagged columns, are tested exactly, and when EVERY flagged column has exactly one
+// partner the disjoint pairs are rotated in one round.  Returns 1 then: X <- X J, s.sig / s.order as after the
+// sweeps, and the 2 x 2 blocks of J in s.vn1 (J[c, c]), s.wv (J[partner, c]), s.perm (partner, -1 = untouched) for
+// the two-entries-per-row coefficient matrix (layout 4 of Engine::step).  Returns 0 with X untouched otherwise.
+// No atomics: candidates are tabulated in s.part and matched by the leader, so host emulation and device agree.
+// -------------------------------------------------------------------------------------------------
+template <int CHI>
+MD_DEV int pair_fix(Smem<CHI>& s, int R, int C) {
+  constexpr int LD = Smem<CHI>::LD;
+  constexpr int NPART = Smem<CHI>::NPART;
+  double* X = s.X;
+  const double tol = EPS * sqrt((double)R);
+  const double tol2 = tol * tol;
+  const double floor2 = s.dscr[6];
+  double* G = s.part;   // offending dot products, 0 elsewhere
+  MD_LEADER {
+    int nf = 0;
+    for (int c = 0; c < C; ++c) if (s.flag[c]) s.order[nf++] = c;
+    s.iscr[13] = nf;
   }
-  MD_LEADER { s.iscr[4] = 0; s.iscr[5] = 0; }
+  MD_PAR_FOR(c, C) s.perm[c] = -1;
+  MD_SYNC();
+  const int nf = s.iscr[13];
+  if (nf < 1 || nf > PROBE_PAIR_MAX || nf * nf > NPART) return 0;
+  // flagged x flagged
+  MD_PAR_FOR(t, nf * nf) {
+    const int i = t / nf, j = t - i * nf;
+    double g = 0.0;
+    if (i < j) {
+      const int a = s.order[i], b = s.order[j];
+      double sab = 0.0;
+      for (int r = 0; r < R; ++r) sab += X[r * LD + a] * X[r * LD + b];
+      const double saa = s.vn2[a], sbb = s.vn2[b];
+      if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) g = sab;
+    }
+    G[t] = g;
+  }
+  MD_SYNC();
+  MD_LEADER {
+    int ok = 1, matched = 0;
+    for (int i = 0; i < nf && ok; ++i)
+      for (int j = i + 1; j < nf; ++j)
+        if (G[i * nf + j] != 0.0) {
+          const int a = s.order[i], b = s.order[j];
+          if (s.perm[a] != -1 || s.perm[b] != -1) { ok = 0; break; }
+          s.perm[a] = b; s.perm[b] = a;
+          s.rot[2 * a] = G[i * nf + j];   // the pair's dot product, kept for the rotation
+          matched += 2;
+        }
+    int nu = 0;
+    if (ok && matched < nf)
+      for (int i = 0; i < nf; ++i) { const int c = s.order[i]; if (s.perm[c] < 0) s.order[nu++] = c; }
+    s.iscr[12] = ok ? 0 : 1; s.iscr[14] = matched; s.iscr[13] = nu;
+    s.cnt.flops_jacobi += 1.0 * R * nf * (nf - 1);
+  }
+  MD_SYNC();
+  if (s.iscr[12]) return 0;
+  const int nu = s.iscr[13];
+  if (s.iscr[14] < nf) {
+    // the partners of the unmatched flagged columns are looked for among the unflagged ones
+    if (nu * C > NPART) return 0;
+    MD_PAR_FOR(t, nu * C) {
+      const int i = t / C, b = t - i * C;
+      double g = 0.0;
+      if (!s.flag[b]) {
+        const int a = s.order[i];
+        double sab = 0.0;
+        for (int r = 0; r < R; ++r) sab += X[r * LD + a] * X[r * LD + b];
+        const double saa = s.vn2[a], sbb = s.vn2[b];
+        if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) g = sab;
+      }
+      G[t] = g;
+    }
+    MD_SYNC();
+    MD_LEADER {
+      int ok = 1, matched = s.iscr[14];
+      for (int i = 0; i < nu && ok; ++i)
+        for (int b = 0; b < C; ++b)
+          if (G[i * C + b] != 0.0) {
+            const int a = s.order[i];
+            if (s.perm[a] != -1 || s.perm[b] != -1) { ok = 0; break; }
+            s.perm[a] = b; s.perm[b] = a;
+            s.rot[2 * (a < b ? a : b)] = G[i * C + b];
+            matched += 1;
+          }
+      s.iscr[12] = ok ? 0 : 1; s.iscr[14] = matched;
+      s.cnt.flops_jacobi += 2.0 * R * nu * C;
+    }
+    MD_SYNC();
+    if (s.iscr[12] || s.iscr[14] < nf) return 0;
+  }
+  // every flagged column has exactly one partner: rotate the pairs (a < b = s.perm[a]); s.rot[2a] = their dot product
+  MD_LEADER {
+    int np = 0;
+    for (int a = 0; a < C; ++a) {
+      const int b = s.perm[a];
+      if (b > a) {
+        const double saa = s.vn2[a], sbb = s.vn2[b], sab = s.rot[2 * a];
+        const double alpha = sbb - saa, beta = 2.0 * sab;
+        const double t = copysign(beta, alpha * beta) / (fabs(alpha) + sqrt(alpha * alpha + beta * beta));
+        const double c = 1.0 / sqrt(1.0 + t * t);
+        const double sn = c * t;
+        s.vn1[a] = c; s.wv[a] = -sn;
+        s.vn1[b] = c; s.wv[b] = sn;
+        s.order[np++] = a;
+      }
+    }
+    s.iscr[13] = np;
+    s.cnt.flops_jacobi += 12.0 * R * np;
+  }
+  MD_SYNC();
+  const int np = s.iscr[13];
+  MD_PAR_FOR(t, np * R) {
+    const int q = t / R, r = t - q * R;
+    const int a = s.order[q], b = s.perm[a];
+    const double c = s.vn1[a], sn = s.wv[b];
+    const double xa = X[r * LD + a], xb = X[r * LD + b];
+    X[r * LD + a] = c * xa - sn * xb;
+    X[r * LD + b] = sn * xa + c * xb;
+  }
+  MD_SYNC();
+  MD_PAR_FOR(t, 2 * np) {   // fresh squared norms of the rotated columns
+    const int a = s.order[t >> 1];
+    const int col = (t & 1) ? s.perm[a] : a;
+    double acc = 0.0;
+    for (int r = 0; r < R; ++r) { const double v = X[r * LD + col]; acc += v * v; }
+    s.vn2[col] = acc;
+  }
+  MD_SYNC();
+  rank_columns<CHI>(s, R, C);
+  MD_LEADER { s.iscr[4] = 1; s.cnt.n_jacobi_sweeps += 1.0; }
   MD_SYNC();
   return 1;
 }
@@ -685,9 +839,7 @@ MD_DEV void truncation_rule(Smem<CHI>& s, int C, int chi_lim, double cut) {
     for (int i = 0; i < C; ++i) { double v = s.sig[s.order[i]]; k += (v > cut && v > sig_floor); }
     if (k > chi_lim) {   // chi_max cuts into the values the cut would have kept: a truncating step
       k = chi_lim;
-#ifndef MD_JPROF
       s.cnt.n_trunc += 1.0;
-#endif
     }
     double err = 0.0, kept = 0.0;
     for (int i = 0; i < C; ++i) {
@@ -1107,9 +1259,7 @@ __device__ __forceinline__ void truncation_rule_dev(Smem<CHI>& s, int C, int chi
   int k = __syncthreads_count(pred);
   if (k > chi_lim) {   // chi_max cuts into the values the cut would have kept: a truncating step
     k = chi_lim;
-#ifndef MD_JPROF
     if (tid == 0) s.cnt.n_trunc += 1.0;
-#endif
   }
   double err = (tid < C && tid >= k) ? v * v : 0.0;
   double kept = (tid < C && tid < k) ? v * v : 0.0;
@@ -1389,19 +1539,13 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
         if (f) s.order[nf + __popc(m & ((1u << tid) - 1u))] = c;
         nf += __popc(m);
       }
-      if (tid == 0) { s.iscr[13] = nf; s.iscr[12] = 0; s.iscr[14] = 0; }
+      if (tid == 0) { s.iscr[13] = nf; s.iscr[12] = 0; s.iscr[14] = 0; s.iscr[15] = 0; }
     }
     MD_PAR_FOR(c, C) s.perm[c] = -1;
     __syncthreads();
     const int nf = s.iscr[13];
     want_probe_pairs = (nf >= 1 && nf <= PROBE_PAIR_MAX);
-#ifdef MD_JPROF
-    if (tid == 0) { s.cnt.flops_qr += 1.0 + 1e7 * want_probe_pairs; s.cnt.cyc_pad += nf; }
-#endif
   }
-#ifdef MD_JPROF
-  long long tpp0 = clock64();
-#endif
   // Dot products between two lists of columns (la[0..na) x lb[0..nb); a null list is the identity) on the FP64
   // tensor pipe: a warp task is one 8 x 8 tile, accumulated over the rows in steps of 4 with mma.m8n8k4.f64 (DMMA);
   // lane l feeds A[m = l/4][k = l%4] = X[r0 + k][la[m]] and B[k][n = l/4] = X[r0 + k][lb[n]] and receives the
@@ -1510,8 +1654,9 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     }
     pair_round_done = 1;
     ++pair_rounds;
-    if (nrot_pairs) atomicAdd(&s.cnt.flops_jacobi, 12.0 * R * nrot_pairs);
+    if (nrot_pairs) atomicAdd(&s.iscr[15], nrot_pairs);   // (a double atomicAdd on shared memory is a CAS loop)
     __syncthreads();
+    if (tid == 0) { s.cnt.flops_jacobi += 12.0 * R * s.iscr[15]; s.iscr[15] = 0; }
   };
   if (want_probe_pairs) {
     const int nf = s.iscr[13];
@@ -1574,9 +1719,6 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       const bool perfect = (s.iscr[14] == nf);
       pair_round(spill != nullptr, perfect);
       converged = perfect ? 1 : probe_check();
-#ifdef MD_JPROF
-      if (tid == 0) s.cnt.n_qr_reflectors += 1.0 + 1e7 * converged;
-#endif
       norms_ready = converged;
       if (!converged && spill != nullptr) {   // complete the copy: untouched columns still hold the original
         MD_PAR_FOR(t, R * C) { int r = t / C, c = t - r * C; if (s.perm[c] < 0) spill[t] = X[r * LD + c]; }
@@ -1585,14 +1727,10 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       __syncthreads();
     }
   }
-#ifdef MD_JPROF
-  if (tid == 0 && probe_failed) s.cnt.cyc_formq += (double)(clock64() - tpp0);
-  if (tid == 0 && !converged && try_ortho) s.cnt.cyc_qr += 1.0;
-#endif
   if (!converged && try_ortho) {
     if (pair_rounds) pair_rounds = 2;      // s.perm is about to be reused: the earlier round no longer counts as the only one
     MD_PAR_FOR(c, C) s.perm[c] = -1;       // partner of a column in an offending pair (s.perm is free in the SVD path)
-    if (tid == 0) s.iscr[12] = 0;          // 1: the offending pairs do not form a matching
+    if (tid == 0) { s.iscr[12] = 0; s.iscr[15] = 0; }   // [12] = 1: the offending pairs do not form a matching; [15]: rotations
     __syncthreads();
     converged = gram_check(true);
     gram_recorded = 1;
@@ -1678,9 +1816,6 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       __syncthreads();
     }
   }
-#ifdef MD_JPROF
-  long long tfin0 = clock64();
-#endif
   // One pair round and nothing else: X' = X J with J the identity plus 2x2 rotation blocks, so the coefficient
   // matrix sigma J^T has one or two entries per row.  s.vn1[c] = J[c, c], s.wv[c] = J[partner, c] (s.perm[c] = the
   // partner, -1 for untouched columns); step() reads them instead of forming U^T X (layout 4).
@@ -1734,9 +1869,6 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     // 1: columns were orthogonal on entry, X is untouched; 2: one round of disjoint pair rotations settled it
     s.iscr[9] = (sweeps == 0 && !pair_round_done && C >= 2) ? 1 : (pairs_only ? 2 : 0);
     s.cnt.n_jacobi_sweeps += sweeps + pair_round_done;
-#ifdef MD_JPROF
-    s.cnt.n_trunc += (double)(clock64() - tfin0);
-#endif
     s.cnt.flops_jacobi += 2.0 * R * C;
   }
   __syncthreads();

@@ -347,7 +347,15 @@ struct Engine {
     {
       // portable path (host emulation, large-chi tier): the same probe, then the sweeps if it fails
       int ortho = 0;
-      if (st.P.mode != MODE_FAST && C >= 2) ortho = ortho_probe<CHI>(s, R, C);
+      if (st.P.mode != MODE_FAST && C >= 2) {
+        ortho = ortho_probe<CHI>(s, R, C);
+        // failed on a few columns that pair up: one round of disjoint rotations settles the split (layout 4)
+#ifdef MDOPT_EMU
+        if (!ortho && !emu_pair_fix_off() && pair_fix<CHI>(s, R, C)) ortho = 2;
+#else
+        if (!ortho && pair_fix<CHI>(s, R, C)) ortho = 2;
+#endif
+      }
       MD_LEADER { s.iscr[9] = ortho; }
       if (!ortho) {
         if (x_loaded) {  // the rotations are about to change X: refresh the flat copy the coefficient product reads

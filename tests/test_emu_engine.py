@@ -159,6 +159,32 @@ def test_depolarising_bias_matches_reference(mode):
         np.testing.assert_allclose(dist, r["dist"], rtol=1e-10, atol=1e-14)
 
 
+def test_pair_rotations_agree_with_cyclic_sweeps():
+    """X+Z depolarising syndromes are the rotating splits: after a failed orthogonality probe the flagged columns pair
+    up and one round of disjoint rotations settles the split (block_ops.cuh pair_fix, layout 4 of Engine::step).  The
+    same decodes with that shortcut switched off run the cyclic Jacobi sweeps; both follow the canonical order, so
+    the marginals must agree closely, and the shortcut must actually be the one taken."""
+    g = load_golden("d3_chi64_depol")
+    kw = g["kwargs"]
+    rows = [r for r in g["results"] if "X" in r["error"] and "Z" in r["error"]][:6]
+    assert rows
+    errors = [r["error"] for r in rows]
+    args = (surface_code(3), errors, kw["chi_max"], kw["cut"], kw["bias_prob"], schedule.MODE_SVD)
+    H.lib().emu_set_pair_fix_off(1)
+    try:
+        swept = emu_decode(*args, bias_type="Depolarising")
+    finally:
+        H.lib().emu_set_pair_fix_off(0)
+    paired = emu_decode(*args, bias_type="Depolarising")
+    sweeps_off = sum(r[4][6] for r in swept)     # counters[6] = Jacobi sweeps + pair rounds
+    sweeps_on = sum(r[4][6] for r in paired)
+    print("sweeps with / without the pair rotations:", sweeps_on, sweeps_off)
+    assert sweeps_on < 0.8 * sweeps_off          # a pair round counts 1, the sweeps it replaces at least 2
+    for (d0, ok0, st0, _, _), (d1, ok1, st1, _, _) in zip(swept, paired):
+        assert st0 == 0 and st1 == 0 and ok0 == ok1
+        np.testing.assert_allclose(d1, d0, rtol=1e-8, atol=1e-13)
+
+
 def test_erasure_errors_match_reference():
     """'E' -> '++' and the reference's erased-qubit marginal (decoding.py:1341-1347), incl. erasures of qubits 0/1."""
     g = load_golden("erasure_3x3")
