@@ -627,12 +627,15 @@ MD_DEV int ortho_probe(Smem<CHI>& s, int R, int C) {
   double* pr = s.part;   // [3][4][N2] partial sums
   MD_PAR_FOR(c, C) { z0[c] = probe_z(c, 0x9E3779B9u); z1[c] = probe_z(c, 0x7F4A7C15u); }
   MD_SYNC();
-  // pass 1: y = X z; task t = (row t % N2, quarter t / N2 of the columns)
+  // pass 1: y = X z; task t = (row t % N2, quarter t / N2 of the columns -- a contiguous quarter, so that a task
+  // walking its row re-uses the 32-byte sectors it fetched when X lives in global memory)
+  const int cq = (C + 3) / 4;
   MD_PAR_FOR(t, 4 * N2) {
     const int idx = t % N2, grp = t / N2;
     double a0 = 0.0, a1 = 0.0;
     if (idx < R) {
-      for (int c = grp; c < C; c += 4) { const double x = X[idx * LD + c]; a0 += x * z0[c]; a1 += x * z1[c]; }
+      const int c1 = (grp + 1) * cq < C ? (grp + 1) * cq : C;
+      for (int c = grp * cq; c < c1; ++c) { const double x = X[idx * LD + c]; a0 += x * z0[c]; a1 += x * z1[c]; }
     }
     pr[(0 * 4 + grp) * N2 + idx] = a0;
     pr[(1 * 4 + grp) * N2 + idx] = a1;
@@ -697,17 +700,17 @@ MD_DEV int ortho_probe(Smem<CHI>& s, int R, int C) {
 // partner the disjoint pairs are rotated in one round.  Returns 1 then: X <- X J, s.sig / s.order as after the
 // sweeps, and the 2 x 2 blocks of J in s.vn1 (J[c, c]), s.wv (J[partner, c]), s.perm (partner, -1 = untouched) for
 // the two-entries-per-row coefficient matrix (layout 4 of Engine::step).  Returns 0 with X untouched otherwise.
-// No atomics: candidates are tabulated in s.part and matched by the leader, so host emulation and device agree.
+// No atomics: candidates are tabulated in s.P2 and matched by the leader, so host emulation and device agree.
 // -------------------------------------------------------------------------------------------------
 template <int CHI>
 MD_DEV int pair_fix(Smem<CHI>& s, int R, int C) {
   constexpr int LD = Smem<CHI>::LD;
-  constexpr int NPART = Smem<CHI>::NPART;
+  constexpr int N2 = Smem<CHI>::N2;
   double* X = s.X;
   const double tol = EPS * sqrt((double)R);
   const double tol2 = tol * tol;
   const double floor2 = s.dscr[6];
-  double* G = s.part;   // offending dot products, 0 elsewhere
+  int* cand = s.order + N2;  // cand[-1 - i]: partner of flagged column i (-1 none yet, -2 several); the list sits at the head
   MD_LEADER {
     int nf = 0;
     for (int c = 0; c < C; ++c) if (s.flag[c]) s.order[nf++] = c;
@@ -716,74 +719,74 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C) {
   MD_PAR_FOR(c, C) s.perm[c] = -1;
   MD_SYNC();
   const int nf = s.iscr[13];
-  if (nf < 1 || nf > PROBE_PAIR_MAX || nf * nf > NPART) return 0;
-  // flagged x flagged
+  if (nf < 1 || 2 * nf > N2) return 0;
+  // tables of offending dot products (0 elsewhere) in s.P2, which is free during a split on this path and holds
+  // CHI * LD doubles: nf * nf <= N2^2 / 4 and nf * C <= N2^2 / 2 both fit; G1 is dead once its rows are scanned
+  double* G1 = s.P2;   // nf x nf: flagged x flagged
+  double* G2 = s.P2;   // nf x C : rows of the flagged columns still without a partner x unflagged columns
+  static_assert((size_t)(N2 / 2) * N2 <= (size_t)CHI * LD, "pair tables fit the coefficient store");
   MD_PAR_FOR(t, nf * nf) {
     const int i = t / nf, j = t - i * nf;
     double g = 0.0;
-    if (i < j) {
-      const int a = s.order[i], b = s.order[j];
+    if (i != j) {
+      const int a = s.order[i], c = s.order[j];
       double sab = 0.0;
-      for (int r = 0; r < R; ++r) sab += X[r * LD + a] * X[r * LD + b];
-      const double saa = s.vn2[a], sbb = s.vn2[b];
-      if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) g = sab;
+      for (int r = 0; r < R; ++r) sab += X[r * LD + a] * X[r * LD + c];
+      const double saa = s.vn2[a], scc = s.vn2[c];
+      if (sab != 0.0 && sab * sab > tol2 * saa * scc && saa > floor2 && scc > floor2) g = sab;
     }
-    G[t] = g;
+    G1[t] = g;
+  }
+  MD_LEADER { s.cnt.flops_jacobi += 2.0 * R * nf * nf; }
+  MD_SYNC();
+  MD_PAR_FOR(i, nf) {
+    int cnt = 0, b = -1;
+    for (int j = 0; j < nf; ++j) if (G1[i * nf + j] != 0.0) { ++cnt; b = j; }
+    cand[-1 - i] = (cnt == 0) ? -1 : ((cnt == 1) ? s.order[b] : -2);
+    if (cnt == 1) s.tau[s.order[i]] = G1[i * nf + b];   // the pair's dot product, kept for the rotation
   }
   MD_SYNC();
+  // Flagged columns without a partner among the flagged: the probe's criterion for a column is relative to that
+  // column's own norm, so the larger column of a very unequal pair can pass while the smaller one is flagged.  Their
+  // partners are looked for among the unflagged columns; consecutive tasks walk consecutive columns c (coalesced when
+  // X lives in global memory), the flagged column is the same for a run of tasks (broadcast).
+  MD_PAR_FOR(t, nf * C) {
+    const int i = t / C, c = t - i * C;
+    if (cand[-1 - i] == -1) {
+      double g = 0.0;
+      if (!s.flag[c]) {
+        const int a = s.order[i];
+        double sab = 0.0;
+        for (int r = 0; r < R; ++r) sab += X[r * LD + a] * X[r * LD + c];
+        const double saa = s.vn2[a], scc = s.vn2[c];
+        if (sab != 0.0 && sab * sab > tol2 * saa * scc && saa > floor2 && scc > floor2) g = sab;
+      }
+      G2[t] = g;
+    }
+  }
+  MD_SYNC();
+  MD_PAR_FOR(i, nf) {
+    if (cand[-1 - i] == -1) {
+      int cnt = 0, b = -1;
+      for (int c = 0; c < C; ++c) if (G2[i * C + c] != 0.0) { ++cnt; b = c; }
+      cand[-1 - i] = (cnt == 0) ? -1 : ((cnt == 1) ? b : -2);
+      if (cnt == 1) s.tau[s.order[i]] = G2[i * C + b];
+    }
+  }
+  MD_SYNC();
+  // every flagged column must have exactly one partner, and the pairs must be disjoint
   MD_LEADER {
-    int ok = 1, matched = 0;
-    for (int i = 0; i < nf && ok; ++i)
-      for (int j = i + 1; j < nf; ++j)
-        if (G[i * nf + j] != 0.0) {
-          const int a = s.order[i], b = s.order[j];
-          if (s.perm[a] != -1 || s.perm[b] != -1) { ok = 0; break; }
-          s.perm[a] = b; s.perm[b] = a;
-          s.rot[2 * a] = G[i * nf + j];   // the pair's dot product, kept for the rotation
-          matched += 2;
-        }
-    int nu = 0;
-    if (ok && matched < nf)
-      for (int i = 0; i < nf; ++i) { const int c = s.order[i]; if (s.perm[c] < 0) s.order[nu++] = c; }
-    s.iscr[12] = ok ? 0 : 1; s.iscr[14] = matched; s.iscr[13] = nu;
-    s.cnt.flops_jacobi += 1.0 * R * nf * (nf - 1);
+    int ok = 1;
+    for (int i = 0; i < nf && ok; ++i) {
+      const int a = s.order[i], b = cand[-1 - i];
+      if (b < 0) ok = 0;
+      else if (s.perm[a] == -1 && s.perm[b] == -1) { s.perm[a] = b; s.perm[b] = a; s.rot[2 * (a < b ? a : b)] = s.tau[a]; }
+      else if (!(s.perm[a] == b && s.perm[b] == a)) ok = 0;
+    }
+    s.iscr[12] = ok ? 0 : 1;
   }
   MD_SYNC();
   if (s.iscr[12]) return 0;
-  const int nu = s.iscr[13];
-  if (s.iscr[14] < nf) {
-    // the partners of the unmatched flagged columns are looked for among the unflagged ones
-    if (nu * C > NPART) return 0;
-    MD_PAR_FOR(t, nu * C) {
-      const int i = t / C, b = t - i * C;
-      double g = 0.0;
-      if (!s.flag[b]) {
-        const int a = s.order[i];
-        double sab = 0.0;
-        for (int r = 0; r < R; ++r) sab += X[r * LD + a] * X[r * LD + b];
-        const double saa = s.vn2[a], sbb = s.vn2[b];
-        if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) g = sab;
-      }
-      G[t] = g;
-    }
-    MD_SYNC();
-    MD_LEADER {
-      int ok = 1, matched = s.iscr[14];
-      for (int i = 0; i < nu && ok; ++i)
-        for (int b = 0; b < C; ++b)
-          if (G[i * C + b] != 0.0) {
-            const int a = s.order[i];
-            if (s.perm[a] != -1 || s.perm[b] != -1) { ok = 0; break; }
-            s.perm[a] = b; s.perm[b] = a;
-            s.rot[2 * (a < b ? a : b)] = G[i * C + b];
-            matched += 1;
-          }
-      s.iscr[12] = ok ? 0 : 1; s.iscr[14] = matched;
-      s.cnt.flops_jacobi += 2.0 * R * nu * C;
-    }
-    MD_SYNC();
-    if (s.iscr[12] || s.iscr[14] < nf) return 0;
-  }
   // every flagged column has exactly one partner: rotate the pairs (a < b = s.perm[a]); s.rot[2a] = their dot product
   MD_LEADER {
     int np = 0;

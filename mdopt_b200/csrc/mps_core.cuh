@@ -347,8 +347,14 @@ struct Engine {
     {
       // portable path (host emulation, large-chi tier): the same probe, then the sweeps if it fails
       int ortho = 0;
+#ifdef MD_JPROF
+      long long tq0 = MD_CLOCK(), tq1 = tq0, tq2 = tq0;
+#endif
       if (st.P.mode != MODE_FAST && C >= 2) {
         ortho = ortho_probe<CHI>(s, R, C);
+#ifdef MD_JPROF
+        tq1 = MD_CLOCK();
+#endif
         // failed on a few columns that pair up: one round of disjoint rotations settles the split (layout 4)
 #ifdef MDOPT_EMU
         if (!ortho && !emu_pair_fix_off() && pair_fix<CHI>(s, R, C)) ortho = 2;
@@ -356,6 +362,10 @@ struct Engine {
         if (!ortho && pair_fix<CHI>(s, R, C)) ortho = 2;
 #endif
       }
+#ifdef MD_JPROF
+      tq2 = MD_CLOCK();
+      MD_LEADER { s.cnt.cyc_qr += (double)(tq1 - tq0); s.cnt.cyc_formq += (double)(tq2 - tq1); if (!ortho) s.cnt.n_qr_reflectors += 1.0; }
+#endif
       MD_LEADER { s.iscr[9] = ortho; }
       if (!ortho) {
         if (x_loaded) {  // the rotations are about to change X: refresh the flat copy the coefficient product reads
@@ -363,6 +373,9 @@ struct Engine {
           MD_SYNC();
         }
         jacobi_columns<CHI>(s, R, C);
+#ifdef MD_JPROF
+        MD_LEADER { s.cnt.cyc_pad += (double)(MD_CLOCK() - tq2); }
+#endif
       }
       MD_SYNC();
     }
