@@ -700,17 +700,23 @@ MD_DEV int ortho_probe(Smem<CHI>& s, int R, int C) {
 // partner the disjoint pairs are rotated in one round.  Returns 1 then: X <- X J, s.sig / s.order as after the
 // sweeps, and the 2 x 2 blocks of J in s.vn1 (J[c, c]), s.wv (J[partner, c]), s.perm (partner, -1 = untouched) for
 // the two-entries-per-row coefficient matrix (layout 4 of Engine::step).  Returns 0 with X untouched otherwise.
-// No atomics: candidates are tabulated in s.P2 and matched by the leader, so host emulation and device agree.
+// greedy = 1 (the step before the cyclic sweeps, X already saved by the caller): columns with several partners take
+// the one with the largest cosine, whatever disjoint pairs result are rotated, and the caller asks the probe again
+// -- classical Jacobi restricted to the offending pairs instead of C - 1 rounds over all of them.
+// No atomics: candidates are tabulated in `table` and matched by the leader, so host emulation and device agree.
 // -------------------------------------------------------------------------------------------------
 template <int CHI>
-MD_DEV int pair_fix(Smem<CHI>& s, int R, int C) {
+MD_DEV int pair_fix(Smem<CHI>& s, int R, int C, double* table, int greedy = 0) {
   constexpr int LD = Smem<CHI>::LD;
   constexpr int N2 = Smem<CHI>::N2;
   double* X = s.X;
   const double tol = EPS * sqrt((double)R);
   const double tol2 = tol * tol;
   const double floor2 = s.dscr[6];
-  int* cand = s.order + N2;  // cand[-1 - i]: partner of flagged column i (-1 none yet, -2 several); the list sits at the head
+  // cand[-1 - i]: partner of flagged column i (-1 none yet, -2 several), in the tail of s.part viewed as ints (the
+  // probe's partial sums are dead by now)
+  static_assert(2 * Smem<CHI>::NPART >= N2, "one int per column fits s.part");
+  int* cand = reinterpret_cast<int*>(s.part) + N2;
   MD_LEADER {
     int nf = 0;
     for (int c = 0; c < C; ++c) if (s.flag[c]) s.order[nf++] = c;
@@ -719,12 +725,11 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C) {
   MD_PAR_FOR(c, C) s.perm[c] = -1;
   MD_SYNC();
   const int nf = s.iscr[13];
-  if (nf < 1 || 2 * nf > N2) return 0;
-  // tables of offending dot products (0 elsewhere) in s.P2, which is free during a split on this path and holds
-  // CHI * LD doubles: nf * nf <= N2^2 / 4 and nf * C <= N2^2 / 2 both fit; G1 is dead once its rows are scanned
-  double* G1 = s.P2;   // nf x nf: flagged x flagged
-  double* G2 = s.P2;   // nf x C : rows of the flagged columns still without a partner x unflagged columns
-  static_assert((size_t)(N2 / 2) * N2 <= (size_t)CHI * LD, "pair tables fit the coefficient store");
+  if (nf < 1) return 0;
+  // tables of offending dot products (0 elsewhere) in `table` (N2 * N2 doubles: the flat scratch matrix the split
+  // does not read); G1 is dead once its rows are scanned
+  double* G1 = table;   // nf x nf: flagged x flagged
+  double* G2 = table;   // nf x C : rows of the flagged columns still without a partner x unflagged columns
   MD_PAR_FOR(t, nf * nf) {
     const int i = t / nf, j = t - i * nf;
     double g = 0.0;
@@ -741,9 +746,17 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C) {
   MD_SYNC();
   MD_PAR_FOR(i, nf) {
     int cnt = 0, b = -1;
-    for (int j = 0; j < nf; ++j) if (G1[i * nf + j] != 0.0) { ++cnt; b = j; }
-    cand[-1 - i] = (cnt == 0) ? -1 : ((cnt == 1) ? s.order[b] : -2);
-    if (cnt == 1) s.tau[s.order[i]] = G1[i * nf + b];   // the pair's dot product, kept for the rotation
+    double best = 0.0;
+    for (int j = 0; j < nf; ++j) {
+      const double g = G1[i * nf + j];
+      if (g != 0.0) {
+        ++cnt;
+        const double w = g * g / s.vn2[s.order[j]];   // greedy: the partner with the largest cosine
+        if (!greedy || w > best) { best = w; b = j; }
+      }
+    }
+    cand[-1 - i] = (cnt == 0) ? -1 : ((cnt == 1 || greedy) ? s.order[b] : -2);
+    if (cnt == 1 || (greedy && cnt > 0)) s.tau[s.order[i]] = G1[i * nf + b];   // the pair's dot product, kept for the rotation
   }
   MD_SYNC();
   // Flagged columns without a partner among the flagged: the probe's criterion for a column is relative to that
@@ -768,22 +781,33 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C) {
   MD_PAR_FOR(i, nf) {
     if (cand[-1 - i] == -1) {
       int cnt = 0, b = -1;
-      for (int c = 0; c < C; ++c) if (G2[i * C + c] != 0.0) { ++cnt; b = c; }
-      cand[-1 - i] = (cnt == 0) ? -1 : ((cnt == 1) ? b : -2);
-      if (cnt == 1) s.tau[s.order[i]] = G2[i * C + b];
+      double best = 0.0;
+      for (int c = 0; c < C; ++c) {
+        const double g = G2[i * C + c];
+        if (g != 0.0) {
+          ++cnt;
+          const double w = g * g / s.vn2[c];
+          if (!greedy || w > best) { best = w; b = c; }
+        }
+      }
+      cand[-1 - i] = (cnt == 0) ? -1 : ((cnt == 1 || greedy) ? b : -2);
+      if (cnt == 1 || (greedy && cnt > 0)) s.tau[s.order[i]] = G2[i * C + b];
     }
   }
   MD_SYNC();
   // every flagged column must have exactly one partner, and the pairs must be disjoint
+  // (greedy: whatever disjoint pairs the flagged columns' best partners form, at least one)
   MD_LEADER {
-    int ok = 1;
+    int ok = 1, np = 0;
     for (int i = 0; i < nf && ok; ++i) {
       const int a = s.order[i], b = cand[-1 - i];
-      if (b < 0) ok = 0;
-      else if (s.perm[a] == -1 && s.perm[b] == -1) { s.perm[a] = b; s.perm[b] = a; s.rot[2 * (a < b ? a : b)] = s.tau[a]; }
-      else if (!(s.perm[a] == b && s.perm[b] == a)) ok = 0;
+      if (b < 0) ok = greedy;
+      else if (s.perm[a] == -1 && s.perm[b] == -1) {
+        s.perm[a] = b; s.perm[b] = a; s.rot[2 * (a < b ? a : b)] = s.tau[a];
+        ++np;
+      } else if (!(s.perm[a] == b && s.perm[b] == a)) ok = greedy;
     }
-    s.iscr[12] = ok ? 0 : 1;
+    s.iscr[12] = (ok && np > 0) ? 0 : 1;
   }
   MD_SYNC();
   if (s.iscr[12]) return 0;
@@ -825,8 +849,10 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C) {
     s.vn2[col] = acc;
   }
   MD_SYNC();
+  MD_LEADER { s.cnt.n_jacobi_sweeps += 1.0; }
+  if (greedy) { MD_SYNC(); return 1; }   // the caller asks the probe again
   rank_columns<CHI>(s, R, C);
-  MD_LEADER { s.iscr[4] = 1; s.cnt.n_jacobi_sweeps += 1.0; }
+  MD_LEADER { s.iscr[4] = 1; }
   MD_SYNC();
   return 1;
 }

@@ -347,6 +347,8 @@ struct Engine {
     {
       // portable path (host emulation, large-chi tier): the same probe, then the sweeps if it fails
       int ortho = 0;
+      // N2 x N2 doubles the split does not read: the flat scratch matrix that is not `orig`
+      double* pair_table = (orig == st.scr1) ? st.scr0 : st.scr1;
 #ifdef MD_JPROF
       long long tq0 = MD_CLOCK(), tq1 = tq0, tq2 = tq0;
 #endif
@@ -357,9 +359,9 @@ struct Engine {
 #endif
         // failed on a few columns that pair up: one round of disjoint rotations settles the split (layout 4)
 #ifdef MDOPT_EMU
-        if (!ortho && !emu_pair_fix_off() && pair_fix<CHI>(s, R, C)) ortho = 2;
+        if (!ortho && !emu_pair_fix_off() && pair_fix<CHI>(s, R, C, pair_table)) ortho = 2;
 #else
-        if (!ortho && pair_fix<CHI>(s, R, C)) ortho = 2;
+        if (!ortho && pair_fix<CHI>(s, R, C, pair_table)) ortho = 2;
 #endif
       }
 #ifdef MD_JPROF
@@ -372,7 +374,18 @@ struct Engine {
           MD_PAR_FOR(t, R * C) { int r = t / C, c = t - r * C; st.scr0[t] = s.X[r * LD + c]; }
           MD_SYNC();
         }
-        jacobi_columns<CHI>(s, R, C);
+        // a few rounds of rotations restricted to the offending pairs, each followed by the probe; the cyclic sweeps
+        // (C - 1 rounds over every pair, at least twice) only if that does not settle
+        int settled = 0;
+        int rounds = (st.P.mode != MODE_FAST && C >= 2) ? 12 : 0;   // the probe ran: s.flag holds its verdict per column
+#ifdef MDOPT_EMU
+        if (emu_pair_fix_off() == 1) rounds = 0;   // 2: only the single-round shortcut is off, so every rotating split comes here
+#endif
+        for (int it = 0; it < rounds && !settled; ++it) {
+          if (!pair_fix<CHI>(s, R, C, pair_table, 1)) break;
+          settled = ortho_probe<CHI>(s, R, C);
+        }
+        if (!settled) jacobi_columns<CHI>(s, R, C);
 #ifdef MD_JPROF
         MD_LEADER { s.cnt.cyc_pad += (double)(MD_CLOCK() - tq2); }
 #endif

@@ -175,7 +175,8 @@ int program_impl(const mdopt_decode_desc* d, const int32_t* program, const doubl
 }  // namespace
 
 extern "C" {
-// test switch: 1 = skip the pair rotations after a failed probe (every rotating split runs the cyclic sweeps)
+// test switch: 1 = skip the pair rotations after a failed probe (every rotating split runs the cyclic sweeps);
+// 2 = skip only the single-round shortcut (every rotating split runs the greedy rounds, each followed by the probe)
 void emu_set_pair_fix_off(int off) { mdopt::emu_pair_fix_off() = off; }
 int emu_decode_batch(const mdopt_decode_desc* d, int chi_cap, const int32_t* program, const double* wtab,
                      const int32_t* wdim, const uint8_t* symbols, int batch, double* dist, int32_t* success,

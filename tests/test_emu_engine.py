@@ -175,7 +175,15 @@ def test_pair_rotations_agree_with_cyclic_sweeps():
         swept = emu_decode(*args, bias_type="Depolarising")
     finally:
         H.lib().emu_set_pair_fix_off(0)
+    H.lib().emu_set_pair_fix_off(2)   # no single-round shortcut: greedy rounds, each followed by the probe
+    try:
+        greedy = emu_decode(*args, bias_type="Depolarising")
+    finally:
+        H.lib().emu_set_pair_fix_off(0)
     paired = emu_decode(*args, bias_type="Depolarising")
+    for (d0, ok0, st0, _, _), (d2, ok2, st2, _, _) in zip(swept, greedy):
+        assert st2 == 0 and ok0 == ok2
+        np.testing.assert_allclose(d2, d0, rtol=1e-8, atol=1e-13)
     sweeps_off = sum(r[4][6] for r in swept)     # counters[6] = Jacobi sweeps + pair rounds
     sweeps_on = sum(r[4][6] for r in paired)
     print("sweeps with / without the pair rotations:", sweeps_on, sweeps_off)
