@@ -418,7 +418,11 @@ def run_ours(args):
         value = total * args.steps / (total_ms * 1e-3)
         e2e_value = total * args.steps / float(t_e2e.item())
         kernel_s = (sum(step_ms) / args.steps) * 1e-3
-        kernel = "mono_decode_kernel<64>" if mono else "decode_kernel<64>"
+        # chi = 64 launches the lock-step variant (28 warps per CTA) unless MDOPT_MONO_LOCKSTEP=0 selects the
+        # free-running one-warp CTAs (mono_kernels.cuh launch_mono_decode)
+        lockstep = os.environ.get("MDOPT_MONO_LOCKSTEP", "28")
+        mono_kernel = "mono_decode_kernel<64>" if lockstep == "0" else f"mono_decode_lockstep_kernel<64, {lockstep}>"
+        kernel = mono_kernel if mono else "decode_kernel<64>"
         hbm_peak, hbm_src = hbm_peak_gbs()
         if mono:
             achieved_gbs = counters["bytes"] / kernel_s / 1e9

@@ -412,9 +412,6 @@ MD_DEV void form_q(Smem<CHI>& s, int R, int K) {
 //   before(o, c) == true  <=>  column o is ranked ahead of column c
 // -------------------------------------------------------------------------------------------------
 constexpr double ORDER_TIE_REL = 1e-10;
-// probe mode: up to this many flagged columns are paired by exact dot products among themselves (above it the full
-// Gram check is the cheaper way to find the offending pairs)
-constexpr int PROBE_PAIR_MAX = 96;
 MD_HD bool canon_before(double w, int fo, int o, double v, int fc, int c) {
   if (w > v * (1.0 + ORDER_TIE_REL)) return true;
   if (v > w * (1.0 + ORDER_TIE_REL)) return false;
@@ -1573,7 +1570,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
     MD_PAR_FOR(c, C) s.perm[c] = -1;
     __syncthreads();
     const int nf = s.iscr[13];
-    want_probe_pairs = (nf >= 1 && nf <= PROBE_PAIR_MAX);
+    want_probe_pairs = (nf >= 1);   // any number of flagged columns: the dense-looking splits are perfect matchings too
   }
   // Dot products between two lists of columns (la[0..na) x lb[0..nb); a null list is the identity) on the FP64
   // tensor pipe: a warp task is one 8 x 8 tile, accumulated over the rows in steps of 4 with mma.m8n8k4.f64 (DMMA);
