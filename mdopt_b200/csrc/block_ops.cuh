@@ -596,12 +596,19 @@ MD_DEV void rank_columns(Smem<CHI>& s, int R, int C) {
   MD_PAR_FOR(c, C) s.sig[c] = sqrt(s.vn2[c]);
   MD_SYNC();
   first_rows<CHI>(s, R, C, s.flag);
-  MD_PAR_FOR(c, C) {
+  // four tasks per column, each ranking it against a quarter of the others; the partial ranks meet in s.part (ints)
+  constexpr int N2 = Smem<CHI>::N2;
+  int* ipart = reinterpret_cast<int*>(s.part);
+  MD_PAR_FOR(t, 4 * C) {
+    const int c = t % C, q = t / C;
     const double v = s.sig[c];
+    const int fc = s.flag[c];
     int pos = 0;
-    for (int o = 0; o < C; ++o) pos += canon_before(s.sig[o], s.flag[o], o, v, s.flag[c], c) ? 1 : 0;
-    s.order[pos] = c;
+    for (int o = q; o < C; o += 4) pos += canon_before(s.sig[o], s.flag[o], o, v, fc, c) ? 1 : 0;
+    ipart[q * N2 + c] = pos;
   }
+  MD_SYNC();
+  MD_PAR_FOR(c, C) s.order[(ipart[c] + ipart[N2 + c]) + (ipart[2 * N2 + c] + ipart[3 * N2 + c])] = c;
   MD_LEADER { s.iscr[4] = 0; s.iscr[5] = 0; }
   MD_SYNC();
 }
@@ -643,9 +650,15 @@ MD_DEV int ortho_probe(Smem<CHI>& s, int R, int C) {
     y1[r] = (pr[4 * N2 + r] + pr[5 * N2 + r]) + (pr[6 * N2 + r] + pr[7 * N2 + r]);
   }
   MD_SYNC();
+  MD_PAR_FOR(k, 16) {   // |y|^2 in 16 interleaved partial sums (s.rot holds 2 N2 >= 32 doubles) (s.rot), then the leader
+    double n0 = 0.0, n1 = 0.0;
+    for (int r = k; r < R; r += 16) { n0 += y0[r] * y0[r]; n1 += y1[r] * y1[r]; }
+    s.rot[k] = n0; s.rot[16 + k] = n1;
+  }
+  MD_SYNC();
   MD_LEADER {
     double n0 = 0.0, n1 = 0.0;
-    for (int r = 0; r < R; ++r) { n0 += y0[r] * y0[r]; n1 += y1[r] * y1[r]; }
+    for (int k = 0; k < 16; ++k) { n0 += s.rot[k]; n1 += s.rot[16 + k]; }
     s.dscr[8] = n0; s.dscr[9] = n1;
   }
   // pass 2: w = X^T y and the squared column norms; task t = (column t % N2, quarter t / N2 of the rows)
@@ -670,24 +683,54 @@ MD_DEV int ortho_probe(Smem<CHI>& s, int R, int C) {
     s.flag[c] = (e0 * e0 > 1e-24 * d * ny0 || e1 * e1 > 1e-24 * d * ny1) ? 1 : 0;
   }
   MD_SYNC();
+  MD_PAR_FOR(k, 16) {
+    double mx = 0.0;
+    for (int c = k; c < C; c += 16) mx = fmax(mx, s.vn2[c]);
+    s.rot[k] = mx;
+  }
+  MD_SYNC();
   MD_LEADER {
     double mx = 0.0;
-    for (int c = 0; c < C; ++c) mx = fmax(mx, s.vn2[c]);
+    for (int k = 0; k < 16; ++k) mx = fmax(mx, s.rot[k]);
     s.dscr[6] = mx * (4.0 * EPS) * (4.0 * EPS);
-    // a numerically zero column (rounding residue of earlier rotations, below the floor the rotations and the
-    // truncation rule ignore) has a random direction and would fail the test for ever: it does not count
+    s.cnt.flops_jacobi += 10.0 * R * C;
+  }
+  MD_SYNC();
+  // a numerically zero column (rounding residue of earlier rotations, below the floor the rotations and the
+  // truncation rule ignore) has a random direction and would fail the test for ever: it does not count
+  MD_PAR_FOR(k, 16) {
     int bad = 0;
-    for (int c = 0; c < C; ++c) {
+    for (int c = k; c < C; c += 16) {
       if (s.flag[c] && !(s.vn2[c] > s.dscr[6])) s.flag[c] = 0;
       bad |= s.flag[c];
     }
+    s.rot[16 + k] = bad ? 1.0 : 0.0;
+  }
+  MD_SYNC();
+  MD_LEADER {
+    int bad = 0;
+    for (int k = 0; k < 16; ++k) bad |= (s.rot[16 + k] != 0.0);
     s.iscr[11] = bad ? 0 : 1;
-    s.cnt.flops_jacobi += 10.0 * R * C;
   }
   MD_SYNC();
   if (!s.iscr[11]) return 0;
   rank_columns<CHI>(s, R, C);
   return 1;
+}
+
+// dot product of two strided vectors of length R: four independent partial sums, so that the loads of a matrix in
+// global memory are in flight together instead of one per dependent FMA
+MD_HD double dot4(const double* pa, int sa, const double* pc, int sc, int R) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int r = 0;
+  for (; r + 3 < R; r += 4) {
+    s0 += pa[(r + 0) * sa] * pc[(r + 0) * sc];
+    s1 += pa[(r + 1) * sa] * pc[(r + 1) * sc];
+    s2 += pa[(r + 2) * sa] * pc[(r + 2) * sc];
+    s3 += pa[(r + 3) * sa] * pc[(r + 3) * sc];
+  }
+  for (; r < R; ++r) s0 += pa[r * sa] * pc[r * sc];
+  return (s0 + s1) + (s2 + s3);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -732,8 +775,7 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C, double* table, int greedy = 0) {
     double g = 0.0;
     if (i != j) {
       const int a = s.order[i], c = s.order[j];
-      double sab = 0.0;
-      for (int r = 0; r < R; ++r) sab += X[r * LD + a] * X[r * LD + c];
+      const double sab = dot4(X + a, LD, X + c, LD, R);
       const double saa = s.vn2[a], scc = s.vn2[c];
       if (sab != 0.0 && sab * sab > tol2 * saa * scc && saa > floor2 && scc > floor2) g = sab;
     }
@@ -766,8 +808,7 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C, double* table, int greedy = 0) {
       double g = 0.0;
       if (!s.flag[c]) {
         const int a = s.order[i];
-        double sab = 0.0;
-        for (int r = 0; r < R; ++r) sab += X[r * LD + a] * X[r * LD + c];
+        const double sab = dot4(X + a, LD, X + c, LD, R);
         const double saa = s.vn2[a], scc = s.vn2[c];
         if (sab != 0.0 && sab * sab > tol2 * saa * scc && saa > floor2 && scc > floor2) g = sab;
       }
@@ -809,21 +850,21 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C, double* table, int greedy = 0) {
   MD_SYNC();
   if (s.iscr[12]) return 0;
   // every flagged column has exactly one partner: rotate the pairs (a < b = s.perm[a]); s.rot[2a] = their dot product
+  MD_PAR_FOR(a, C) {
+    const int b = s.perm[a];
+    if (b > a) {
+      const double saa = s.vn2[a], sbb = s.vn2[b], sab = s.rot[2 * a];
+      const double alpha = sbb - saa, beta = 2.0 * sab;
+      const double t = copysign(beta, alpha * beta) / (fabs(alpha) + sqrt(alpha * alpha + beta * beta));
+      const double c = 1.0 / sqrt(1.0 + t * t);
+      const double sn = c * t;
+      s.vn1[a] = c; s.wv[a] = -sn;
+      s.vn1[b] = c; s.wv[b] = sn;
+    }
+  }
   MD_LEADER {
     int np = 0;
-    for (int a = 0; a < C; ++a) {
-      const int b = s.perm[a];
-      if (b > a) {
-        const double saa = s.vn2[a], sbb = s.vn2[b], sab = s.rot[2 * a];
-        const double alpha = sbb - saa, beta = 2.0 * sab;
-        const double t = copysign(beta, alpha * beta) / (fabs(alpha) + sqrt(alpha * alpha + beta * beta));
-        const double c = 1.0 / sqrt(1.0 + t * t);
-        const double sn = c * t;
-        s.vn1[a] = c; s.wv[a] = -sn;
-        s.vn1[b] = c; s.wv[b] = sn;
-        s.order[np++] = a;
-      }
-    }
+    for (int a = 0; a < C; ++a) if (s.perm[a] > a) s.order[np++] = a;
     s.iscr[13] = np;
     s.cnt.flops_jacobi += 12.0 * R * np;
   }
@@ -841,9 +882,7 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C, double* table, int greedy = 0) {
   MD_PAR_FOR(t, 2 * np) {   // fresh squared norms of the rotated columns
     const int a = s.order[t >> 1];
     const int col = (t & 1) ? s.perm[a] : a;
-    double acc = 0.0;
-    for (int r = 0; r < R; ++r) { const double v = X[r * LD + col]; acc += v * v; }
-    s.vn2[col] = acc;
+    s.vn2[col] = dot4(X + col, LD, X + col, LD, R);
   }
   MD_SYNC();
   MD_LEADER { s.cnt.n_jacobi_sweeps += 1.0; }
