@@ -349,7 +349,8 @@ struct Engine {
       int ortho = 0;
       // N2 x N2 doubles the split does not read: the flat scratch matrix that is not `orig`
       double* pair_table = (orig == st.scr1) ? st.scr0 : st.scr1;
-#ifdef MD_JPROF
+#ifdef MD_JPROF   // profiling build (scripts/build_variant.sh NAME -DMD_JPROF): probe / pair search / sweeps split of this
+                  // phase, reported through the QR counters that the SVD modes leave at zero
       long long tq0 = MD_CLOCK(), tq1 = tq0, tq2 = tq0;
 #endif
       if (st.P.mode != MODE_FAST && C >= 2) {

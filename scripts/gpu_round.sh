@@ -8,6 +8,8 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/round_gputests.log 2>&1; echo "pytest exit $?" >> gpurun_out/round_gputests.log
 tail -5 gpurun_out/round_gputests.log
+# the measured agreement figures the parity section of DESIGN.md quotes
+timeout 600 python -m pytest tests/test_gpu_decode.py tests/test_gpu_mono.py -m gpu -q -s -k "depolarising_d5 or truncating_configs or headline_config or stock" 2>&1 | grep -i "deviation\|agreement\|mismatch\|max rel\|flags" | cut -c1-300 > gpurun_out/round_parity_figures.log; cat gpurun_out/round_parity_figures.log
 timeout 900 python bench.py > gpurun_out/round_bench.json 2> gpurun_out/round_bench.err; echo "bench exit $?"
 tail -c 2500 gpurun_out/round_bench.json; tail -3 gpurun_out/round_bench.err
 timeout 600 python bench.py --workload config3 --lattice 5 --chi 64 --batch 1184 --steps 2 --warmup 1 > gpurun_out/round_config3_d5_chi64.json 2>> gpurun_out/round_bench.err
