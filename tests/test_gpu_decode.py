@@ -286,10 +286,10 @@ def test_depolarising_bias_and_errors(api, mode):
 
 def test_depolarising_d5_against_reference_and_check_paths_agree(api):
     """Config-3 style workload at the size the CPU reference affords: 64 depolarising syndromes at d=5, chi_max=64
-    decoded by the unmodified reference (oracle/make_golden.py big).  Every X+Z syndrome truncates inside degenerate
-    multiplets and the reference there follows LAPACK's basis, so flags and marginals agree to the driver-to-driver
-    spread; the dense engine's two orthogonality-check routes (probe with restricted pair rotations, full Gram check)
-    follow the same canonical rule and must agree with each other closely."""
+    decoded by the unmodified reference (oracle/make_golden.py big).  Flags must be identical and the marginals close
+    (the reference's LAPACK basis inside near-degenerate multiplets is the only freedom left); the dense engine's two
+    orthogonality-check routes (probe with restricted pair rotations, full Gram check) follow the same canonical rule
+    and must agree with each other closely."""
     g = load_golden("d5_chi64_depol_64")
     kw = dict(g["kwargs"])
     code = api["surface_code"](5)
@@ -303,8 +303,10 @@ def test_depolarising_d5_against_reference_and_check_paths_agree(api):
     agree = np.mean(np.asarray(success) == np.asarray(g["success"]))
     dev = np.max(np.abs(dist - np.asarray(g["dist"])))
     print("d5 depolarising: flag agreement", agree, "max abs deviation", dev)
-    assert agree >= 0.9, agree
-    assert dev < 0.15, dev
+    # measured on B200 (profiles/r02_parity_figures.log): agreement 1.0, max abs deviation 2.2e-8 -- at this size the
+    # depolarising truncations do not cut inside exactly degenerate multiplets, so the stock reference is a sharp check
+    assert agree == 1.0, agree
+    assert dev < 1e-6, dev
     np.testing.assert_array_equal(out["svd"][1], out["svd-gram"][1])
     np.testing.assert_allclose(out["svd"][0], out["svd-gram"][0], rtol=1e-8, atol=1e-12)
 
