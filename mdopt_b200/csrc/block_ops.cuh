@@ -718,6 +718,49 @@ MD_DEV int ortho_probe(Smem<CHI>& s, int R, int C) {
   return 1;
 }
 
+#ifndef MDOPT_EMU
+// Device form of the dot-product tables of pair_fix: 8 x 8 tiles on the FP64 tensor pipe (mma.m8n8k4.f64), one tile per
+// warp task, rows la[0..na) x columns lb[0..nb) (a null list is the identity).  Lane l feeds A[m = l/4][k = l%4] =
+// X[r0 + k][la[m]] and B[k][n = l/4] = X[r0 + k][lb[n]] and receives the entries (m = l/4, n = 2 (l%4) + {0, 1}).
+// A warp load touches 4 rows x 8 columns, so a tile of 64 dot products costs R/2 load instructions instead of the
+// 128 R of 64 scalar column walks -- what matters when X is a row-major matrix in global memory.
+// row_wanted(m) (list position) lets the caller skip tiles none of whose rows is of interest; visit(m, n, value)
+// receives list positions.
+template <typename Want, typename Visit>
+__device__ __forceinline__ void md_tile_dots(const double* X, int LD, int R, const int* la, int na, const int* lb,
+                                             int nb, Want&& row_wanted, Visit&& visit) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (int)(blockDim.x >> 5);
+  const int nta = (na + 7) >> 3, ntb = (nb + 7) >> 3;
+  for (int t = warp; t < nta * ntb; t += nwarps) {
+    const int ti = t / ntb, tj = t - ti * ntb;
+    const int ma = 8 * ti + (lane >> 2);
+    if (!__any_sync(0xffffffffu, ma < na && row_wanted(ma))) continue;
+    const int ia = min(ma, na - 1), ib = min(8 * tj + (lane >> 2), nb - 1);
+    const int ca = la ? la[ia] : ia, cb = lb ? lb[ib] : ib;
+    const double* pa = X + (size_t)(lane & 3) * LD + ca;
+    const double* pb = X + (size_t)(lane & 3) * LD + cb;
+    double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
+    const int R8 = R & ~7;
+#pragma unroll 4
+    for (int r0 = 0; r0 < R8; r0 += 8) {
+      const double a0 = pa[(size_t)r0 * LD], b0 = pb[(size_t)r0 * LD];
+      const double a1 = pa[(size_t)(r0 + 4) * LD], b1 = pb[(size_t)(r0 + 4) * LD];
+      md_dmma_8x8x4(acc0, a0, b0);
+      md_dmma_8x8x4(acc1, a1, b1);
+    }
+    for (int r0 = R8; r0 < R; r0 += 4) {
+      const bool ok = r0 + (lane & 3) < R;
+      md_dmma_8x8x4(acc0, ok ? pa[(size_t)r0 * LD] : 0.0, ok ? pb[(size_t)r0 * LD] : 0.0);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int ob = 8 * tj + 2 * (lane & 3) + e;
+      if (ma < na && ob < nb) visit(ma, ob, acc0[e] + acc1[e]);
+    }
+  }
+}
+#endif
+
 // dot product of two strided vectors of length R: four independent partial sums, so that the loads of a matrix in
 // global memory are in flight together instead of one per dependent FMA
 MD_HD double dot4(const double* pa, int sa, const double* pc, int sc, int R) {
@@ -770,6 +813,16 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C, double* table, int greedy = 0) {
   // does not read); G1 is dead once its rows are scanned
   double* G1 = table;   // nf x nf: flagged x flagged
   double* G2 = table;   // nf x C : rows of the flagged columns still without a partner x unflagged columns
+#ifndef MDOPT_EMU
+  md_tile_dots(X, LD, R, s.order, nf, s.order, nf, [](int) { return true; }, [&](int i, int j, double sab) {
+    double g = 0.0;
+    if (i != j) {
+      const double saa = s.vn2[s.order[i]], scc = s.vn2[s.order[j]];
+      if (sab != 0.0 && sab * sab > tol2 * saa * scc && saa > floor2 && scc > floor2) g = sab;
+    }
+    G1[i * nf + j] = g;
+  });
+#else
   MD_PAR_FOR(t, nf * nf) {
     const int i = t / nf, j = t - i * nf;
     double g = 0.0;
@@ -781,6 +834,7 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C, double* table, int greedy = 0) {
     }
     G1[t] = g;
   }
+#endif
   MD_LEADER { s.cnt.flops_jacobi += 2.0 * R * nf * nf; }
   MD_SYNC();
   MD_PAR_FOR(i, nf) {
@@ -802,6 +856,19 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C, double* table, int greedy = 0) {
   // column's own norm, so the larger column of a very unequal pair can pass while the smaller one is flagged.  Their
   // partners are looked for among the unflagged columns; consecutive tasks walk consecutive columns c (coalesced when
   // X lives in global memory), the flagged column is the same for a run of tasks (broadcast).
+#ifndef MDOPT_EMU
+  md_tile_dots(X, LD, R, s.order, nf, nullptr, C, [&](int i) { return cand[-1 - i] == -1; },
+               [&](int i, int c, double sab) {
+    if (cand[-1 - i] == -1) {
+      double g = 0.0;
+      if (!s.flag[c]) {
+        const double saa = s.vn2[s.order[i]], scc = s.vn2[c];
+        if (sab != 0.0 && sab * sab > tol2 * saa * scc && saa > floor2 && scc > floor2) g = sab;
+      }
+      G2[i * C + c] = g;
+    }
+  });
+#else
   MD_PAR_FOR(t, nf * C) {
     const int i = t / C, c = t - i * C;
     if (cand[-1 - i] == -1) {
@@ -815,6 +882,7 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C, double* table, int greedy = 0) {
       G2[t] = g;
     }
   }
+#endif
   MD_SYNC();
   MD_PAR_FOR(i, nf) {
     if (cand[-1 - i] == -1) {
