@@ -947,10 +947,23 @@ MD_DEV int pair_fix(Smem<CHI>& s, int R, int C, double* table, int greedy = 0) {
     X[r * LD + b] = sn * xa + c * xb;
   }
   MD_SYNC();
-  MD_PAR_FOR(t, 2 * np) {   // fresh squared norms of the rotated columns
+  // fresh squared norms of the rotated columns: NCH row chunks per column, partial sums in s.part (behind the ints)
+  double* pn = s.part + N2;
+  const int rows_per = (R + NCH - 1) / NCH;
+  MD_PAR_FOR(t, 2 * np * NCH) {
+    const int ch = t % NCH, q = t / NCH;
+    const int a = s.order[q >> 1];
+    const int col = (q & 1) ? s.perm[a] : a;
+    const int r0 = ch * rows_per, r1 = (r0 + rows_per < R) ? r0 + rows_per : R;
+    pn[ch * N2 + col] = (r0 < r1) ? dot4(X + (size_t)r0 * LD + col, LD, X + (size_t)r0 * LD + col, LD, r1 - r0) : 0.0;
+  }
+  MD_SYNC();
+  MD_PAR_FOR(t, 2 * np) {
     const int a = s.order[t >> 1];
     const int col = (t & 1) ? s.perm[a] : a;
-    s.vn2[col] = dot4(X + col, LD, X + col, LD, R);
+    double acc = 0.0;
+    for (int ch = 0; ch < NCH; ++ch) acc += pn[ch * N2 + col];
+    s.vn2[col] = acc;
   }
   MD_SYNC();
   MD_LEADER { s.cnt.n_jacobi_sweeps += 1.0; }
