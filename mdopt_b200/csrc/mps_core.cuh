@@ -533,12 +533,18 @@ struct Engine {
     long long ts = MD_CLOCK();
     store_u(jn - 1, st.K, Knew);
     if (iso) {
-      if (!(pre && lay >= 3)) stage_site(jn, stage, st.Mr, Bn);   // layouts 3 / 4: already in s.P2 (prefetched)
+      // the site tensor the carried matrix absorbs next: staged (transposed in the mirrored frame) -- except on the
+      // capacities whose work matrices live in global memory anyway, where the unmirrored site is read in place
+      const double* site = stage;
+      if constexpr (!Smem<CHI>::MATS_IN_SMEM) {
+        if (!st.mirrored) site = st.sites + (size_t)phys(jn) * SITE_STRIDE;
+      }
+      if (site == stage && !(pre && lay >= 3)) stage_site(jn, stage, st.Mr, Bn);   // layouts 3 / 4: already in s.P2 (prefetched)
       MD_LEADER { s.cnt.cyc_io += (double)(MD_CLOCK() - ts); }
       long long ta = MD_CLOCK();
-      if (lay >= 3) apply_site_diag(dscale, Knew, vl, vr, st.Mr, Bn, stage, lay == 4);   // result stays in s.X (st.in_x)
+      if (lay >= 3) apply_site_diag(dscale, Knew, vl, vr, st.Mr, Bn, site, lay == 4);   // result stays in s.X (st.in_x)
       else {
-        apply_site(coef, LD, Knew, vl, vr, st.Mr, Bn, stage, st.scr0);
+        apply_site(coef, LD, Knew, vl, vr, st.Mr, Bn, site, st.scr0);
         MD_LEADER { st.in_x = 0; }
       }
       MD_LEADER { s.cnt.cyc_apply += (double)(MD_CLOCK() - ta); }
