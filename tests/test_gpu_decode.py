@@ -311,9 +311,10 @@ def test_depolarising_d5_against_reference_and_check_paths_agree(api):
     np.testing.assert_allclose(out["svd"][0], out["svd-gram"][0], rtol=1e-8, atol=1e-12)
 
 
-def test_global_memory_tier_equals_shared_memory_tier_on_depolarising(api, monkeypatch):
-    """The capacity-128 build (work matrices in global memory; portable probe, pair tables as DMMA tiles, pair rotations
-    matched by the leader, greedy rounds) must reproduce the capacity-64 build (register Jacobi path) when both are
+@pytest.mark.parametrize("capacity", [128, 256])
+def test_global_memory_tier_equals_shared_memory_tier_on_depolarising(api, monkeypatch, capacity):
+    """The capacity-128 / 256 builds (work matrices in global memory; portable probe, pair tables as DMMA tiles, pair rotations
+    matched by the leader, greedy rounds) must reproduce the capacity-64 build (register Jacobi path) when all are
     given chi_max = 64: same canonical rule, different code.  Workload: the X+Z syndromes of the d=5 depolarising
     fixture -- every one of them rotates and truncates."""
     from mdopt_b200 import _abi, engine
@@ -325,7 +326,7 @@ def test_global_memory_tier_equals_shared_memory_tier_on_depolarising(api, monke
     assert len(errors) >= 6
     small = api["decode_css_batch"](code, errors, contraction_strategy="Optimised", mode="svd", return_status=True, **kw)
     real = _abi.chi_capacity
-    monkeypatch.setattr(_abi, "chi_capacity", lambda chi: real(max(int(chi), 128)))
+    monkeypatch.setattr(_abi, "chi_capacity", lambda chi: real(max(int(chi), capacity)))
     engine.clear_engines()
     try:
         big = api["decode_css_batch"](code, errors, contraction_strategy="Optimised", mode="svd", return_status=True, **kw)
@@ -333,7 +334,7 @@ def test_global_memory_tier_equals_shared_memory_tier_on_depolarising(api, monke
     finally:
         monkeypatch.undo()
         engine.clear_engines()
-    assert caps == {128}
+    assert caps == {capacity}
     assert (small[2] == 0).all() and (big[2] == 0).all()
     np.testing.assert_array_equal(small[1], big[1])
     np.testing.assert_allclose(big[0], small[0], rtol=1e-8, atol=1e-12)
