@@ -1762,6 +1762,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       const int a = grp + it * NGRP;
       const int b = (a < C) ? s.perm[a] : -1;
       const bool valid = (b > a);
+      if (!__any_sync(0xffffffffu, valid)) continue;   // none of the warp's four groups holds a pair
       double xa[RPT], xb[RPT];
       double saa, sbb, sab;
       pair_dots(a, b, valid, xa, xb, saa, sbb, sab);
