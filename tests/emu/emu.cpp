@@ -124,6 +124,37 @@ int svd_impl(int m, int n, const double* a, int chi_max, double cut, double* u, 
   return bad;
 }
 
+// The split of the SVD modes on the portable tier, as Engine::factor runs it: orthogonality probe; one round of
+// disjoint pair rotations; greedy rounds, each followed by the probe; cyclic sweeps.  Returns the route taken
+// (0 orthogonal, 1 single pair round, 2 greedy rounds, 3 cyclic sweeps), X J in xout (m x n) and the ranking.
+template <int CHI>
+int split_impl(int m, int n, const double* a, double* xout, int* order, double* sig) {
+  Smem<CHI>* sm = new Smem<CHI>();
+  Smem<CHI>& s = *sm;
+  constexpr int LD = Smem<CHI>::LD;
+  constexpr int N2 = Smem<CHI>::N2;
+  std::vector<double> table((size_t)N2 * N2);
+  for (int i = 0; i < m; ++i) for (int c = 0; c < n; ++c) s.X[i * LD + c] = a[i * n + c];
+  int route = 0;
+  if (!ortho_probe<CHI>(s, m, n)) {
+    if (pair_fix<CHI>(s, m, n, table.data())) route = 1;
+    else {
+      int settled = 0;
+      for (int it = 0; it < 12 && !settled; ++it) {
+        if (!pair_fix<CHI>(s, m, n, table.data(), 1)) break;
+        settled = ortho_probe<CHI>(s, m, n);
+      }
+      route = settled ? 2 : 3;
+      if (!settled) jacobi_columns<CHI>(s, m, n);
+    }
+  }
+  for (int i = 0; i < m; ++i) for (int c = 0; c < n; ++c) xout[i * n + c] = s.X[i * LD + c];
+  for (int c = 0; c < n; ++c) { order[c] = s.order[c]; sig[c] = s.sig[c]; }
+  if (s.iscr[5]) route = -1;
+  delete sm;
+  return route;
+}
+
 // QRCP + form Q: returns K; q (m x K, ld kcap), coeff (K x n, ld n)
 template <int CHI>
 int qr_impl(int m, int n, const double* a, int kmax, double rel_tol, double* q, double* coeff, int* more) {
@@ -227,6 +258,15 @@ int emu_svd(int chi_cap, int m, int n, const double* a, int chi_max, double cut,
     case 64: return svd_impl<64>(m, n, a, chi_max, cut, u, sv, vh, kept);
   }
   return -2;
+}
+int emu_split(int chi_cap, int m, int n, const double* a, double* xout, int* order, double* sig) {
+  switch (chi_cap) {
+    case 8: return split_impl<8>(m, n, a, xout, order, sig);
+    case 16: return split_impl<16>(m, n, a, xout, order, sig);
+    case 32: return split_impl<32>(m, n, a, xout, order, sig);
+    case 64: return split_impl<64>(m, n, a, xout, order, sig);
+    default: return -2;
+  }
 }
 int emu_qr(int chi_cap, int m, int n, const double* a, int kmax, double rel_tol, double* q, double* coeff, int* more) {
   switch (chi_cap) {

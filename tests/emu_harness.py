@@ -106,6 +106,19 @@ def svd(a, chi_max, cut):
     return u, s, vh, kept.value, bad
 
 
+def split(a):
+    """The SVD-mode split of the portable tier on one matrix: (route, X J, order, sigma); routes: 0 orthogonal columns,
+    1 one round of disjoint pair rotations, 2 greedy rounds, 3 cyclic sweeps."""
+    a = np.ascontiguousarray(a, dtype=float)
+    m, n = a.shape
+    cap = _abi.chi_capacity((max(m, n) + 1) // 2)
+    x = np.zeros((m, n))
+    order = np.zeros(n, dtype=np.int32)
+    sig = np.zeros(n)
+    route = lib().emu_split(cap, m, n, _ptr(a), _ptr(x), _ptr(order), _ptr(sig))
+    return route, x, order, sig
+
+
 def qr(a, kmax, rel_tol=1e-14):
     a = np.ascontiguousarray(a, dtype=float)
     m, n = a.shape

@@ -339,3 +339,81 @@ def test_dense_engine_uses_the_canonical_tie_break(mode):
     ref, ok = np.array(g["dist"])[idx], np.array(g["success"])[idx]
     assert (st == 0).all() and (s == ok).all()
     assert (np.abs(d - ref).max(axis=1) / ref.max(axis=1)).max() < 1e-10
+
+
+def _orthogonal_columns(rng, m, n, scales):
+    q, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    return q * np.asarray(scales)[None, :]
+
+
+def _check_split(a, x, order, sig):
+    """X = A J with J orthogonal and mutually orthogonal columns: same Gram operator from the left, orthogonal columns,
+    column norms = the singular values of A in the reported order."""
+    np.testing.assert_allclose(x @ x.T, a @ a.T, rtol=0, atol=1e-12 * np.linalg.norm(a) ** 2)
+    norms = np.linalg.norm(x, axis=0)
+    gram = x.T @ x
+    big = norms > 1e-12 * norms.max()
+    cos = gram[np.ix_(big, big)] / np.outer(norms[big], norms[big])
+    assert np.max(np.abs(cos - np.eye(big.sum()))) < 1e-11
+    np.testing.assert_allclose(sig[order], norms[order], rtol=1e-12, atol=1e-300)
+    sv = np.linalg.svd(a, compute_uv=False)
+    got = sig[order][:len(sv)]
+    keep = sv > 1e-9 * sv[0]
+    np.testing.assert_allclose(got[keep], sv[keep], rtol=1e-10)
+    assert np.all(np.diff(got) <= 1e-10 * got[0])
+
+
+def test_split_routes_of_the_portable_tier():
+    """The split of the SVD modes, route by route (block_ops.cuh: ortho_probe, pair_fix, jacobi_columns):
+    orthogonal columns pass the probe; disjoint non-orthogonal pairs -- also very unequal ones, whose larger column
+    the probe does not flag -- take one round of pair rotations; a cluster of three takes the greedy rounds or the
+    sweeps; a random dense matrix takes the cyclic sweeps.  Every route must deliver the singular values."""
+    rng = np.random.default_rng(2024)
+    m = n = 32
+    scales = np.exp(rng.uniform(-6, 0, n))
+    base = _orthogonal_columns(rng, m, n, scales)
+
+    route, x, order, sig = H.split(base)
+    assert route == 0
+    _check_split(base, x, order, sig)
+
+    pairs = base.copy()
+    for a, b, w in ((1, 7, 0.4), (3, 20, -1.3), (10, 11, 0.05), (30, 2, 2.0)):
+        pairs[:, b] += w * pairs[:, a] * (scales[b] / scales[a])
+    route, x, order, sig = H.split(pairs)
+    assert route == 1, route
+    _check_split(pairs, x, order, sig)
+
+    unequal = _orthogonal_columns(rng, m, n, np.where(np.arange(n) == 5, 1e-7, 1.0))
+    unequal[:, 5] += 3e-8 * unequal[:, 9]        # the small column leans on a large one: only the small one is flagged
+    route, x, order, sig = H.split(unequal)
+    assert route == 1, route
+    _check_split(unequal, x, order, sig)
+
+    cluster = base.copy()
+    cluster[:, 4] += 0.5 * cluster[:, 8] * (scales[4] / scales[8])
+    cluster[:, 12] += 0.7 * cluster[:, 8] * (scales[12] / scales[8])
+    route, x, order, sig = H.split(cluster)
+    assert route in (2, 3), route
+    _check_split(cluster, x, order, sig)
+
+    dense = rng.standard_normal((m, n))
+    route, x, order, sig = H.split(dense)
+    assert route in (2, 3), route
+    _check_split(dense, x, order, sig)
+
+
+def test_split_pairs_every_column():
+    """More than half of the columns flagged -- every column has a partner, as behind a two-site bias gate: still one
+    round of pair rotations (the candidate tables live in the flat scratch matrix, so their size is not a limit)."""
+    rng = np.random.default_rng(77)
+    m = n = 64
+    scales = np.exp(rng.uniform(-3, 0, n))
+    a = _orthogonal_columns(rng, m, n, scales)
+    perm = rng.permutation(n)
+    for k in range(0, n, 2):
+        p, q = perm[k], perm[k + 1]
+        a[:, q] += rng.uniform(0.2, 1.5) * a[:, p] * (scales[q] / scales[p])
+    route, x, order, sig = H.split(a)
+    assert route == 1, route
+    _check_split(a, x, order, sig)
