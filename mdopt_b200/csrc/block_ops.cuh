@@ -1654,7 +1654,9 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
             const double saa = s.vn2[ca], sbb = s.vn2[cb], sab = g[u][v];
             if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) {
               bad = 1;
-              if (record) {   // remember the offending pair; a column with two different partners breaks the matching
+              // remember the offending pair; a column with two different partners breaks the matching -- and once it
+              // is broken nothing more needs recording (a dense matrix would queue thousands of atomics here)
+              if (record && *(volatile int*)&s.iscr[12] == 0) {
                 const int o1 = atomicCAS(&s.perm[ca], -1, cb);
                 const int o2 = atomicCAS(&s.perm[cb], -1, ca);
                 if ((o1 != -1 && o1 != cb) || (o2 != -1 && o2 != ca)) s.iscr[12] = 1;
@@ -1813,6 +1815,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
       const double saa = s.vn2[a], sbb = s.vn2[b];   // squared norms from the probe's second pass
       if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) {
         found = 1;
+        if (*(volatile int*)&s.iscr[12]) return;   // the matching is already broken: nothing more to record
         const int o1 = atomicCAS(&s.perm[a], -1, b);
         const int o2 = atomicCAS(&s.perm[b], -1, a);
         if ((o1 != -1 && o1 != b) || (o2 != -1 && o2 != a)) s.iscr[12] = 1;
@@ -1846,6 +1849,7 @@ __device__ __noinline__ void jacobi_columns_dev(Smem<CHI>& s, int R, int C, int 
         const double saa = s.vn2[a], sbb = s.vn2[b];
         if (sab != 0.0 && sab * sab > tol2 * saa * sbb && saa > floor2 && sbb > floor2) {
           found2 = 1;
+          if (*(volatile int*)&s.iscr[12]) return;
           const int o1 = atomicCAS(&s.perm[a], -1, b);
           const int o2 = atomicCAS(&s.perm[b], -1, a);
           if ((o1 != -1 && o1 != b) || (o2 != -1 && o2 != a)) s.iscr[12] = 1;

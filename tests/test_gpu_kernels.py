@@ -381,3 +381,46 @@ def test_compress_on_gpu(torch_mod):
         right.compress_bond(n - 1)
     with pytest.raises(ValueError):
         right.compress(strategy="lu")
+
+
+@pytest.mark.gpu
+def test_svd_kernel_split_routes():
+    """`svd` / `split_two_site_tensor` (svd_kernel, cyclic one-sided Jacobi) on the matrix shapes the decode produces and
+    on a dense one: orthogonal columns spanning six decades, disjoint non-orthogonal pairs -- equal, very unequal,
+    every column --, a cluster of three, random dense.  Singular values against LAPACK, reconstruction, orthonormal
+    factors.  (The probe / pair-rotation routes of the decode's own splits are covered by the d=5 depolarising tests
+    in test_gpu_decode.py and, route by route, by the host build in test_emu_engine.py.)"""
+    from mdopt_b200.utils import svd_batch
+
+    rng = np.random.default_rng(2024)
+    m = n = 64
+
+    def ortho(scales):
+        q, _ = np.linalg.qr(rng.standard_normal((m, n)))
+        return q * np.asarray(scales)[None, :]
+
+    scales = np.exp(rng.uniform(-6, 0, n))
+    base = ortho(scales)
+    pairs = base.copy()
+    for a, b, w in ((1, 7, 0.4), (3, 20, -1.3), (10, 11, 0.05), (30, 2, 2.0), (40, 63, 0.8)):
+        pairs[:, b] += w * pairs[:, a] * (scales[b] / scales[a])
+    unequal = ortho(np.where(np.arange(n) == 5, 1e-7, 1.0))
+    unequal[:, 5] += 3e-8 * unequal[:, 9]
+    every = ortho(np.exp(rng.uniform(-3, 0, n)))
+    perm = rng.permutation(n)
+    for k in range(0, n, 2):
+        every[:, perm[k + 1]] += rng.uniform(0.2, 1.5) * every[:, perm[k]]
+    cluster = base.copy()
+    cluster[:, 4] += 0.5 * cluster[:, 8] * (scales[4] / scales[8])
+    cluster[:, 12] += 0.7 * cluster[:, 8] * (scales[12] / scales[8])
+    dense = rng.standard_normal((m, n))
+    mats = np.stack([base, pairs, unequal, every, cluster, dense])
+    u, s, vh, kept, trunc, status = svd_batch(mats, cut=0.0, chi_max=n)
+    assert (status == 0).all()
+    for i, a in enumerate(mats):
+        sv = np.linalg.svd(a, compute_uv=False)
+        k = int(kept[i])
+        big = sv > 1e-9 * sv[0]
+        np.testing.assert_allclose(s[i][:len(sv)][big], sv[big], rtol=1e-10, err_msg=f"matrix {i}")
+        np.testing.assert_allclose((u[i][:, :k] * s[i][:k]) @ vh[i][:k], a, atol=1e-12 * sv[0], err_msg=f"matrix {i}")
+        np.testing.assert_allclose(u[i][:, :k].T @ u[i][:, :k], np.eye(k), atol=1e-10, err_msg=f"matrix {i}")
